@@ -1,0 +1,49 @@
+"""ctypes binding of libvglamm.so (C ABI declared in include/vglamm.h).
+
+The product path has NO fallback: if the library is missing or a call fails, a RuntimeError is raised."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libvglamm.so"
+_lib = None
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_GELU, ACT_QUICKGELU, ACT_RELU, ACT_SILU, ACT_SIGMOID = range(6)
+ACT = {None: ACT_NONE, "none": ACT_NONE, "gelu": ACT_GELU, "quick_gelu": ACT_QUICKGELU, "relu": ACT_RELU,
+       "silu": ACT_SILU, "sigmoid": ACT_SIGMOID}
+
+
+class VgGemm(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_longlong), ("strideA", C.c_longlong),
+        ("B", C.c_void_p), ("ldb", C.c_longlong), ("strideB", C.c_longlong),
+        ("C", C.c_void_p), ("ldc", C.c_longlong), ("strideC", C.c_longlong),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
+        ("out_dtype", C.c_int),
+        ("bias", C.c_void_p),
+        ("act", C.c_int), ("glu", C.c_int),
+        ("col_scale", C.c_void_p),
+        ("resid", C.c_void_p), ("ldr", C.c_longlong), ("strideR", C.c_longlong), ("resid_dtype", C.c_int),
+        ("alpha", C.c_float),
+        ("force_block_n", C.c_int),
+    ]
+
+
+def lib() -> C.CDLL:
+    """Load libvglamm.so (built in-tree by videoglamm_b200.build). Raises if it is absent."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(f"{_LIB_PATH} not built: run `python -m videoglamm_b200.build` (no CPU fallback exists)")
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.vg_last_error.restype = C.c_char_p
+        _lib.vg_launch_count.restype = C.c_longlong
+        _lib.vg_launch_count_reset.restype = None
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed ({rc}): {lib().vg_last_error().decode()}")

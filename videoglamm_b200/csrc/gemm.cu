@@ -1,0 +1,478 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:
+//   warp 0 (1 lane)  TMA producer      global --cp.async.bulk.tensor (SWIZZLE_128B)--> smem ring
+//   warp 1 (1 lane)  MMA issuer        tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM (double-buffered)
+//   warp 2           TMEM allocator
+//   warps 4..7       epilogue          tcgen05.ld -> bias/act/GLU/scale/residual -> global
+// C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (nn.Linear layout). See include/vglamm.h for the contract.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 128/256/512 are powers of two
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K, batch;
+  int tiles_m, tiles_n;
+  void* C;
+  long long ldc, strideC;
+  int out_f32;
+  const float* bias;
+  int act, glu;
+  const float* col_scale;
+  const void* resid;
+  long long ldr, strideR;
+  int resid_f32;
+  float alpha;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case VG_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case VG_ACT_QUICKGELU: return x / (1.0f + __expf(-1.702f * x));
+    case VG_ACT_RELU: return fmaxf(x, 0.0f);
+    case VG_ACT_SILU: return x / (1.0f + __expf(-x));
+    case VG_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
+    default: return x;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int total_tiles = tiles_per_batch * p.batch;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_batch;
+        const int r = t - b * tiles_per_batch;
+        const int n_blk = r / p.tiles_m;
+        const int m_blk = r - n_blk * p.tiles_m;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_3d(&tmA, &full_bar[stage], sA + stage * Cfg::A_BYTES, kb * BLOCK_K, m_blk * BLOCK_M, b);
+          tma_load_3d(&tmB, &full_bar[stage], sB + stage * Cfg::B_BYTES, kb * BLOCK_K, n_blk * BN, b);
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(sA + stage * Cfg::A_BYTES));
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == Cfg::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue: TMEM -> regs -> global
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_out = p.glu ? p.N / 2 : p.N;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_batch;
+      const int r = t - b * tiles_per_batch;
+      const int n_blk = r / p.tiles_m;
+      const int m_blk = r - n_blk * p.tiles_m;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n_blk * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t raw[32];
+        tmem_ld32(taddr + c * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+        }
+        int ocol0, nvals;
+        if (p.glu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act) * v[16 + j];
+          ocol0 = col0 >> 1;
+          nvals = 16;
+        } else {
+          if (p.act != VG_ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          ocol0 = col0;
+          nvals = 32;
+        }
+        if (p.col_scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvals && ocol0 + j < n_out) v[j] *= __ldg(p.col_scale + ocol0 + j);
+        }
+        if (row_ok) {
+          const int nvalid = min(nvals, n_out - ocol0);
+          if (p.resid != nullptr) {
+            if (p.resid_f32) {
+              const float* rp = reinterpret_cast<const float*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += rp[j];
+            } else {
+              const __nv_bfloat16* rp =
+                  reinterpret_cast<const __nv_bfloat16*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (p.out_f32) {
+            float* cp = reinterpret_cast<float*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
+            if (nvalid == nvals && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (j < nvals) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) cp[j] = v[j];
+            }
+          } else {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
+            if (nvalid == nvals && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                if (j < nvals)
+                  *reinterpret_cast<uint4*>(cp + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                                 pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) cp[j] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- naive reference
+__global__ void gemm_naive_kernel(const __nv_bfloat16* A, long long lda, long long sA, const __nv_bfloat16* B, long long ldb,
+                                  long long sB, GemmParams p) {
+  const int n_out = p.glu ? p.N / 2 : p.N;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long per_batch = static_cast<long long>(p.M) * n_out;
+  if (idx >= per_batch * p.batch) return;
+  const int b = static_cast<int>(idx / per_batch);
+  const long long r = idx - b * per_batch;
+  const int m = static_cast<int>(r / n_out);
+  const int oc = static_cast<int>(r - static_cast<long long>(m) * n_out);
+  auto dot = [&](int n) {
+    const __nv_bfloat16* a = A + b * sA + static_cast<long long>(m) * lda;
+    const __nv_bfloat16* w = B + b * sB + static_cast<long long>(n) * ldb;
+    float acc = 0.f;
+    for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(w[k]), acc);
+    acc *= p.alpha;
+    if (p.bias) acc += p.bias[n];
+    return acc;
+  };
+  float v;
+  if (p.glu) {
+    const int blk = oc / 16, j = oc % 16;
+    v = apply_act(dot(blk * 32 + j), p.act) * dot(blk * 32 + 16 + j);
+  } else {
+    v = apply_act(dot(oc), p.act);
+  }
+  if (p.col_scale) v *= p.col_scale[oc];
+  if (p.resid) {
+    const long long off = b * p.strideR + static_cast<long long>(m) * p.ldr + oc;
+    v += p.resid_f32 ? reinterpret_cast<const float*>(p.resid)[off] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[off]);
+  }
+  const long long off = b * p.strideC + static_cast<long long>(m) * p.ldc + oc;
+  if (p.out_f32)
+    reinterpret_cast<float*>(p.C)[off] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr;
+  long long ld, stride;
+  int rows, cols, batch, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && ld == o.ld && stride == o.stride && rows == o.rows && cols == o.cols && batch == o.batch &&
+           box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    auto mix = [&](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(static_cast<size_t>(k.ld));
+    mix(static_cast<size_t>(k.stride));
+    mix(static_cast<size_t>(k.rows));
+    mix(static_cast<size_t>(k.cols));
+    mix(static_cast<size_t>(k.batch));
+    mix(static_cast<size_t>(k.box_rows));
+    return h;
+  }
+};
+
+// bf16 [batch][rows][ld] (cols valid per row) -> 3D tiled map with box {64, box_rows, 1}, 128B swizzle, zero OOB fill.
+static int make_map(CUtensorMap* out, const void* ptr, int rows, int cols, int batch, long long ld, long long stride, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{ptr, ld, stride, rows, cols, batch, box_rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return VG_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(batch > 1 ? stride : static_cast<long long>(rows) * ld) * 2};
+  cuuint32_t box[3] = {BLOCK_K, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled failed (%d): rows=%d cols=%d ld=%lld", (int)r, rows, cols, ld);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return VG_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int check_gemm(const VgGemm* g) {
+  if (!g || !g->A || !g->B || !g->C) return set_error(VG_EINVAL, "vg_gemm: null pointer");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0 || g->batch <= 0) return set_error(VG_EINVAL, "vg_gemm: non-positive dimension");
+  if (g->glu && (g->N % 32) != 0) return set_error(VG_EINVAL, "vg_gemm: glu needs N %% 32 == 0");
+  if (g->resid && g->ldr <= 0) return set_error(VG_EINVAL, "vg_gemm: residual needs ldr");
+  return VG_OK;
+}
+
+static GemmParams to_params(const VgGemm* g) {
+  GemmParams p;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.batch = g->batch;
+  p.tiles_m = 0; p.tiles_n = 0;
+  p.C = g->C; p.ldc = g->ldc; p.strideC = g->strideC;
+  p.out_f32 = g->out_dtype == VG_F32;
+  p.bias = g->bias; p.act = g->act; p.glu = g->glu; p.col_scale = g->col_scale;
+  p.resid = g->resid; p.ldr = g->ldr; p.strideR = g->strideR; p.resid_f32 = g->resid_dtype == VG_F32;
+  p.alpha = g->alpha;
+  return p;
+}
+
+template <int BN>
+static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(VG_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g->A, g->M, g->K, g->batch, g->lda, g->strideA, BLOCK_M);
+  if (rc) return rc;
+  rc = make_map(&tmB, g->B, g->N, g->K, g->batch, g->ldb, g->strideB, BN);
+  if (rc) return rc;
+  GemmParams p = to_params(g);
+  p.tiles_m = (g->M + BLOCK_M - 1) / BLOCK_M;
+  p.tiles_n = (g->N + BN - 1) / BN;
+  const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * g->batch;
+  const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  count_launch();
+  return check_launch("gemm_tcgen05_kernel");
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_gemm(const VgGemm* g, void* stream) {
+  int rc = check_gemm(g);
+  if (rc) return rc;
+  if ((g->lda % 8) || (g->ldb % 8) || (reinterpret_cast<uintptr_t>(g->A) & 15) || (reinterpret_cast<uintptr_t>(g->B) & 15) ||
+      (g->batch > 1 && ((g->strideA % 8) || (g->strideB % 8))))
+    return set_error(VG_EINVAL, "vg_gemm: A/B must be 16B aligned with lda/ldb/strides multiples of 8 (lda=%lld ldb=%lld)", g->lda, g->ldb);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int bn = g->force_block_n;
+  if (bn == 0) {
+    const long long tm = (g->M + BLOCK_M - 1) / BLOCK_M;
+    const long long t256 = tm * ((g->N + 255) / 256) * g->batch;
+    const long long t128 = tm * ((g->N + 127) / 128) * g->batch;
+    if (g->N > 128 && t256 >= num_sms())
+      bn = 256;
+    else if (g->N > 64 && t128 >= num_sms() / 2)
+      bn = 128;
+    else
+      bn = (g->N > 64 && g->N % 128 == 0 && t128 * 2 > num_sms()) ? 128 : 64;
+  }
+  switch (bn) {
+    case 256: return launch_gemm<256>(g, s);
+    case 128: return launch_gemm<128>(g, s);
+    case 64: return launch_gemm<64>(g, s);
+    default: return set_error(VG_EINVAL, "vg_gemm: force_block_n must be 0/64/128/256");
+  }
+}
+
+extern "C" int vg_gemm_naive(const VgGemm* g, void* stream) {
+  int rc = check_gemm(g);
+  if (rc) return rc;
+  GemmParams p = to_params(g);
+  const int n_out = g->glu ? g->N / 2 : g->N;
+  const long long total = static_cast<long long>(g->M) * n_out * g->batch;
+  const int threads = 256;
+  const long long blocks = (total + threads - 1) / threads;
+  gemm_naive_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(g->A), g->lda, g->strideA, reinterpret_cast<const __nv_bfloat16*>(g->B), g->ldb,
+      g->strideB, p);
+  count_launch();
+  return check_launch("gemm_naive_kernel");
+}
