@@ -70,6 +70,82 @@ int vg_gemm(const VgGemm* g, void* stream);
 /* Same contract, one thread per output element, fp32 accumulate in k order. Test/diagnostic reference ON DEVICE. */
 int vg_gemm_naive(const VgGemm* g, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ attention
+ * O = softmax(scale * Q K^T + mask) V, flash style (scores never materialised), bf16 in/out, fp32 softmax.
+ * Element (b,h,row,d) of X lives at X + b*x_bs + h*x_hs + row*x_rs + d, so a packed [tokens, 3*H*D] qkv GEMM output
+ * is consumed in place. causal: query i sees keys j <= i + (Nk-Nq). window>0 additionally requires
+ * j >= i + (Nk-Nq) - window (transformers 4.41 Phi-3 sliding-window rule).
+ * 2D window addressing (Hiera): if *_win > 0 the batch index enumerates (image, window_y, window_x) and token t of a
+ * window maps to row img*(nwy*win*gridw) + (wy*win + t/win)*gridw + wx*win + t%win of the un-partitioned token grid
+ * (replaces window_partition/unpartition copies, .../sam2/modeling/backbones/utils.py:16-62); *_bs is ignored then.
+ * Replaces F.scaled_dot_product_attention at .../backbones/hieradet.py:72-76, .../sam/transformer.py:249-255,316-322,
+ * InternVideo2 _naive_attn (internvideo2.py:190-209), HF CLIP / Phi-3 attention (called from clip_encoder.py:45-72, phi3.py:72-81).
+ * Requirements: D % 8 == 0, D <= 256; q/k/v strides multiples of 8 elements, 16-byte aligned bases.
+ */
+typedef struct VgAttention {
+  const void *q, *k, *v; void* o;
+  long long q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
+  int B, H, Nq, Nk, D;
+  float scale;
+  int causal, window;
+  int q_win, q_gridw, q_nwx, q_nwy;
+  int k_win, k_gridw, k_nwx, k_nwy;
+} VgAttention;
+int vg_attention(const VgAttention* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ normalisation
+ * Row-wise LayerNorm (rms=0: (x-mean)/sqrt(var+eps)*w+b) or RMSNorm (rms=1: x/sqrt(mean(x^2)+eps)*w), fp32 statistics.
+ * x: [rows][ldx] (x_dtype), y: [rows][ldy] (y_dtype). LayerNorm2d on channels-last tensors is the same operation.
+ * Replaces nn.LayerNorm / LayerNorm2d (.../sam2/modeling/sam2_utils.py:137-149), InternVideo2 RMSNorm (internvideo2.py:134-145),
+ * HF Phi3RMSNorm. b may be NULL.
+ */
+int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, const float* w, const float* b,
+            int rows, int cols, float eps, int rms, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ elementwise / layout
+ * out[r][c] = a[r][c] + alpha * b[r % b_rows][c]   (b NULL: plain dtype cast). Row strides in elements.
+ * Covers q = queries + query_pe / k = keys + key_pe (.../sam/transformer.py:160-193), + pos_embed, + no_mem_embed
+ * (.../sam2_base.py:641-645), curr + 0.1*curr_pos (.../memory_attention.py:140-141).
+ */
+int vg_add(const void* a, int a_dtype, long long lda, const void* b, int b_dtype, long long ldb, int b_rows, float alpha,
+           void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
+/* 2x2 max (is_max=1; Hiera q-pool, hieradet.py:21-33) or mean (is_max=0; arch.py:88-96 adaptive pooling by 2) over a
+ * channels-last [n][h][w][c] grid; row stride of the input in elements (reads a column slice of a wider tensor). */
+int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int n, int h, int w, int c, int is_max,
+               void* stream);
+/* out[n][2y+dy][2x+dx][c] = lat[n][2y+dy][2x+dx][c] + top[n][y][x][c]  (FPN nearest top-down, image_encoder.py:115-126); fp32 */
+int vg_upsample2x_add(const float* lat, const float* top, float* out, int n, int h, int w, int c, void* stream);
+/* ConvTranspose2d(k=2,s=2) epilogue after the [n*h*w, 4*cout] GEMM (columns ordered (dy,dx,co)): pixel-shuffle, + bias[co],
+ * + feat[n][2h][2w][cout] (may be NULL), optional LayerNorm2d(ln_w, ln_b, eps) then GELU. (mask_decoder.py:221-225) */
+int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bias, const void* feat, int feat_dtype, const float* ln_w,
+                         const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, void* stream);
+/* im2col for Conv2d(kernel k, stride s, pad p) on NCHW fp32/bf16 input -> bf16 [n*oh*ow][kpad], column order (ci,ky,kx),
+ * zero-filled to kpad (multiple of 8). Patch embeddings: Hiera 7x7/4 (backbones/utils.py:65-95), CLIP 14x14/14, IV2 1x14x14. */
+int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
+              void* stream);
+/* Depthwise KxK conv, stride 1, pad K/2, channels-last [n][h][w][c]; weight [c][K][K] fp32 (CXBlock.dwconv, memory_encoder.py:62-118). */
+int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, void* y, int y_dtype, int n, int h, int wd, int c, int k,
+              void* stream);
+/* Conv2d 3x3 stride 2 pad 1, channels-last, weights [ (ky,kx,ci) ][cout] fp32, + bias, then LayerNorm2d + GELU
+ * (MaskDownSampler stage, memory_encoder.py:17-58). x: [n][h][w][cin] -> y: [n][h/2][w/2][cout]. */
+int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
+                         void* y, int y_dtype, int n, int h, int wd, int cin, int cout, void* stream);
+/* Bilinear resize (align_corners=False, no antialias) of fp32 planes [n][ih][iw] -> [n][oh][ow] with a fused output map:
+ * mode 0: identity; 1: sigmoid(x)*scale+bias; 2: (x>0)*scale+bias (sam2_base.py:366-374, 687-697; sam2_video_predictor.py:498-518);
+ * mode 3: write uint8 (x > 0) instead of fp32 (VideoGLaMM.py:870-875). */
+int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream);
+/* 2D axial RoPE on rows of a [rows][ld] bf16 tensor, in place: row r has grid position (r % gw, (r / gw) % gh); the first
+ * dim/2 features rotate with x, the rest with y, consecutive (even,odd) pairs are one complex number
+ * (position_encoding.py:174-216). Rows [0, nrows). theta 10000. */
+int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* stream);
+/* Phi-3 / Llama rotate-half RoPE in place on q and k slices of a packed qkv tensor [rows][ld] (bf16): for each head, pairs (i, i+hd/2).
+ * pos[r] is the position of row r. */
+int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream);
+/* out[r][:] = table[ids[r]][:] (nn.Embedding), bf16 table -> out dtype */
+int vg_embedding(const void* table, long long ldt, const long long* ids, void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
+/* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
+int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,249 @@
+"""Kernel-level parity: every C-ABI op vs a plain torch fp32 reference of the same op on the same (bf16-rounded) inputs.
+Tolerances: fp32-output ops are compared at 1e-5 relative L2 (only accumulation order differs); bf16-output ops at 4e-3
+(one bf16 rounding of the result, 2^-9 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from videoglamm_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(autouse=True)
+def _seed():
+    torch.manual_seed(0)
+    torch.backends.cudnn.allow_tf32 = False  # the torch reference must be true fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 64, 64, 64), (128, 256, 64, 256), (300, 200, 136, 0), (77, 40, 72, 64),
+                                      (1000, 1000, 1000, 256), (9, 256, 256, 0), (1664, 9216, 3072, 0), (1, 32064, 3072, 0), (4096, 4, 32, 0)])
+def test_gemm_plain(M, N, K, bn):
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    y = ops.gemm(a, w, out_dtype=torch.float32, force_block_n=bn)
+    assert rel(y, a.float() @ w.float().T) < 1e-5
+
+
+@pytest.mark.parametrize("act", ["gelu", "quick_gelu", "relu", "silu", "sigmoid"])
+def test_gemm_bias_act(act):
+    a = torch.randn(256, 256, device=DEV).bfloat16()
+    w = (torch.randn(384, 256, device=DEV) / 16).bfloat16()
+    bias = torch.randn(384, device=DEV)
+    f = dict(gelu=F.gelu, quick_gelu=lambda x: x * torch.sigmoid(1.702 * x), relu=torch.relu, silu=F.silu, sigmoid=torch.sigmoid)[act]
+    y = ops.gemm(a, w, bias=bias, act=act, out_dtype=torch.float32)
+    assert rel(y, f(a.float() @ w.float().T + bias)) < 1e-5
+
+
+def test_gemm_glu_scale_resid_batched():
+    a = torch.randn(256, 256, device=DEV).bfloat16()
+    w = (torch.randn(512, 256, device=DEV) / 16).bfloat16()
+    y = ops.gemm(a, w, glu=True, act="silu", out_dtype=torch.float32)
+    r = (a.float() @ w.float().T).reshape(256, -1, 2, 16)
+    assert rel(y, (F.silu(r[:, :, 0]) * r[:, :, 1]).reshape(256, -1)) < 1e-5
+    bias, cs, res = torch.randn(512, device=DEV), torch.randn(512, device=DEV), torch.randn(256, 512, device=DEV)
+    y = ops.gemm(a, w, bias=bias, col_scale=cs, resid=res, out=res.clone())
+    assert rel(y, (a.float() @ w.float().T + bias) * cs + res) < 1e-5
+    ab = torch.randn(5, 200, 64, device=DEV).bfloat16()
+    wb = torch.randn(5, 96, 64, device=DEV).bfloat16()
+    assert rel(ops.gemm(ab, wb, out_dtype=torch.float32), ab.float() @ wb.float().transpose(1, 2)) < 1e-5
+    yb = ops.gemm(a, w, out_dtype=torch.bfloat16)
+    assert rel(yb, a.float() @ w.float().T) < 4e-3
+
+
+def test_gemm_matches_naive_device_reference():
+    a = torch.randn(333, 200, device=DEV).bfloat16()
+    w = torch.randn(129, 200, device=DEV).bfloat16()
+    assert rel(ops.gemm(a, w, out_dtype=torch.float32), ops.gemm(a, w, out_dtype=torch.float32, naive=True)) < 1e-5
+
+
+def test_gemm_rejects_bad_alignment():
+    a = torch.randn(16, 20, device=DEV).bfloat16()[:, :12]  # lda=20 not a multiple of 8
+    w = torch.randn(8, 12, device=DEV).bfloat16()
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w)
+
+
+def sdpa_ref(q, k, v, scale, causal=False, window=0):
+    q, k, v = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    s = q @ k.transpose(-1, -2) * scale
+    Nq, Nk = s.shape[-2:]
+    i = torch.arange(Nq, device=s.device)[:, None] + (Nk - Nq)
+    j = torch.arange(Nk, device=s.device)[None]
+    mask = torch.ones(Nq, Nk, dtype=torch.bool, device=s.device)
+    if causal:
+        mask &= j <= i
+    if window:
+        mask &= j >= i - window
+    s = s.masked_fill(~mask, float("-inf"))
+    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,D,causal,window", [
+    (2, 4, 64, 64, 64, False, 0), (1, 16, 577, 577, 64, False, 0), (1, 16, 1025, 1025, 88, False, 0), (1, 8, 300, 300, 72, False, 0),
+    (1, 32, 333, 333, 96, True, 0), (1, 4, 1, 500, 96, True, 0), (1, 4, 700, 700, 96, True, 128), (2, 1, 256, 1100, 256, False, 0),
+    (3, 8, 9, 4096, 16, False, 0), (3, 8, 4096, 9, 16, False, 0), (2, 8, 9, 9, 32, False, 0), (1, 2, 130, 70, 128, False, 0)])
+def test_attention(B, H, Nq, Nk, D, causal, window):
+    q = torch.randn(B, Nq, H, D, device=DEV).bfloat16()
+    k = torch.randn(B, Nk, H, D, device=DEV).bfloat16()
+    v = torch.randn(B, Nk, H, D, device=DEV).bfloat16()
+    o = ops.attention(q, k, v, causal=causal, window=window)
+    assert rel(o, sdpa_ref(q, k, v, D ** -0.5, causal, window)) < 6e-3  # P is rounded to bf16 before PV
+
+
+def test_attention_packed_qkv_strides():
+    B, N, H, D = 2, 200, 4, 72
+    qkv = torch.randn(B, N, 3, H, D, device=DEV).bfloat16()
+    q, k, v = qkv.unbind(2)
+    assert rel(ops.attention(q, k, v), sdpa_ref(q, k, v, D ** -0.5)) < 6e-3
+
+
+@pytest.mark.parametrize("pooled", [False, True])
+def test_attention_hiera_windows(pooled):
+    n_img, gh, gw, win, H, D = 2, 16, 24, 8, 2, 72
+    qkv = torch.randn(n_img * gh * gw, 3, H, D, device=DEV).bfloat16()
+    q, k, v = qkv.unbind(1)
+    nwy, nwx = gh // win, gw // win
+
+    def part(t, g_h, g_w, ws):  # window_partition on [n, gh, gw, H, D]
+        t = t.reshape(n_img, g_h // ws, ws, g_w // ws, ws, H, D).permute(0, 1, 3, 2, 4, 5, 6)
+        return t.reshape(-1, ws * ws, H, D)
+
+    if pooled:
+        qp = F.max_pool2d(q.float().reshape(n_img, gh, gw, H * D).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, H, D).bfloat16()
+        o = ops.attention(qp[None], k[None], v[None], q_win=(win // 2, gw // 2, nwx, nwy), k_win=(win, gw, nwx, nwy))
+        ref = sdpa_ref(part(qp, gh // 2, gw // 2, win // 2), part(k, gh, gw, win), part(v, gh, gw, win), D ** -0.5)
+        got = part(o[0], gh // 2, gw // 2, win // 2)
+    else:
+        o = ops.attention(q[None], k[None], v[None], q_win=(win, gw, nwx, nwy))
+        ref = sdpa_ref(part(q, gh, gw, win), part(k, gh, gw, win), part(v, gh, gw, win), D ** -0.5)
+        got = part(o[0], gh, gw, win)
+    assert rel(got, ref) < 6e-3
+
+
+@pytest.mark.parametrize("rows,cols,rms,xdt", [(100, 256, False, torch.float32), (77, 1408, True, torch.float32), (5, 3072, True, torch.bfloat16),
+                                               (1000, 144, False, torch.float32), (64, 64, False, torch.bfloat16), (10, 32, False, torch.float32)])
+def test_norm(rows, cols, rms, xdt):
+    x = (torch.randn(rows, cols, device=DEV) * 3 + 1).to(xdt)
+    w, b = torch.randn(cols, device=DEV), torch.randn(cols, device=DEV)
+    y = ops.norm(x, w, None if rms else b, eps=1e-6, rms=rms, out_dtype=torch.float32)
+    xf = x.float()
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w if rms else F.layer_norm(xf, (cols,), w, b, 1e-6)
+    assert rel(y, ref) < 1e-5
+
+
+def test_add_pool_upsample():
+    a = torch.randn(12, 40, device=DEV)
+    b = torch.randn(3, 40, device=DEV).bfloat16()
+    assert rel(ops.add(a, b, alpha=0.1), a + 0.1 * b.float().repeat(4, 1)) < 1e-6
+    assert ops.cast(a, torch.bfloat16).dtype == torch.bfloat16
+    x = torch.randn(2 * 8 * 6, 3 * 16, device=DEV).bfloat16()
+    q = x[:, :16]
+    ref = F.max_pool2d(q.float().reshape(2, 8, 6, 16).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 16)
+    assert rel(ops.pool2x2(q, 2, 8, 6, is_max=True), ref) < 1e-6
+    ref = F.avg_pool2d(q.float().reshape(2, 8, 6, 16).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 16)
+    assert rel(ops.pool2x2(q, 2, 8, 6, is_max=False, out_dtype=torch.float32), ref) < 1e-6
+    lat, top = torch.randn(2 * 8 * 8, 32, device=DEV), torch.randn(2 * 4 * 4, 32, device=DEV)
+    ref = lat.reshape(2, 8, 8, 32) + F.interpolate(top.reshape(2, 4, 4, 32).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert rel(ops.upsample2x_add(lat, top, 2, 4, 4), ref.reshape(-1, 32)) < 1e-6
+
+
+@pytest.mark.parametrize("cout,with_ln", [(64, True), (32, False)])
+def test_convtranspose_as_gemm(cout, with_ln):
+    n, h, w, cin = 2, 8, 8, 256 if cout == 64 else 64
+    x = torch.randn(n, cin, h, w, device=DEV).bfloat16()
+    W = (torch.randn(cin, cout, 2, 2, device=DEV) / cin ** 0.5).bfloat16()
+    bias, lw, lb = torch.randn(cout, device=DEV), torch.randn(cout, device=DEV), torch.randn(cout, device=DEV)
+    feat = torch.randn(n, cout, 2 * h, 2 * w, device=DEV)
+    ref = F.conv_transpose2d(x.float(), W.float(), bias, stride=2) + feat
+    if with_ln:
+        u = ref.mean(1, keepdim=True)
+        s = (ref - u).pow(2).mean(1, keepdim=True)
+        ref = lw[:, None, None] * ((ref - u) / torch.sqrt(s + 1e-6)) + lb[:, None, None]
+    ref = F.gelu(ref).permute(0, 2, 3, 1).reshape(-1, cout)
+    wg = W.permute(2, 3, 1, 0).reshape(4 * cout, cin).contiguous()  # rows (dy,dx,co), cols ci
+    g = ops.gemm(x.permute(0, 2, 3, 1).reshape(-1, cin).contiguous(), wg, out_dtype=torch.float32)
+    y = ops.convt2x2_epilogue(g, bias, feat.permute(0, 2, 3, 1).reshape(-1, cout).contiguous(), lw if with_ln else None, lb if with_ln else None,
+                              1e-6, n, h, w, cout, out_dtype=torch.float32)
+    assert rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("cin,k,s,p,hw", [(3, 7, 4, 3, 64), (3, 14, 14, 0, 56)])
+def test_im2col_conv(cin, k, s, p, hw):
+    x = torch.randn(2, cin, hw, hw, device=DEV)
+    W = torch.randn(48, cin, k, k, device=DEV).bfloat16()
+    bias = torch.randn(48, device=DEV)
+    cols, oh, ow = ops.im2col(x, k, s, p)
+    wk = torch.zeros(48, cols.shape[1], device=DEV, dtype=torch.bfloat16)
+    wk[:, : cin * k * k] = W.reshape(48, -1)
+    y = ops.gemm(cols, wk, bias=bias, out_dtype=torch.float32)
+    ref = F.conv2d(x.bfloat16().float(), W.float(), bias, stride=s, padding=p).permute(0, 2, 3, 1).reshape(-1, 48)
+    assert rel(y, ref) < 1e-5
+
+
+def test_dwconv_conv3x3_bilinear():
+    n, h, w, c = 2, 16, 16, 64
+    x = torch.randn(n, c, h, w, device=DEV)
+    W, b = torch.randn(c, 1, 7, 7, device=DEV), torch.randn(c, device=DEV)
+    ref = F.conv2d(x, W, b, padding=3, groups=c).permute(0, 2, 3, 1).reshape(-1, c)
+    y = ops.dwconv(x.permute(0, 2, 3, 1).reshape(-1, c).contiguous(), W.reshape(c, 7, 7).contiguous(), b, n, h, w, 7)
+    assert rel(y, ref) < 1e-5
+    for cin in (1, 4, 16, 64):
+        cout = cin * 4
+        x = torch.randn(n, cin, h, w, device=DEV)
+        W, b = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5), torch.randn(cout, device=DEV)
+        lw, lb = torch.randn(cout, device=DEV), torch.randn(cout, device=DEV)
+        r = F.conv2d(x, W, b, stride=2, padding=1)
+        u = r.mean(1, keepdim=True)
+        s = (r - u).pow(2).mean(1, keepdim=True)
+        ref = F.gelu(lw[:, None, None] * ((r - u) / torch.sqrt(s + 1e-6)) + lb[:, None, None]).permute(0, 2, 3, 1).reshape(-1, cout)
+        y = ops.conv3x3s2_ln_gelu(x.permute(0, 2, 3, 1).reshape(-1, cin).contiguous(), W.permute(2, 3, 1, 0).reshape(9 * cin, cout).contiguous(), b,
+                                  lw, lb, 1e-6, n, h, w, cin, cout)
+        assert rel(y, ref) < 2e-5
+    m = torch.randn(3, 64, 64, device=DEV)
+    for oh, ow in ((256, 256), (120, 214), (31, 47)):
+        ref = F.interpolate(m[:, None], size=(oh, ow), mode="bilinear", align_corners=False)[:, 0]
+        assert rel(ops.bilinear(m, oh, ow), ref) < 1e-5
+        assert torch.equal(ops.bilinear(m, oh, ow, mode=3).bool(), ops.bilinear(m, oh, ow) > 0)
+    ref = torch.sigmoid(F.interpolate(m[:, None], size=(256, 256), mode="bilinear", align_corners=False)[:, 0]) * 20 - 10
+    assert rel(ops.bilinear(m, 256, 256, mode=1, scale=20.0, bias=-10.0), ref) < 1e-5
+
+
+def test_rope_embedding_argmax():
+    # SAM2 axial RoPE (position_encoding.py:174-216), 2 repeats along keys
+    gw = gh = 8
+    dim = 64
+    x = torch.randn(2 * gw * gh, dim, device=DEV).bfloat16()
+    fr = 1.0 / (10000.0 ** (torch.arange(0, dim, 4, device=DEV)[: dim // 4].float() / dim))
+    t = torch.arange(gw * gh, device=DEV, dtype=torch.float32)
+    fx, fy = torch.outer(t % gw, fr), torch.outer(torch.div(t, gw, rounding_mode="floor"), fr)
+    cis = torch.cat([torch.polar(torch.ones_like(fx), fx), torch.polar(torch.ones_like(fy), fy)], -1).repeat(2, 1)
+    ref = torch.view_as_real(torch.view_as_complex(x.float().reshape(-1, dim // 2, 2)) * cis).flatten(1)
+    assert rel(ops.rope2d_(x.clone(), dim, gw, gh), ref) < 4e-3
+    # Phi-3 rotate-half RoPE on q,k heads of packed qkv
+    rows, nh, hd = 37, 4, 96
+    qkv = torch.randn(rows, 3 * nh * hd, device=DEV).bfloat16()
+    pos = torch.arange(5, 5 + rows, device=DEV, dtype=torch.int32)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2, device=DEV).float() / hd))
+    ang = pos.float()[:, None] * inv[None]
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1)[:, None], torch.cat([ang.sin(), ang.sin()], -1)[:, None]
+    qk = qkv[:, : 2 * nh * hd].float().reshape(rows, 2 * nh, hd)
+    rot = torch.cat([-qk[..., hd // 2:], qk[..., : hd // 2]], -1)
+    ref = torch.cat([(qk * cos + rot * sin).reshape(rows, -1), qkv[:, 2 * nh * hd:].float()], 1)
+    assert rel(ops.rope_neox_(qkv.clone(), pos, 2 * nh, hd, 10000.0), ref) < 4e-3
+    table = torch.randn(100, 48, device=DEV).bfloat16()
+    ids = torch.randint(0, 100, (17,), device=DEV)
+    assert torch.equal(ops.embedding(table, ids), table[ids].float())
+    lg = torch.randn(6, 32064, device=DEV)
+    lg[2, 77] = lg[2, 9000] = 50.0
+    assert torch.equal(ops.argmax(lg), lg.argmax(-1))

@@ -47,3 +47,23 @@ def lib() -> C.CDLL:
 def check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {lib().vg_last_error().decode()}")
+
+
+class VgAttention(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        *[(n, C.c_longlong) for n in ("q_bs", "q_hs", "q_rs", "k_bs", "k_hs", "k_rs", "v_bs", "v_hs", "v_rs", "o_bs", "o_hs", "o_rs")],
+        ("B", C.c_int), ("H", C.c_int), ("Nq", C.c_int), ("Nk", C.c_int), ("D", C.c_int),
+        ("scale", C.c_float),
+        ("causal", C.c_int), ("window", C.c_int),
+        ("q_win", C.c_int), ("q_gridw", C.c_int), ("q_nwx", C.c_int), ("q_nwy", C.c_int),
+        ("k_win", C.c_int), ("k_gridw", C.c_int), ("k_nwx", C.c_int), ("k_nwy", C.c_int),
+    ]
+
+
+# every symbol include/vglamm.h declares (tests check that the built library exports all of them)
+SYMBOLS = [
+    "vg_last_error", "vg_version", "vg_launch_count", "vg_launch_count_reset", "vg_gemm", "vg_gemm_naive", "vg_attention", "vg_norm",
+    "vg_add", "vg_pool2x2", "vg_upsample2x_add", "vg_convt2x2_epilogue", "vg_im2col", "vg_dwconv", "vg_conv3x3s2_ln_gelu", "vg_bilinear",
+    "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax",
+]

@@ -1,0 +1,246 @@
+// Flash-attention forward (online softmax, no score materialisation) for every attention on the path:
+// CLIP (hd 64), Hiera windowed/global (hd 72), InternVideo2 (hd 88), Phi-3 causal / sliding-window (hd 96),
+// SAM2 mask decoder (hd 16/32) and memory attention (1 head x 256).
+// Q/K/V/O are addressed through (batch, head, row) element strides so packed qkv GEMM outputs are read in place;
+// Hiera windows are addressed by index arithmetic on the un-partitioned [H,W] token grid (no window_partition copy).
+// Bring-up tensor path: mma.sync m16n8k16 bf16 with fp32 accumulate, cp.async double-buffered K/V tiles.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+struct AttnParams {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* o;
+  long long q_bs, q_hs, q_rs, k_bs, k_hs, k_rs, v_bs, v_hs, v_rs, o_bs, o_hs, o_rs;
+  int B, H, Nq, Nk, D;
+  float scale;
+  int causal, window;
+  int q_win, q_gridw, q_nwx, q_nwy;  // 2D window addressing for q/o rows (0 = linear)
+  int k_win, k_gridw, k_nwx, k_nwy;  // 2D window addressing for k/v rows
+};
+
+// row index inside the (batch-strided) tensor for token t of batch entry b
+__device__ __forceinline__ long long tok_row(int b, int t, int win, int gridw, int nwx, int nwy) {
+  if (win == 0) return t;
+  const int per_img = nwx * nwy;
+  const int img = b / per_img, w = b - img * per_img;
+  const int wy = w / nwx, wx = w - wy * nwx;
+  const int ty = t / win, tx = t - ty * win;
+  return static_cast<long long>(img) * (static_cast<long long>(nwy) * win * gridw) + static_cast<long long>(wy * win + ty) * gridw + wx * win + tx;
+}
+
+template <int DP>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
+  constexpr int BM = 64, BN = 64, LD = DP + 8, CH = DP / 8;  // CH: 16-byte chunks per row
+  constexpr bool Q_IN_REGS = DP <= 128;
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
+  __nv_bfloat16* sK = sQ + BM * LD;
+  __nv_bfloat16* sV = sK + 2 * BN * LD;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int off = p.Nk - p.Nq;  // causal alignment: query i may see keys j <= i + off
+  int k_end = p.Nk;
+  if (p.causal) k_end = min(p.Nk, q0 + BM + off);
+  int k_begin = 0;
+  if (p.window > 0) k_begin = max(0, (q0 + off - p.window) / BN * BN);
+  const int ntiles = (k_end - k_begin + BN - 1) / BN;
+
+  const bool lin_q = p.q_win == 0, lin_k = p.k_win == 0;
+  const __nv_bfloat16* qb = p.q + (lin_q ? b * p.q_bs : 0) + h * p.q_hs;
+  const __nv_bfloat16* kb = p.k + (lin_k ? b * p.k_bs : 0) + h * p.k_hs;
+  const __nv_bfloat16* vb = p.v + (lin_k ? b * p.v_bs : 0) + h * p.v_hs;
+
+  for (int i = tid; i < BM * CH; i += 128) {
+    const int r = i / CH, c = i - r * CH;
+    const bool ok = (q0 + r < p.Nq) && (c * 8 < p.D);
+    const long long row = ok ? tok_row(b, q0 + r, p.q_win, p.q_gridw, p.q_nwx, p.q_nwy) : 0;
+    cp_async16(sQ + r * LD + c * 8, qb + row * p.q_rs + c * 8, ok);
+  }
+  auto load_kv = [&](int tile, int stage) {
+    const int kbase = k_begin + tile * BN;
+    for (int i = tid; i < BN * CH; i += 128) {
+      const int r = i / CH, c = i - r * CH;
+      const bool ok = (kbase + r < p.Nk) && (c * 8 < p.D);
+      const long long row = ok ? tok_row(b, kbase + r, p.k_win, p.k_gridw, p.k_nwx, p.k_nwy) : 0;
+      cp_async16(sK + (stage * BN + r) * LD + c * 8, kb + row * p.k_rs + c * 8, ok);
+      cp_async16(sV + (stage * BN + r) * LD + c * 8, vb + row * p.v_rs + c * 8, ok);
+    }
+  };
+  if (ntiles > 0) load_kv(0, 0);
+  cp_async_commit();
+
+  const float sl2 = p.scale * 1.4426950408889634f;
+  float o_acc[DP / 8][4];
+#pragma unroll
+  for (int i = 0; i < DP / 8; ++i) o_acc[i][0] = o_acc[i][1] = o_acc[i][2] = o_acc[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  uint32_t qf[Q_IN_REGS ? DP / 16 : 1][4];
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int a_row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;       // A-operand ldmatrix address
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;                  // B (K tile, non-trans)
+  const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_col = (lane >> 4) * 8;                  // B (V tile, trans)
+
+  for (int it = 0; it < ntiles; ++it) {
+    if (it + 1 < ntiles) load_kv(it + 1, (it + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
+    if (it == 0 && Q_IN_REGS) {
+#pragma unroll
+      for (int kt = 0; kt < DP / 16; ++kt) ldmatrix_x4(qf[Q_IN_REGS ? kt : 0], sQ + a_row * LD + kt * 16 + a_col);
+    }
+    const __nv_bfloat16* tK = sK + (it & 1) * BN * LD;
+    const __nv_bfloat16* tV = sV + (it & 1) * BN * LD;
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < DP / 16; ++kt) {
+      uint32_t a[4];
+      if (Q_IN_REGS) {
+        a[0] = qf[Q_IN_REGS ? kt : 0][0]; a[1] = qf[Q_IN_REGS ? kt : 0][1]; a[2] = qf[Q_IN_REGS ? kt : 0][2]; a[3] = qf[Q_IN_REGS ? kt : 0][3];
+      } else {
+        ldmatrix_x4(a, sQ + a_row * LD + kt * 16 + a_col);
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        uint32_t bb[4];
+        ldmatrix_x4(bb, tK + (n2 * 16 + b_row) * LD + kt * 16 + b_col);
+        mma_bf16_16816(s[2 * n2], a, bb[0], bb[1]);
+        mma_bf16_16816(s[2 * n2 + 1], a, bb[2], bb[3]);
+      }
+    }
+    // masking + online softmax (rows g and g+8 of this warp's 16)
+    const int kbase = k_begin + it * BN;
+    const int qrow0 = q0 + warp * 16 + g;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = kbase + nt * 8 + 2 * t4 + (e & 1);
+        const int row = qrow0 + (e >> 1) * 8;
+        bool ok = col < p.Nk;
+        if (p.causal) ok = ok && (col <= row + off);
+        if (p.window > 0) ok = ok && (col >= row + off - p.window);
+        s[nt][e] = ok ? s[nt][e] : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    }
+    float alpha[2], msc[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      msc[r] = (m_new == -INFINITY) ? 0.f : m_new * sl2;
+      alpha[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] * sl2 - msc[r]);
+      m_run[r] = m_new;
+      l_run[r] *= alpha[r];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = exp2f(s[nt][e] * sl2 - msc[e >> 1]);  // exp2(-inf) = 0 for masked entries
+        s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < DP / 8; ++i) {
+      o_acc[i][0] *= alpha[0]; o_acc[i][1] *= alpha[0];
+      o_acc[i][2] *= alpha[1]; o_acc[i][3] *= alpha[1];
+    }
+    // O += P V
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * k2][0], s[2 * k2][1]);
+      a[1] = pack_bf16(s[2 * k2][2], s[2 * k2][3]);
+      a[2] = pack_bf16(s[2 * k2 + 1][0], s[2 * k2 + 1][1]);
+      a[3] = pack_bf16(s[2 * k2 + 1][2], s[2 * k2 + 1][3]);
+#pragma unroll
+      for (int d2 = 0; d2 < DP / 16; ++d2) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, tV + (k2 * 16 + v_row) * LD + d2 * 16 + v_col);
+        mma_bf16_16816(o_acc[2 * d2], a, bb[0], bb[1]);
+        mma_bf16_16816(o_acc[2 * d2 + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
+
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+    l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  __nv_bfloat16* ob = p.o + (lin_q ? b * p.o_bs : 0) + h * p.o_hs;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int row = q0 + warp * 16 + g + r * 8;
+    if (row >= p.Nq) continue;
+    const float inv = l_run[r] > 0.f ? 1.0f / l_run[r] : 0.f;
+    __nv_bfloat16* orow = ob + tok_row(b, row, p.q_win, p.q_gridw, p.q_nwx, p.q_nwy) * p.o_rs;
+#pragma unroll
+    for (int nt = 0; nt < DP / 8; ++nt) {
+      const int col = nt * 8 + 2 * t4;
+      if (col < p.D) *reinterpret_cast<uint32_t*>(orow + col) = pack_bf16(o_acc[nt][2 * r] * inv, o_acc[nt][2 * r + 1] * inv);
+    }
+  }
+}
+
+template <int DP>
+static int launch_attn(const AttnParams& p, cudaStream_t s) {
+  constexpr int LD = DP + 8;
+  constexpr int smem = (64 * LD + 4 * 64 * LD) * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_error(VG_ECUDA, "attention smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((p.Nq + 63) / 64, p.H, p.B);
+  flash_attn_kernel<DP><<<grid, 128, smem, s>>>(p);
+  count_launch();
+  return check_launch("flash_attn_kernel");
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" int vg_attention(const VgAttention* a, void* stream) {
+  if (!a || !a->q || !a->k || !a->v || !a->o) return set_error(VG_EINVAL, "vg_attention: null pointer");
+  if (a->B <= 0 || a->H <= 0 || a->Nq <= 0 || a->Nk <= 0 || a->D <= 0) return set_error(VG_EINVAL, "vg_attention: bad dims");
+  if (a->D % 8) return set_error(VG_EINVAL, "vg_attention: head dim must be a multiple of 8 (got %d)", a->D);
+  const long long strides[] = {a->q_bs, a->q_hs, a->q_rs, a->k_bs, a->k_hs, a->k_rs, a->v_bs, a->v_hs, a->v_rs};
+  for (long long st : strides)
+    if (st % 8) return set_error(VG_EINVAL, "vg_attention: q/k/v strides must be multiples of 8 elements");
+  if ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v)) & 15)
+    return set_error(VG_EINVAL, "vg_attention: q/k/v must be 16-byte aligned");
+  if ((a->o_rs | a->o_hs | a->o_bs) % 2 || (reinterpret_cast<uintptr_t>(a->o) & 3)) return set_error(VG_EINVAL, "vg_attention: o strides must be even");
+  AttnParams p;
+  p.q = static_cast<const __nv_bfloat16*>(a->q); p.k = static_cast<const __nv_bfloat16*>(a->k);
+  p.v = static_cast<const __nv_bfloat16*>(a->v); p.o = static_cast<__nv_bfloat16*>(a->o);
+  p.q_bs = a->q_bs; p.q_hs = a->q_hs; p.q_rs = a->q_rs; p.k_bs = a->k_bs; p.k_hs = a->k_hs; p.k_rs = a->k_rs;
+  p.v_bs = a->v_bs; p.v_hs = a->v_hs; p.v_rs = a->v_rs; p.o_bs = a->o_bs; p.o_hs = a->o_hs; p.o_rs = a->o_rs;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.D = a->D;
+  p.scale = a->scale; p.causal = a->causal; p.window = a->window;
+  p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
+  p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->D <= 32) return launch_attn<32>(p, s);
+  if (a->D <= 64) return launch_attn<64>(p, s);
+  if (a->D <= 80) return launch_attn<80>(p, s);
+  if (a->D <= 96) return launch_attn<96>(p, s);
+  if (a->D <= 128) return launch_attn<128>(p, s);
+  if (a->D <= 256) return launch_attn<256>(p, s);
+  return set_error(VG_ENOSUP, "vg_attention: head dim %d > 256", a->D);
+}

@@ -1,0 +1,463 @@
+// Normalisation, elementwise, pooling, resampling, small convolutions, RoPE, embedding, argmax.
+// All HBM-bound: coalesced channel-contiguous access, fp32 math, dtype (bf16/fp32) chosen at run time.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+__device__ __forceinline__ float ld(const void* p, int dt, long long i) {
+  return dt == VG_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st(void* p, int dt, long long i, float v) {
+  if (dt == VG_F32)
+    reinterpret_cast<float*>(p)[i] = v;
+  else
+    reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
+
+// ------------------------------------------------------------------------------------------------ norm
+// one warp per row; two passes over registers-cached row when cols <= 32*MAXV, else re-read.
+template <int MAXV>
+__global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, const float* w, const float* b,
+                            int rows, int cols, float eps, int rms) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long xo = static_cast<long long>(row) * ldx, yo = static_cast<long long>(row) * ldy;
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < cols ? ld(x, xdt, xo + c) : 0.f;
+    sum += v[i];
+  }
+  float mean = 0.f;
+  if (!rms) mean = warp_sum(sum) / cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    const float d = c < cols ? v[i] - mean : 0.f;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = lane + i * 32;
+    if (c < cols) {
+      float o = (v[i] - mean) * rstd * w[c];
+      if (b) o += b[c];
+      st(y, ydt, yo + c, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ add / cast
+__global__ void add_kernel(const void* a, int adt, long long lda, const void* b, int bdt, long long ldb, int b_rows, float alpha, void* out,
+                           int odt, long long ldo, long long rows, int cols) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = static_cast<int>(i - r * cols);
+  float v = ld(a, adt, r * lda + c);
+  if (b) v += alpha * ld(b, bdt, (r % b_rows) * ldb + c);
+  st(out, odt, r * ldo + c, v);
+}
+
+__global__ void pool2x2_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, int n, int h, int w, int c, int is_max) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int oh = h / 2, ow = w / 2;
+  if (i >= static_cast<long long>(n) * oh * ow * c) return;
+  const int ch = static_cast<int>(i % c);
+  long long t = i / c;
+  const int ox = static_cast<int>(t % ow);
+  t /= ow;
+  const int oy = static_cast<int>(t % oh);
+  const int img = static_cast<int>(t / oh);
+  const long long base = (static_cast<long long>(img) * h + 2 * oy) * w + 2 * ox;
+  const float v00 = ld(x, xdt, base * ldx + ch), v01 = ld(x, xdt, (base + 1) * ldx + ch);
+  const float v10 = ld(x, xdt, (base + w) * ldx + ch), v11 = ld(x, xdt, (base + w + 1) * ldx + ch);
+  const float v = is_max ? fmaxf(fmaxf(v00, v01), fmaxf(v10, v11)) : 0.25f * (v00 + v01 + v10 + v11);
+  st(y, ydt, ((static_cast<long long>(img) * oh + oy) * ow + ox) * ldy + ch, v);
+}
+
+__global__ void upsample2x_add_kernel(const float* lat, const float* top, float* out, int n, int h, int w, int c) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int H = 2 * h, W = 2 * w;
+  if (i >= static_cast<long long>(n) * H * W * c) return;
+  const int ch = static_cast<int>(i % c);
+  long long t = i / c;
+  const int X = static_cast<int>(t % W);
+  t /= W;
+  const int Y = static_cast<int>(t % H);
+  const int img = static_cast<int>(t / H);
+  out[i] = lat[i] + top[((static_cast<long long>(img) * h + Y / 2) * w + X / 2) * c + ch];
+}
+
+// one warp per output pixel; cout <= 128 (4 values per lane)
+__global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bias, const void* feat, int fdt, const float* ln_w,
+                                         const float* ln_b, float eps, void* out, int odt, int n, int h, int w, int cout) {
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int H = 2 * h, W = 2 * w;
+  if (pix >= static_cast<long long>(n) * H * W) return;
+  const int X = static_cast<int>(pix % W);
+  const int Y = static_cast<int>((pix / W) % H);
+  const int img = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const long long src_row = (static_cast<long long>(img) * h + Y / 2) * w + X / 2;
+  const int sub = (Y & 1) * 2 + (X & 1);
+  float v[4];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + i * 32;
+    v[i] = 0.f;
+    if (c < cout) {
+      v[i] = ld(g, gdt, src_row * (4LL * cout) + sub * cout + c) + bias[c];
+      if (feat) v[i] += ld(feat, fdt, pix * cout + c);
+      sum += v[i];
+    }
+  }
+  if (ln_w) {
+    const float mean = warp_sum(sum) / cout;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + i * 32;
+      const float d = c < cout ? v[i] - mean : 0.f;
+      sq += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / cout + eps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = lane + i * 32;
+      if (c < cout) v[i] = (v[i] - mean) * rstd * ln_w[c] + ln_b[c];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = lane + i * 32;
+    if (c < cout) st(out, odt, pix * cout + c, gelu_erf(v[i]));
+  }
+}
+
+__global__ void im2col_kernel(const void* x, int xdt, __nv_bfloat16* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow,
+                              int kpad) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(n) * oh * ow * kpad) return;
+  const int col = static_cast<int>(i % kpad);
+  long long t = i / kpad;
+  const int ox = static_cast<int>(t % ow);
+  t /= ow;
+  const int oy = static_cast<int>(t % oh);
+  const int img = static_cast<int>(t / oh);
+  float v = 0.f;
+  if (col < cin * k * k) {
+    const int ci = col / (k * k), rem = col - ci * k * k;
+    const int ky = rem / k, kx = rem - ky * k;
+    const int iy = oy * s - p + ky, ix = ox * s - p + kx;
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = ld(x, xdt, ((static_cast<long long>(img) * cin + ci) * h + iy) * w + ix);
+  }
+  out[i] = __float2bfloat16(v);
+}
+
+__global__ void dwconv_kernel(const void* x, int xdt, const float* wt, const float* bias, void* y, int ydt, int n, int h, int w, int c, int k) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(n) * h * w * c) return;
+  const int ch = static_cast<int>(i % c);
+  long long t = i / c;
+  const int px = static_cast<int>(t % w);
+  t /= w;
+  const int py = static_cast<int>(t % h);
+  const int img = static_cast<int>(t / h);
+  const int r = k / 2;
+  float acc = bias ? bias[ch] : 0.f;
+  for (int ky = 0; ky < k; ++ky) {
+    const int iy = py + ky - r;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < k; ++kx) {
+      const int ix = px + kx - r;
+      if (ix < 0 || ix >= w) continue;
+      acc = fmaf(ld(x, xdt, ((static_cast<long long>(img) * h + iy) * w + ix) * c + ch), wt[(ch * k + ky) * k + kx], acc);
+    }
+  }
+  st(y, ydt, i, acc);
+}
+
+// one warp per output pixel; lanes stride over cout (<= 256 -> 8 per lane)
+__global__ void conv3x3s2_ln_gelu_kernel(const void* x, int xdt, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
+                                         float eps, void* y, int ydt, int n, int h, int w, int cin, int cout) {
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int oh = h / 2, ow = w / 2;
+  if (pix >= static_cast<long long>(n) * oh * ow) return;
+  const int ox = static_cast<int>(pix % ow);
+  const int oy = static_cast<int>((pix / ow) % oh);
+  const int img = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int co = lane + i * 32;
+    acc[i] = co < cout ? bias[co] : 0.f;
+  }
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = 2 * ox - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      const long long xb = ((static_cast<long long>(img) * h + iy) * w + ix) * cin;
+      const float* wk = wt + static_cast<long long>((ky * 3 + kx) * cin) * cout;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float xv = ld(x, xdt, xb + ci);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int co = lane + i * 32;
+          if (co < cout) acc[i] = fmaf(xv, wk[static_cast<long long>(ci) * cout + co], acc[i]);
+        }
+      }
+    }
+  }
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += (lane + i * 32 < cout) ? acc[i] : 0.f;
+  const float mean = warp_sum(sum) / cout;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float d = (lane + i * 32 < cout) ? acc[i] - mean : 0.f;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / cout + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int co = lane + i * 32;
+    if (co < cout) st(y, ydt, pix * cout + co, gelu_erf((acc[i] - mean) * rstd * ln_w[co] + ln_b[co]));
+  }
+}
+
+__global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(n) * oh * ow) return;
+  const int ox = static_cast<int>(i % ow);
+  const int oy = static_cast<int>((i / ow) % oh);
+  const int img = static_cast<int>(i / (static_cast<long long>(ow) * oh));
+  // PyTorch upsample_bilinear2d, align_corners=False: src = max(0, (dst + 0.5) * (in/out) - 0.5)
+  const float ry = static_cast<float>(ih) / oh, rx = static_cast<float>(iw) / ow;
+  const float sy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
+  const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+  const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
+  const float ly = sy - y0, lx = sx - x0;
+  const float* p = x + static_cast<long long>(img) * ih * iw;
+  const float v = (1.f - ly) * ((1.f - lx) * p[y0 * iw + x0] + lx * p[y0 * iw + x1]) + ly * ((1.f - lx) * p[y1 * iw + x0] + lx * p[y1 * iw + x1]);
+  if (mode == 3) {
+    reinterpret_cast<uint8_t*>(y)[i] = v > 0.f ? 1 : 0;
+    return;
+  }
+  float o = v;
+  if (mode == 1) o = scale / (1.f + expf(-v)) + bias;
+  if (mode == 2) o = (v > 0.f ? scale : 0.f) + bias;
+  reinterpret_cast<float*>(y)[i] = o;
+}
+
+__global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim, int gw, int gh) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int half = dim / 2;  // complex pairs per row
+  if (i >= static_cast<long long>(nrows) * half) return;
+  const int pr = static_cast<int>(i % half);
+  const long long r = i / half;
+  const int quarter = dim / 4;
+  const int px = static_cast<int>(r % gw), py = static_cast<int>((r / gw) % gh);
+  const int fi = pr < quarter ? pr : pr - quarter;
+  const float freq = 1.0f / powf(10000.0f, static_cast<float>(4 * fi) / dim);
+  const float ang = (pr < quarter ? px : py) * freq;
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  __nv_bfloat16* p = x + r * ld + 2 * pr;
+  const float a = __bfloat162float(p[0]), b = __bfloat162float(p[1]);
+  p[0] = __float2bfloat16(a * cs - b * sn);
+  p[1] = __float2bfloat16(a * sn + b * cs);
+}
+
+__global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int half = hd / 2;
+  if (i >= static_cast<long long>(rows) * nheads * half) return;
+  const int j = static_cast<int>(i % half);
+  const int hh = static_cast<int>((i / half) % nheads);
+  const long long r = i / (static_cast<long long>(half) * nheads);
+  const float inv = powf(theta, -2.0f * j / hd);
+  float sn, cs;
+  sincosf(pos[r] * inv, &sn, &cs);
+  __nv_bfloat16* p = qkv + r * ld + hh * hd;
+  const float a = __bfloat162float(p[j]), b = __bfloat162float(p[j + half]);
+  p[j] = __float2bfloat16(a * cs - b * sn);
+  p[j + half] = __float2bfloat16(b * cs + a * sn);
+}
+
+__global__ void embedding_kernel(const __nv_bfloat16* table, long long ldt, const long long* ids, void* out, int odt, long long ldo, int rows,
+                                 int cols) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(rows) * cols) return;
+  const int c = static_cast<int>(i % cols);
+  const long long r = i / cols;
+  st(out, odt, r * ldo + c, __bfloat162float(table[ids[r] * ldt + c]));
+}
+
+// one block (256 threads) per row
+__global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
+  const int row = blockIdx.x;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const float v = ld(x, xdt, static_cast<long long>(row) * ldx + c);
+    if (v > best || (v == best && c < bi)) {
+      best = v;
+      bi = c;
+    }
+  }
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const float ov = sv[threadIdx.x + s];
+      const int oi = si[threadIdx.x + s];
+      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = ov;
+        si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[row] = si[0];
+}
+
+}  // namespace vg
+
+using namespace vg;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, const float* w, const float* b,
+                       int rows, int cols, float eps, int rms, void* stream) {
+  if (!x || !y || !w || rows <= 0 || cols <= 0) return set_error(VG_EINVAL, "vg_norm: bad argument");
+  const int warps = 8;
+  const unsigned grid = (rows + warps - 1) / warps;
+  if (cols <= 32 * 4)
+    norm_kernel<4><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+  else if (cols <= 32 * 12)
+    norm_kernel<12><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+  else if (cols <= 32 * 48)
+    norm_kernel<48><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+  else if (cols <= 32 * 100)
+    norm_kernel<100><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+  else
+    return set_error(VG_ENOSUP, "vg_norm: cols %d > 3200", cols);
+  count_launch();
+  return check_launch("norm_kernel");
+}
+
+extern "C" int vg_add(const void* a, int a_dtype, long long lda, const void* b, int b_dtype, long long ldb, int b_rows, float alpha, void* out,
+                      int out_dtype, long long ldo, int rows, int cols, void* stream) {
+  if (!a || !out || rows <= 0 || cols <= 0 || (b && b_rows <= 0)) return set_error(VG_EINVAL, "vg_add: bad argument");
+  add_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(a, a_dtype, lda, b, b_dtype, ldb, b_rows, alpha, out,
+                                                                                        out_dtype, ldo, rows, cols);
+  count_launch();
+  return check_launch("add_kernel");
+}
+
+extern "C" int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int n, int h, int w, int c, int is_max,
+                          void* stream) {
+  if (!x || !y || (h & 1) || (w & 1)) return set_error(VG_EINVAL, "vg_pool2x2: bad argument (h, w must be even)");
+  pool2x2_kernel<<<blocks_for(static_cast<long long>(n) * (h / 2) * (w / 2) * c, 256), 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, n, h,
+                                                                                                          w, c, is_max);
+  count_launch();
+  return check_launch("pool2x2_kernel");
+}
+
+extern "C" int vg_upsample2x_add(const float* lat, const float* top, float* out, int n, int h, int w, int c, void* stream) {
+  if (!lat || !top || !out) return set_error(VG_EINVAL, "vg_upsample2x_add: null");
+  upsample2x_add_kernel<<<blocks_for(static_cast<long long>(n) * 4 * h * w * c, 256), 256, 0, STREAM>>>(lat, top, out, n, h, w, c);
+  count_launch();
+  return check_launch("upsample2x_add_kernel");
+}
+
+extern "C" int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bias, const void* feat, int feat_dtype, const float* ln_w,
+                                    const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, void* stream) {
+  if (!g || !bias || !out || cout > 128) return set_error(VG_EINVAL, "vg_convt2x2_epilogue: bad argument (cout <= 128)");
+  const long long pix = static_cast<long long>(n) * 4 * h * w;
+  convt2x2_epilogue_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(g, g_dtype, bias, feat, feat_dtype, ln_w, ln_b, eps, out, out_dtype, n, h, w,
+                                                                    cout);
+  count_launch();
+  return check_launch("convt2x2_epilogue_kernel");
+}
+
+extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
+                         void* stream) {
+  if (!x || !out || kpad < cin * k * k) return set_error(VG_EINVAL, "vg_im2col: bad argument");
+  im2col_kernel<<<blocks_for(static_cast<long long>(n) * oh * ow * kpad, 256), 256, 0, STREAM>>>(x, x_dtype, static_cast<__nv_bfloat16*>(out), n,
+                                                                                                  cin, h, w, k, s, p, oh, ow, kpad);
+  count_launch();
+  return check_launch("im2col_kernel");
+}
+
+extern "C" int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, void* y, int y_dtype, int n, int h, int wd, int c, int k,
+                         void* stream) {
+  if (!x || !w || !y) return set_error(VG_EINVAL, "vg_dwconv: null");
+  dwconv_kernel<<<blocks_for(static_cast<long long>(n) * h * wd * c, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, y, y_dtype, n, h, wd, c, k);
+  count_launch();
+  return check_launch("dwconv_kernel");
+}
+
+extern "C" int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w, const float* ln_b,
+                                    float eps, void* y, int y_dtype, int n, int h, int wd, int cin, int cout, void* stream) {
+  if (!x || !w || !bias || !ln_w || !ln_b || !y || cout > 256 || (h & 1) || (wd & 1)) return set_error(VG_EINVAL, "vg_conv3x3s2_ln_gelu: bad argument");
+  const long long pix = static_cast<long long>(n) * (h / 2) * (wd / 2);
+  conv3x3s2_ln_gelu_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin, cout);
+  count_launch();
+  return check_launch("conv3x3s2_ln_gelu_kernel");
+}
+
+extern "C" int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream) {
+  if (!x || !y) return set_error(VG_EINVAL, "vg_bilinear: null");
+  bilinear_kernel<<<blocks_for(static_cast<long long>(n) * oh * ow, 256), 256, 0, STREAM>>>(x, y, n, ih, iw, oh, ow, mode, scale, bias);
+  count_launch();
+  return check_launch("bilinear_kernel");
+}
+
+extern "C" int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* stream) {
+  if (!x || dim % 4) return set_error(VG_EINVAL, "vg_rope2d: dim must be a multiple of 4");
+  rope2d_kernel<<<blocks_for(static_cast<long long>(nrows) * dim / 2, 256), 256, 0, STREAM>>>(static_cast<__nv_bfloat16*>(x), ld, nrows, dim, gw, gh);
+  count_launch();
+  return check_launch("rope2d_kernel");
+}
+
+extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
+  if (!qkv || !pos || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_neox: bad argument");
+  rope_neox_kernel<<<blocks_for(static_cast<long long>(rows) * n_heads_total * head_dim / 2, 256), 256, 0, STREAM>>>(
+      static_cast<__nv_bfloat16*>(qkv), ld, pos, rows, n_heads_total, head_dim, theta);
+  count_launch();
+  return check_launch("rope_neox_kernel");
+}
+
+extern "C" int vg_embedding(const void* table, long long ldt, const long long* ids, void* out, int out_dtype, long long ldo, int rows, int cols,
+                            void* stream) {
+  if (!table || !ids || !out) return set_error(VG_EINVAL, "vg_embedding: null");
+  embedding_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(table), ldt, ids,
+                                                                                              out, out_dtype, ldo, rows, cols);
+  count_launch();
+  return check_launch("embedding_kernel");
+}
+
+extern "C" int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream) {
+  if (!x || !out) return set_error(VG_EINVAL, "vg_argmax: null");
+  argmax_kernel<<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, out, cols);
+  count_launch();
+  return check_launch("argmax_kernel");
+}

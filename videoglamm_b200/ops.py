@@ -81,3 +81,186 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     L.lib().vg_launch_count_reset()
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, causal: bool = False, window: int = 0,
+              out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None) -> torch.Tensor:
+    """q [B,Nq,H,D], k/v [B,Nk,H,D] bf16 views (any strides with unit last stride) -> out [B,Nq,H,D] (contiguous unless given).
+    q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
+    un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
+    _require_cuda(q, k, v, out)
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    a = L.VgAttention()
+    if q_win is None:
+        B, Nq, H, D = q.shape
+        Nk = k.shape[1]
+    else:
+        win, gridw, nwx, nwy = q_win
+        kw = k_win or q_win
+        H, D = q.shape[-2:]
+        n_img = q.shape[1] // (nwy * win * gridw)
+        B, Nq, Nk = n_img * nwx * nwy, win * win, kw[0] * kw[0]
+        a.q_win, a.q_gridw, a.q_nwx, a.q_nwy = q_win
+        a.k_win, a.k_gridw, a.k_nwx, a.k_nwy = kw
+    if out is None:
+        out = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+    for t in (q, k, v, out):
+        assert t.stride(-1) == 1
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q_bs, a.q_rs, a.q_hs = q.stride(0), q.stride(1), q.stride(2)
+    a.k_bs, a.k_rs, a.k_hs = k.stride(0), k.stride(1), k.stride(2)
+    a.v_bs, a.v_rs, a.v_hs = v.stride(0), v.stride(1), v.stride(2)
+    a.o_bs, a.o_rs, a.o_hs = out.stride(0), out.stride(1), out.stride(2)
+    a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
+    a.scale = float(scale if scale is not None else D ** -0.5)
+    a.causal, a.window = int(causal), int(window)
+    L.check(L.lib().vg_attention(C.byref(a), _stream()), "vg_attention")
+    return out
+
+
+def norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None = None, *, eps: float, rms: bool = False,
+         out_dtype: torch.dtype = torch.bfloat16, out: torch.Tensor | None = None) -> torch.Tensor:
+    """LayerNorm / RMSNorm over the last dim. x [..., C] with unit last stride and uniform row stride (2D after flatten)."""
+    _require_cuda(x, w, b, out)
+    cols = x.shape[-1]
+    x2 = x.reshape(-1, cols) if x.is_contiguous() else x
+    assert x2.dim() == 2 and x2.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    o2 = out.reshape(-1, cols) if out.is_contiguous() else out
+    assert o2.dim() == 2 and o2.stride(1) == 1
+    assert w.dtype == torch.float32 and (b is None or b.dtype == torch.float32)
+    L.check(L.lib().vg_norm(_ptr(x2), _dt(x2.dtype), C.c_longlong(x2.stride(0)), _ptr(o2), _dt(o2.dtype), C.c_longlong(o2.stride(0)), _ptr(w), _ptr(b),
+                            x2.shape[0], cols, C.c_float(eps), int(rms), _stream()), "vg_norm")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor | None = None, *, alpha: float = 1.0, out_dtype: torch.dtype | None = None,
+        out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = a + alpha*b, b broadcast over leading rows (b rows must divide a rows: out[r] uses b[r % b_rows]). b=None casts."""
+    _require_cuda(a, b, out)
+    cols = a.shape[-1]
+    a2 = a.reshape(-1, cols) if a.is_contiguous() else a
+    assert a2.dim() == 2 and a2.stride(1) == 1
+    if out is None:
+        out = torch.empty(a.shape, device=a.device, dtype=out_dtype or a.dtype)
+    o2 = out.reshape(-1, cols) if out.is_contiguous() else out
+    if b is not None:
+        b2 = b.reshape(-1, cols) if b.is_contiguous() else b
+        assert b2.dim() == 2 and b2.stride(1) == 1 and a2.shape[0] % b2.shape[0] == 0
+        bargs = (_ptr(b2), _dt(b2.dtype), C.c_longlong(b2.stride(0)), b2.shape[0])
+    else:
+        bargs = (None, 0, C.c_longlong(0), 1)
+    L.check(L.lib().vg_add(_ptr(a2), _dt(a2.dtype), C.c_longlong(a2.stride(0)), *bargs, C.c_float(alpha), _ptr(o2), _dt(o2.dtype),
+                           C.c_longlong(o2.stride(0)), a2.shape[0], cols, _stream()), "vg_add")
+    return out
+
+
+def cast(a: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    return add(a, None, out_dtype=dtype)
+
+
+def pool2x2(x: torch.Tensor, n: int, h: int, w: int, *, is_max: bool, out_dtype: torch.dtype | None = None) -> torch.Tensor:
+    """x: [n*h*w, C] view (row stride arbitrary) -> [n*(h/2)*(w/2), C]"""
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.shape[0] == n * h * w
+    c = x.shape[1]
+    y = torch.empty((n * (h // 2) * (w // 2), c), device=x.device, dtype=out_dtype or x.dtype)
+    L.check(L.lib().vg_pool2x2(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), _ptr(y), _dt(y.dtype), C.c_longlong(c), n, h, w, c, int(is_max),
+                               _stream()), "vg_pool2x2")
+    return y
+
+
+def upsample2x_add(lat: torch.Tensor, top: torch.Tensor, n: int, h: int, w: int) -> torch.Tensor:
+    """lat [n*2h*2w, C] fp32 + nearest-upsampled top [n*h*w, C] fp32"""
+    _require_cuda(lat, top)
+    assert lat.dtype == top.dtype == torch.float32 and lat.is_contiguous() and top.is_contiguous()
+    out = torch.empty_like(lat)
+    L.check(L.lib().vg_upsample2x_add(_ptr(lat), _ptr(top), _ptr(out), n, h, w, lat.shape[-1], _stream()), "vg_upsample2x_add")
+    return out
+
+
+def convt2x2_epilogue(g: torch.Tensor, bias: torch.Tensor, feat: torch.Tensor | None, ln_w, ln_b, eps: float, n: int, h: int, w: int,
+                      cout: int, out_dtype=torch.bfloat16) -> torch.Tensor:
+    _require_cuda(g, bias, feat)
+    assert g.is_contiguous() and g.shape[-1] == 4 * cout and (feat is None or feat.is_contiguous())
+    out = torch.empty((n * 4 * h * w, cout), device=g.device, dtype=out_dtype)
+    L.check(L.lib().vg_convt2x2_epilogue(_ptr(g), _dt(g.dtype), _ptr(bias), _ptr(feat), _dt(feat.dtype) if feat is not None else 0, _ptr(ln_w),
+                                         _ptr(ln_b), C.c_float(eps), _ptr(out), _dt(out.dtype), n, h, w, cout, _stream()), "vg_convt2x2_epilogue")
+    return out
+
+
+def im2col(x: torch.Tensor, k: int, s: int, p: int, kpad: int | None = None) -> tuple[torch.Tensor, int, int]:
+    """x NCHW (fp32/bf16, contiguous) -> bf16 [n*oh*ow, kpad]"""
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, cin, h, w = x.shape
+    oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+    kk = cin * k * k
+    kpad = kpad or (kk + 7) // 8 * 8
+    out = torch.empty((n * oh * ow, kpad), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().vg_im2col(_ptr(x), _dt(x.dtype), _ptr(out), n, cin, h, w, k, s, p, oh, ow, kpad, _stream()), "vg_im2col")
+    return out, oh, ow
+
+
+def dwconv(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n: int, h: int, wd: int, k: int, out_dtype=None) -> torch.Tensor:
+    """x [n*h*wd, C] channels-last; w [C,k,k] fp32"""
+    _require_cuda(x, w, bias)
+    assert x.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    L.check(L.lib().vg_dwconv(_ptr(x), _dt(x.dtype), _ptr(w), _ptr(bias), _ptr(y), _dt(y.dtype), n, h, wd, x.shape[-1], k, _stream()), "vg_dwconv")
+    return y
+
+
+def conv3x3s2_ln_gelu(x: torch.Tensor, w: torch.Tensor, bias, ln_w, ln_b, eps: float, n: int, h: int, wd: int, cin: int, cout: int,
+                      out_dtype=torch.float32) -> torch.Tensor:
+    """x [n*h*wd, cin] channels-last; w [(ky,kx,ci), cout] fp32"""
+    _require_cuda(x, w)
+    assert x.is_contiguous() and w.is_contiguous() and tuple(w.shape) == (9 * cin, cout)
+    y = torch.empty((n * (h // 2) * (wd // 2), cout), device=x.device, dtype=out_dtype)
+    L.check(L.lib().vg_conv3x3s2_ln_gelu(_ptr(x), _dt(x.dtype), _ptr(w), _ptr(bias), _ptr(ln_w), _ptr(ln_b), C.c_float(eps), _ptr(y), _dt(y.dtype),
+                                         n, h, wd, cin, cout, _stream()), "vg_conv3x3s2_ln_gelu")
+    return y
+
+
+def bilinear(x: torch.Tensor, oh: int, ow: int, *, mode: int = 0, scale: float = 1.0, bias: float = 0.0) -> torch.Tensor:
+    """x [n, ih, iw] fp32 -> [n, oh, ow] fp32 (mode 0/1/2) or uint8 (mode 3: x > 0)"""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
+    n, ih, iw = x.shape
+    y = torch.empty((n, oh, ow), device=x.device, dtype=torch.uint8 if mode == 3 else torch.float32)
+    L.check(L.lib().vg_bilinear(_ptr(x), _ptr(y), n, ih, iw, oh, ow, mode, C.c_float(scale), C.c_float(bias), _stream()), "vg_bilinear")
+    return y
+
+
+def rope2d_(x: torch.Tensor, dim: int, gw: int, gh: int) -> torch.Tensor:
+    """in place on bf16 [rows, >=dim] (row stride arbitrary)"""
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    L.check(L.lib().vg_rope2d(_ptr(x), C.c_longlong(x.stride(0)), x.shape[0], dim, gw, gh, _stream()), "vg_rope2d")
+    return x
+
+
+def rope_neox_(qkv: torch.Tensor, pos: torch.Tensor, n_heads_total: int, head_dim: int, theta: float) -> torch.Tensor:
+    _require_cuda(qkv, pos)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and pos.dtype == torch.int32
+    L.check(L.lib().vg_rope_neox(_ptr(qkv), C.c_longlong(qkv.stride(0)), _ptr(pos), qkv.shape[0], n_heads_total, head_dim, C.c_float(theta),
+                                 _stream()), "vg_rope_neox")
+    return qkv
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+    _require_cuda(table, ids)
+    assert table.dtype == torch.bfloat16 and ids.dtype == torch.int64 and ids.is_contiguous() and table.stride(1) == 1
+    out = torch.empty((ids.numel(), table.shape[1]), device=table.device, dtype=out_dtype)
+    L.check(L.lib().vg_embedding(_ptr(table), C.c_longlong(table.stride(0)), _ptr(ids), _ptr(out), _dt(out.dtype), C.c_longlong(table.shape[1]),
+                                 ids.numel(), table.shape[1], _stream()), "vg_embedding")
+    return out
+
+
+def argmax(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1
+    out = torch.empty((x.shape[0],), device=x.device, dtype=torch.int64)
+    L.check(L.lib().vg_argmax(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), _ptr(out), x.shape[0], x.shape[1], _stream()), "vg_argmax")
+    return out
