@@ -58,7 +58,7 @@ typedef struct VgGemm {
   void* C; long long ldc; long long strideC;       /* out  [batch][M][ldc]   */
   int M, N, K, batch;
   int out_dtype;                                   /* VG_BF16 | VG_F32       */
-  const float* bias;                               /* [N] or NULL            */
+  const float* bias; long long strideBias;         /* [N] or NULL; per-batch stride (0 = shared) */
   int act;                                         /* VG_ACT_*               */
   int glu;                                         /* 0 | 1                  */
   const float* col_scale;                          /* [N_out] or NULL        */
@@ -103,11 +103,11 @@ int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, lon
             int rows, int cols, float eps, int rms, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ elementwise / layout
- * out[r][c] = a[r][c] + alpha * b[r % b_rows][c]   (b NULL: plain dtype cast). Row strides in elements.
+ * out[r][c] = a[r % a_rows][c] + alpha * b[r % b_rows][c]   (b NULL: plain dtype cast). Row strides in elements.
  * Covers q = queries + query_pe / k = keys + key_pe (.../sam/transformer.py:160-193), + pos_embed, + no_mem_embed
  * (.../sam2_base.py:641-645), curr + 0.1*curr_pos (.../memory_attention.py:140-141).
  */
-int vg_add(const void* a, int a_dtype, long long lda, const void* b, int b_dtype, long long ldb, int b_rows, float alpha,
+int vg_add(const void* a, int a_dtype, long long lda, int a_rows, const void* b, int b_dtype, long long ldb, int b_rows, float alpha,
            void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
 /* 2x2 max (is_max=1; Hiera q-pool, hieradet.py:21-33) or mean (is_max=0; arch.py:88-96 adaptive pooling by 2) over a
  * channels-last [n][h][w][c] grid; row stride of the input in elements (reads a column slice of a wider tensor). */
@@ -116,9 +116,10 @@ int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, 
 /* out[n][2y+dy][2x+dx][c] = lat[n][2y+dy][2x+dx][c] + top[n][y][x][c]  (FPN nearest top-down, image_encoder.py:115-126); fp32 */
 int vg_upsample2x_add(const float* lat, const float* top, float* out, int n, int h, int w, int c, void* stream);
 /* ConvTranspose2d(k=2,s=2) epilogue after the [n*h*w, 4*cout] GEMM (columns ordered (dy,dx,co)): pixel-shuffle, + bias[co],
- * + feat[n][2h][2w][cout] (may be NULL), optional LayerNorm2d(ln_w, ln_b, eps) then GELU. (mask_decoder.py:221-225) */
+ * + feat[n][2h][2w][cout] (may be NULL; feat_bcast=1: one [2h][2w][cout] map shared by all n), optional LayerNorm2d(ln_w, ln_b, eps)
+ * then GELU. (mask_decoder.py:221-225) */
 int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bias, const void* feat, int feat_dtype, const float* ln_w,
-                         const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, void* stream);
+                         const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, int feat_bcast, void* stream);
 /* im2col for Conv2d(kernel k, stride s, pad p) on NCHW fp32/bf16 input -> bf16 [n*oh*ow][kpad], column order (ci,ky,kx),
  * zero-filled to kpad (multiple of 8). Patch embeddings: Hiera 7x7/4 (backbones/utils.py:65-95), CLIP 14x14/14, IV2 1x14x14. */
 int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,

@@ -8,6 +8,7 @@ torch.Generator (identical on every machine), with NON-ZERO biases / norm offset
 from __future__ import annotations
 
 import math
+import re
 from collections import OrderedDict
 
 import torch
@@ -142,6 +143,10 @@ def sam2_param_shapes(cfg: Sam2Cfg) -> "OrderedDict[str, tuple]":
     return s
 
 
+_EMBED_RE = re.compile(r"(^|\.)(iou_token|mask_tokens|obj_score_token|not_a_point_embed|no_mask_embed|point_embeddings\.\d+|embed_tokens|"
+                       r"position_embedding|class_embedding|cls_token|\w*pos_embed\w*)(\.weight)?$")
+
+
 def _fill(name: str, shape: tuple, g: torch.Generator) -> torch.Tensor:
     """Deterministic values by parameter role."""
     leaf = name.rsplit(".", 1)[-1]
@@ -159,7 +164,7 @@ def _fill(name: str, shape: tuple, g: torch.Generator) -> torch.Tensor:
         return 0.1 + 0.05 * torch.randn(shape, generator=g)
     if leaf == "bias" or (len(shape) == 1):
         return 0.1 * torch.randn(shape, generator=g)
-    if len(shape) >= 2 and leaf == "weight" and "embed" not in name and "token" not in name:
+    if len(shape) >= 2 and leaf == "weight" and not _EMBED_RE.search(name):
         fan_in = math.prod(shape[1:]) if "output_upscaling" not in name else shape[0]
         bound = math.sqrt(3.0 / fan_in)
         return (torch.rand(shape, generator=g) * 2 - 1) * bound

@@ -1,0 +1,118 @@
+"""SAM2 engine (CUDA, bf16 operands / fp32 accumulate) vs the CPU fp32 oracle, stage by stage ON IDENTICAL INPUTS and end to end,
+on the shrunken Hiera config (true decoder/memory widths). Tolerances are relative L2 and reflect bf16 operand rounding
+(2^-9 per operand): one GEMM ~2e-3; stacks of them up to ~1e-2. Mask sign agreement is the integer-valued check."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import sam2 as O, weights as Wt  # noqa: E402  (checker only)
+from videoglamm_b200.config import Sam2Config  # noqa: E402
+from videoglamm_b200.sam2_engine import Sam2Engine  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def tok(x):
+    return x[0].permute(1, 2, 0).reshape(-1, x.shape[1])
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    ocfg, ecfg = O.Sam2Cfg(**O.TINY), Sam2Config(**O.TINY)
+    sd = Wt.make_sam2_state_dict(ocfg, 1234)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}  # matrices bf16-representable on both sides
+    eng = Sam2Engine(sd, ecfg)
+    torch.manual_seed(5678)
+    images = torch.randn(3, 3, ocfg.image_size, ocfg.image_size)
+    text = torch.randn(2, 1, 256)
+    fpn, pos = O.forward_image(sd, ocfg, images[:1])
+    return dict(ocfg=ocfg, sd=sd, eng=eng, images=images, text=text, fpn=fpn, pos=pos)
+
+
+def test_image_encoder(ctx):
+    f = ctx["eng"].forward_image(ctx["images"][:1].cuda())
+    assert rel(f["s0"], tok(ctx["fpn"][0])) < 1e-2
+    assert rel(f["s1"], tok(ctx["fpn"][1])) < 1e-2
+    assert rel(f["top"], tok(ctx["fpn"][2])) < 1e-2
+
+
+def test_constant_tables(ctx):
+    eng, ocfg, sd = ctx["eng"], ctx["ocfg"], ctx["sd"]
+    assert rel(eng.dense_pe, tok(O.dense_pe(sd, ocfg))) < 1e-6
+    assert rel(eng.pos_top, tok(ctx["pos"][2])) < 1e-6
+    assert rel(eng.pos_mem, O.pos_embed_sine((ocfg.feat_size,) * 2, ocfg.mem_dim).permute(1, 2, 0).reshape(-1, ocfg.mem_dim)) < 1e-6
+
+
+@pytest.mark.parametrize("with_text", [True, False])
+def test_mask_decoder(ctx, with_text):
+    ocfg, sd, eng, fpn = ctx["ocfg"], ctx["sd"], ctx["eng"], ctx["fpn"]
+    B = 2
+    pix = (fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)).expand(B, -1, -1, -1)
+    sparse, dense = O.prompt_encode(sd, ocfg, B, ctx["text"] if with_text else None)
+    hi = [fpn[0].expand(B, -1, -1, -1), fpn[1].expand(B, -1, -1, -1)]
+    om = O.mask_decoder(sd, ocfg, pix, O.dense_pe(sd, ocfg), sparse, dense, hi, True)
+    pix_tok = pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous()
+    em = eng.mask_decoder(pix_tok, tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(), sparse.cuda())
+    side = 4 * ocfg.feat_size
+    assert rel(em[0].view(B, 4, side, side), om[4]) < 1.5e-2
+    assert rel(em[1], om[5]) < 5e-3
+    assert rel(em[3], om[3]) < 1e-2
+    oh = O.forward_sam_heads(sd, ocfg, pix, hi, text_inputs=ctx["text"] if with_text else None)
+    eh = eng.forward_sam_heads(pix_tok, tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(),
+                               ctx["text"].cuda() if with_text else None, B)
+    assert rel(eh["low_res_masks"], oh["low_res_masks"][:, 0]) < 1.5e-2
+    assert rel(eh["obj_ptr"], oh["obj_ptr"]) < 1e-2
+
+
+def test_no_object_branch(ctx):
+    """object_score_logits <= 0 -> NO_OBJ_SCORE masks and no_obj_ptr (sam2_base.py:355-364, 389-401)."""
+    ocfg, fpn = ctx["ocfg"], ctx["fpn"]
+    sd = dict(ctx["sd"])
+    sd["sam_mask_decoder.pred_obj_score_head.layers.2.bias"] = sd["sam_mask_decoder.pred_obj_score_head.layers.2.bias"] - 100.0
+    eng = Sam2Engine(sd, Sam2Config(**O.TINY))
+    pix = fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)
+    oh = O.forward_sam_heads(sd, ocfg, pix, fpn[:2], text_inputs=ctx["text"][:1])
+    eh = eng.forward_sam_heads(tok(pix).cuda().contiguous(), tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(),
+                               ctx["text"][:1].cuda(), 1)
+    assert torch.all(eh["low_res_masks"] == O.NO_OBJ_SCORE) and torch.all(oh["low_res_masks"] == O.NO_OBJ_SCORE)
+    assert rel(eh["obj_ptr"], oh["obj_ptr"]) < 1e-6
+
+
+@pytest.mark.parametrize("binarize", [True, False])
+def test_memory_encoder(ctx, binarize):
+    ocfg, sd, eng, fpn = ctx["ocfg"], ctx["sd"], ctx["eng"], ctx["fpn"]
+    torch.manual_seed(1)
+    low = torch.randn(2, 1, 4 * ocfg.feat_size, 4 * ocfg.feat_size) * 4
+    high = F.interpolate(low, size=(ocfg.image_size,) * 2, mode="bilinear", align_corners=False)
+    mf, _ = O.encode_new_memory(sd, ocfg, fpn[2].expand(2, -1, -1, -1), high, is_mask_from_pts=binarize)
+    emf = eng.encode_memory(tok(fpn[2]).cuda().contiguous(), low[:, 0].cuda().contiguous(), binarize=binarize)
+    assert rel(emf, mf.permute(0, 2, 3, 1).reshape(2, -1, ocfg.mem_dim)) < 1e-2
+
+
+def test_memory_attention(ctx):
+    ocfg, sd, eng, fpn, pos = ctx["ocfg"], ctx["sd"], ctx["eng"], ctx["fpn"], ctx["pos"]
+    B, n_ptr = 2, 8
+    Nk = 2 * eng.HW + n_ptr
+    torch.manual_seed(2)
+    mem = torch.randn(Nk, B, 64).bfloat16().float()
+    mpos = torch.randn(Nk, 1, 64).expand(-1, B, -1)
+    oma = O.memory_attention(sd, ocfg, O._flat(fpn[2]).expand(-1, B, -1), O._flat(pos[2]).expand(-1, B, -1), mem, mpos, n_ptr)
+    ema = eng.memory_attention(tok(fpn[2]).cuda().contiguous(), B, mem.permute(1, 0, 2).contiguous().cuda().bfloat16(), mpos[:, 0].contiguous().cuda(), n_ptr)
+    assert rel(ema.view(B, eng.HW, 256), oma.permute(1, 0, 2)) < 5e-3
+
+
+def test_video_session_end_to_end(ctx):
+    ocfg, sd, eng = ctx["ocfg"], ctx["sd"], ctx["eng"]
+    ref = O.run_video(sd, ocfg, ctx["images"], ctx["text"], (60, 100))
+    got = eng.run_video(ctx["images"].cuda(), ctx["text"].cuda(), (60, 100))
+    gotb = eng.run_video(ctx["images"].cuda(), ctx["text"].cuda(), (60, 100), binary=True)
+    for t in range(len(ref)):
+        a, b = got[t].cpu(), ref[t][:, 0]
+        assert rel(a, b) < 2.5e-2, (t, rel(a, b))
+        assert ((a > 0) == (b > 0)).float().mean() > 0.99
+        assert torch.equal(gotb[t].cpu().bool(), a > 0)

@@ -22,7 +22,7 @@ class VgGemm(C.Structure):
         ("C", C.c_void_p), ("ldc", C.c_longlong), ("strideC", C.c_longlong),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
         ("out_dtype", C.c_int),
-        ("bias", C.c_void_p),
+        ("bias", C.c_void_p), ("strideBias", C.c_longlong),
         ("act", C.c_int), ("glu", C.c_int),
         ("col_scale", C.c_void_p),
         ("resid", C.c_void_p), ("ldr", C.c_longlong), ("strideR", C.c_longlong), ("resid_dtype", C.c_int),

@@ -34,6 +34,7 @@ struct GemmParams {
   long long ldc, strideC;
   int out_f32;
   const float* bias;
+  long long strideBias;
   int act, glu;
   const float* col_scale;
   const void* resid;
@@ -184,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+            if (col0 + j < p.N) v[j] += __ldg(p.bias + b * p.strideBias + col0 + j);
         }
         int ocol0, nvals;
         if (p.glu) {
@@ -282,7 +283,7 @@ __global__ void gemm_naive_kernel(const __nv_bfloat16* A, long long lda, long lo
     float acc = 0.f;
     for (int k = 0; k < p.K; ++k) acc = fmaf(__bfloat162float(a[k]), __bfloat162float(w[k]), acc);
     acc *= p.alpha;
-    if (p.bias) acc += p.bias[n];
+    if (p.bias) acc += p.bias[b * p.strideBias + n];
     return acc;
   };
   float v;
@@ -401,7 +402,7 @@ static GemmParams to_params(const VgGemm* g) {
   p.tiles_m = 0; p.tiles_n = 0;
   p.C = g->C; p.ldc = g->ldc; p.strideC = g->strideC;
   p.out_f32 = g->out_dtype == VG_F32;
-  p.bias = g->bias; p.act = g->act; p.glu = g->glu; p.col_scale = g->col_scale;
+  p.bias = g->bias; p.strideBias = g->strideBias; p.act = g->act; p.glu = g->glu; p.col_scale = g->col_scale;
   p.resid = g->resid; p.ldr = g->ldr; p.strideR = g->strideR; p.resid_f32 = g->resid_dtype == VG_F32;
   p.alpha = g->alpha;
   return p;

@@ -57,13 +57,13 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
 }
 
 // ------------------------------------------------------------------------------------------------ add / cast
-__global__ void add_kernel(const void* a, int adt, long long lda, const void* b, int bdt, long long ldb, int b_rows, float alpha, void* out,
+__global__ void add_kernel(const void* a, int adt, long long lda, int a_rows, const void* b, int bdt, long long ldb, int b_rows, float alpha, void* out,
                            int odt, long long ldo, long long rows, int cols) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= rows * cols) return;
   const long long r = i / cols;
   const int c = static_cast<int>(i - r * cols);
-  float v = ld(a, adt, r * lda + c);
+  float v = ld(a, adt, (r % a_rows) * lda + c);
   if (b) v += alpha * ld(b, bdt, (r % b_rows) * ldb + c);
   st(out, odt, r * ldo + c, v);
 }
@@ -100,7 +100,7 @@ __global__ void upsample2x_add_kernel(const float* lat, const float* top, float*
 
 // one warp per output pixel; cout <= 128 (4 values per lane)
 __global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bias, const void* feat, int fdt, const float* ln_w,
-                                         const float* ln_b, float eps, void* out, int odt, int n, int h, int w, int cout) {
+                                         const float* ln_b, float eps, void* out, int odt, int n, int h, int w, int cout, int feat_bcast) {
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int H = 2 * h, W = 2 * w;
@@ -118,7 +118,7 @@ __global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bi
     v[i] = 0.f;
     if (c < cout) {
       v[i] = ld(g, gdt, src_row * (4LL * cout) + sub * cout + c) + bias[c];
-      if (feat) v[i] += ld(feat, fdt, pix * cout + c);
+      if (feat) v[i] += ld(feat, fdt, (feat_bcast ? pix % (static_cast<long long>(H) * W) : pix) * cout + c);
       sum += v[i];
     }
   }
@@ -363,10 +363,10 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
   return check_launch("norm_kernel");
 }
 
-extern "C" int vg_add(const void* a, int a_dtype, long long lda, const void* b, int b_dtype, long long ldb, int b_rows, float alpha, void* out,
+extern "C" int vg_add(const void* a, int a_dtype, long long lda, int a_rows, const void* b, int b_dtype, long long ldb, int b_rows, float alpha, void* out,
                       int out_dtype, long long ldo, int rows, int cols, void* stream) {
-  if (!a || !out || rows <= 0 || cols <= 0 || (b && b_rows <= 0)) return set_error(VG_EINVAL, "vg_add: bad argument");
-  add_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(a, a_dtype, lda, b, b_dtype, ldb, b_rows, alpha, out,
+  if (!a || !out || rows <= 0 || cols <= 0 || a_rows <= 0 || (b && b_rows <= 0)) return set_error(VG_EINVAL, "vg_add: bad argument");
+  add_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(a, a_dtype, lda, a_rows, b, b_dtype, ldb, b_rows, alpha, out,
                                                                                         out_dtype, ldo, rows, cols);
   count_launch();
   return check_launch("add_kernel");
@@ -389,11 +389,11 @@ extern "C" int vg_upsample2x_add(const float* lat, const float* top, float* out,
 }
 
 extern "C" int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bias, const void* feat, int feat_dtype, const float* ln_w,
-                                    const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, void* stream) {
+                                    const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, int feat_bcast, void* stream) {
   if (!g || !bias || !out || cout > 128) return set_error(VG_EINVAL, "vg_convt2x2_epilogue: bad argument (cout <= 128)");
   const long long pix = static_cast<long long>(n) * 4 * h * w;
   convt2x2_epilogue_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(g, g_dtype, bias, feat, feat_dtype, ln_w, ln_b, eps, out, out_dtype, n, h, w,
-                                                                    cout);
+                                                                    cout, feat_bcast);
   count_launch();
   return check_launch("convt2x2_epilogue_kernel");
 }

@@ -58,8 +58,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
     g.M, g.N, g.K, g.batch = M, N, K, Bt
     g.out_dtype = _dt(out.dtype)
     if bias is not None:
-        assert bias.dtype == torch.float32 and bias.numel() == N and bias.is_contiguous()
-        g.bias = bias.data_ptr()
+        assert bias.dtype == torch.float32 and bias.is_contiguous() and bias.numel() in (N, Bt * N)
+        g.bias, g.strideBias = bias.data_ptr(), (N if bias.numel() == Bt * N and Bt > 1 else 0)
     g.act = L.ACT[act]
     g.glu = int(glu)
     if col_scale is not None:
@@ -136,23 +136,25 @@ def norm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None = None, *, eps
 
 
 def add(a: torch.Tensor, b: torch.Tensor | None = None, *, alpha: float = 1.0, out_dtype: torch.dtype | None = None,
-        out: torch.Tensor | None = None) -> torch.Tensor:
-    """out = a + alpha*b, b broadcast over leading rows (b rows must divide a rows: out[r] uses b[r % b_rows]). b=None casts."""
+        out: torch.Tensor | None = None, rows: int | None = None) -> torch.Tensor:
+    """out[r] = a[r % a_rows] + alpha*b[r % b_rows] (2D after flattening leading dims). b=None casts. `rows` > a rows tiles a."""
     _require_cuda(a, b, out)
     cols = a.shape[-1]
     a2 = a.reshape(-1, cols) if a.is_contiguous() else a
     assert a2.dim() == 2 and a2.stride(1) == 1
+    n_rows = rows or a2.shape[0]
+    assert n_rows % a2.shape[0] == 0
     if out is None:
-        out = torch.empty(a.shape, device=a.device, dtype=out_dtype or a.dtype)
+        out = torch.empty(a.shape if n_rows == a2.shape[0] else (n_rows, cols), device=a.device, dtype=out_dtype or a.dtype)
     o2 = out.reshape(-1, cols) if out.is_contiguous() else out
     if b is not None:
         b2 = b.reshape(-1, cols) if b.is_contiguous() else b
-        assert b2.dim() == 2 and b2.stride(1) == 1 and a2.shape[0] % b2.shape[0] == 0
+        assert b2.dim() == 2 and b2.stride(1) == 1 and n_rows % b2.shape[0] == 0
         bargs = (_ptr(b2), _dt(b2.dtype), C.c_longlong(b2.stride(0)), b2.shape[0])
     else:
         bargs = (None, 0, C.c_longlong(0), 1)
-    L.check(L.lib().vg_add(_ptr(a2), _dt(a2.dtype), C.c_longlong(a2.stride(0)), *bargs, C.c_float(alpha), _ptr(o2), _dt(o2.dtype),
-                           C.c_longlong(o2.stride(0)), a2.shape[0], cols, _stream()), "vg_add")
+    L.check(L.lib().vg_add(_ptr(a2), _dt(a2.dtype), C.c_longlong(a2.stride(0)), a2.shape[0], *bargs, C.c_float(alpha), _ptr(o2), _dt(o2.dtype),
+                           C.c_longlong(o2.stride(0)), n_rows, cols, _stream()), "vg_add")
     return out
 
 
@@ -181,12 +183,12 @@ def upsample2x_add(lat: torch.Tensor, top: torch.Tensor, n: int, h: int, w: int)
 
 
 def convt2x2_epilogue(g: torch.Tensor, bias: torch.Tensor, feat: torch.Tensor | None, ln_w, ln_b, eps: float, n: int, h: int, w: int,
-                      cout: int, out_dtype=torch.bfloat16) -> torch.Tensor:
+                      cout: int, out_dtype=torch.bfloat16, feat_bcast: bool = False) -> torch.Tensor:
     _require_cuda(g, bias, feat)
     assert g.is_contiguous() and g.shape[-1] == 4 * cout and (feat is None or feat.is_contiguous())
     out = torch.empty((n * 4 * h * w, cout), device=g.device, dtype=out_dtype)
     L.check(L.lib().vg_convt2x2_epilogue(_ptr(g), _dt(g.dtype), _ptr(bias), _ptr(feat), _dt(feat.dtype) if feat is not None else 0, _ptr(ln_w),
-                                         _ptr(ln_b), C.c_float(eps), _ptr(out), _dt(out.dtype), n, h, w, cout, _stream()), "vg_convt2x2_epilogue")
+                                         _ptr(ln_b), C.c_float(eps), _ptr(out), _dt(out.dtype), n, h, w, cout, int(feat_bcast), _stream()), "vg_convt2x2_epilogue")
     return out
 
 

@@ -1,0 +1,450 @@
+"""B200 engine for the SAM2 side of VideoGLaMM's grounded-generation path: Hiera-L + FPN image encoder, prompt encoder,
+TwoWay-transformer mask decoder, memory encoder, RoPE memory attention and the per-video tracking session.
+
+Host orchestration only — every tensor operation on activations is a libvglamm kernel (videoglamm_b200.ops). Weights are
+taken from a state_dict with the reference's keys (`model.visual_model.` prefix stripped by the caller).
+Layout: all activations are channels-last token matrices [tokens, C]; residual streams fp32, GEMM operands bf16.
+
+Reference call sites are cited per method (paths relative to VideoGLaMM/model/segment_anything_2/sam2/).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .config import Sam2Config
+
+NO_OBJ_SCORE = -1024.0
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class _Lin:
+    w: torch.Tensor  # bf16 [N, K]
+    b: torch.Tensor | None  # fp32 [N]
+
+
+@dataclass
+class FrameMem:
+    pred_masks: torch.Tensor          # [B, 256, 256] fp32 low-res logits
+    obj_ptr: torch.Tensor             # [B, C] fp32
+    maskmem: torch.Tensor | None      # [B, HW, mem_dim] bf16
+
+
+class Sam2Engine:
+    def __init__(self, sd: dict, cfg: Sam2Config | None = None, device: str = "cuda", prefix: str = ""):
+        self.cfg = cfg or Sam2Config()
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("Sam2Engine needs a CUDA device (there is no CPU path)")
+        self._sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+        self._pack()
+        del self._sd
+
+    # ------------------------------------------------------------------------------------------------ weight packing
+    def _t(self, k):
+        return self._sd[k].detach().to(self.dev, F32)
+
+    def _lin(self, p) -> _Lin:
+        w = self._t(p + ".weight")
+        w = w.reshape(w.shape[0], -1)
+        b = self._sd.get(p + ".bias")
+        return _Lin(w.to(BF).contiguous(), None if b is None else b.detach().to(self.dev, F32).contiguous())
+
+    def _ln(self, p):
+        return self._t(p + ".weight").contiguous(), self._t(p + ".bias").contiguous()
+
+    def _attn_w(self, p):
+        return {n: self._lin(f"{p}.{n}_proj") for n in ("q", "k", "v", "out")}
+
+    def _pack(self):
+        cfg, t = self.cfg, "image_encoder.trunk"
+        C = cfg.d_model
+        # Hiera patch embedding (backbones/utils.py:65-95): [C,3,7,7] -> [C,147] padded to K=152
+        w = self._t(t + ".patch_embed.proj.weight").reshape(cfg.embed_dim, -1)
+        self.pe_kpad = (w.shape[1] + 7) // 8 * 8
+        wp = torch.zeros(cfg.embed_dim, self.pe_kpad, device=self.dev)
+        wp[:, : w.shape[1]] = w
+        self.patch = _Lin(wp.to(BF).contiguous(), self._t(t + ".patch_embed.proj.bias"))
+        # Hiera._get_pos_embed (backbones/hieradet.py:269-277): constant of the weights, folded at load time
+        g = cfg.image_size // 4
+        pe = F.interpolate(self._t(t + ".pos_embed"), size=(g, g), mode="bicubic")
+        win = self._t(t + ".pos_embed_window")
+        pe = pe + win.tile([x // y for x, y in zip(pe.shape, win.shape)])
+        self.hiera_pos = pe.permute(0, 2, 3, 1).reshape(g * g, cfg.embed_dim).contiguous()
+        self.blocks = []
+        for i, (dim, dim_out, heads, window, qs) in enumerate(cfg.block_specs()):
+            b = f"{t}.blocks.{i}"
+            blk = dict(n1=self._ln(b + ".norm1"), qkv=self._lin(b + ".attn.qkv"), proj=self._lin(b + ".attn.proj"), n2=self._ln(b + ".norm2"),
+                       fc1=self._lin(b + ".mlp.layers.0"), fc2=self._lin(b + ".mlp.layers.1"), spec=(dim, dim_out, heads, window, qs))
+            if dim != dim_out:
+                blk["dproj"] = self._lin(b + ".proj")
+            self.blocks.append(blk)
+        # FPN neck (backbones/image_encoder.py:101-133), scalp=1, top-down only into level 2. Levels 0/1 feed only conv_s0/conv_s1
+        # (sam2_base.py:465-477): two chained 1x1 convs with no nonlinearity between them are folded into one at load time (fp32).
+        neck = [self._lin(f"image_encoder.neck.convs.{j}.conv") for j in range(4)]  # j -> stage 3-j
+        self.neck3, self.neck2 = neck[0], neck[1]
+
+        def fold(outer: str, inner: _Lin):
+            wo, bo = self._t(outer + ".weight").reshape(-1, C), self._t(outer + ".bias")
+            return _Lin((wo @ inner.w.float()).to(BF).contiguous(), (wo @ inner.b + bo).contiguous())
+
+        w2 = self._t("image_encoder.neck.convs.2.conv.weight").reshape(C, -1)
+        w3 = self._t("image_encoder.neck.convs.3.conv.weight").reshape(C, -1)
+        self.s1 = fold("sam_mask_decoder.conv_s1", _Lin(w2, self._t("image_encoder.neck.convs.2.conv.bias")))
+        self.s0 = fold("sam_mask_decoder.conv_s0", _Lin(w3, self._t("image_encoder.neck.convs.3.conv.bias")))
+        fs = cfg.feat_size
+        self.HW = fs * fs
+        self.pos_top = self._sine_pos(fs, fs, C)              # [HW, C] vision_pos_enc of the top level
+        self.pos_mem = self._sine_pos(fs, fs, cfg.mem_dim)    # [HW, mem_dim] maskmem_pos_enc
+        tpos = self._t("maskmem_tpos_enc").reshape(cfg.num_maskmem, cfg.mem_dim)
+        self.mem_pos_slot = (self.pos_mem[None] + tpos[:, None]).contiguous()  # [7, HW, mem_dim] (sam2_base.py:577-581)
+        self.no_mem_embed = self._t("no_mem_embed").reshape(1, C).contiguous()
+        self.no_obj_ptr = self._t("no_obj_ptr").reshape(1, C)
+        # prompt encoder constants (sam/prompt_encoder.py:68-77,192-229)
+        gm = self._t("sam_prompt_encoder.pe_layer.positional_encoding_gaussian_matrix")
+        grid = torch.ones((fs, fs), device=self.dev)
+        yy, xx = (grid.cumsum(0) - 0.5) / fs, (grid.cumsum(1) - 0.5) / fs
+        cc = 2 * math.pi * ((2 * torch.stack([xx, yy], -1) - 1) @ gm)
+        self.dense_pe = torch.cat([cc.sin(), cc.cos()], -1).reshape(self.HW, C).contiguous()
+        self.not_a_point = self._t("sam_prompt_encoder.not_a_point_embed.weight")
+        self.no_mask_embed = self._t("sam_prompt_encoder.no_mask_embed.weight").reshape(1, C).contiguous()
+        # mask decoder
+        md = "sam_mask_decoder"
+        self.out_tokens = torch.cat([self._t(md + ".obj_score_token.weight"), self._t(md + ".iou_token.weight"), self._t(md + ".mask_tokens.weight")], 0)
+        self.dec_layers = []
+        for i in range(cfg.dec_depth):
+            l = f"{md}.transformer.layers.{i}"
+            self.dec_layers.append(dict(sa=self._attn_w(l + ".self_attn"), t2i=self._attn_w(l + ".cross_attn_token_to_image"),
+                                        i2t=self._attn_w(l + ".cross_attn_image_to_token"), n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"),
+                                        n3=self._ln(l + ".norm3"), n4=self._ln(l + ".norm4"), fc1=self._lin(l + ".mlp.layers.0"),
+                                        fc2=self._lin(l + ".mlp.layers.1")))
+        self.dec_final = self._attn_w(md + ".transformer.final_attn_token_to_image")
+        self.dec_nf = self._ln(md + ".transformer.norm_final_attn")
+        # ConvTranspose2d weight [Cin, Cout, 2, 2] -> GEMM weight rows (dy,dx,co), cols ci (mask_decoder.py:66-77)
+        for name, key in (("up1", ".output_upscaling.0"), ("up2", ".output_upscaling.3")):
+            wt = self._t(md + key + ".weight")
+            setattr(self, name, _Lin(wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]).to(BF).contiguous(), self._t(md + key + ".bias")))
+        self.up_ln = self._ln(md + ".output_upscaling.1")
+        # 4 hypernetwork MLPs as batched GEMMs: [4, out, in] weights, [4, out] biases
+        self.hyper = []
+        for j in range(3):
+            ws = torch.stack([self._t(f"{md}.output_hypernetworks_mlps.{i}.layers.{j}.weight") for i in range(4)])
+            bs = torch.stack([self._t(f"{md}.output_hypernetworks_mlps.{i}.layers.{j}.bias") for i in range(4)])
+            self.hyper.append(_Lin(ws.to(BF).contiguous(), bs.contiguous()))
+        self.iou_head = [self._lin(f"{md}.iou_prediction_head.layers.{j}") for j in range(3)]
+        self.obj_head = [self._lin(f"{md}.pred_obj_score_head.layers.{j}") for j in range(3)]
+        self.obj_ptr_proj = [self._lin(f"obj_ptr_proj.layers.{j}") for j in range(3)]
+        # memory encoder (memory_encoder.py)
+        me = "memory_encoder"
+        self.ds = []
+        for j in range(4):
+            wt = self._t(f"{me}.mask_downsampler.encoder.{3 * j}.weight")  # [cout, cin, 3, 3]
+            self.ds.append(dict(w=wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]).contiguous(), b=self._t(f"{me}.mask_downsampler.encoder.{3 * j}.bias"),
+                                ln=self._ln(f"{me}.mask_downsampler.encoder.{3 * j + 1}"), cin=wt.shape[1], cout=wt.shape[0]))
+        self.ds_out = self._lin(f"{me}.mask_downsampler.encoder.12")
+        self.pix_proj = self._lin(me + ".pix_feat_proj")
+        self.fuser = []
+        for j in range(2):
+            l = f"{me}.fuser.layers.{j}"
+            self.fuser.append(dict(dw=self._t(l + ".dwconv.weight").reshape(C, 7, 7).contiguous(), dwb=self._t(l + ".dwconv.bias"), ln=self._ln(l + ".norm"),
+                                   pw1=self._lin(l + ".pwconv1"), pw2=self._lin(l + ".pwconv2"), gamma=self._t(l + ".weight").contiguous()))
+        self.mem_out = self._lin(me + ".out_proj")
+        # memory attention (memory_attention.py); self-attention q/k/v fused into one [3C, C] GEMM
+        self.ma_layers = []
+        for i in range(cfg.mem_attn_layers):
+            l = f"memory_attention.layers.{i}"
+            sa, ca = self._attn_w(l + ".self_attn"), self._attn_w(l + ".cross_attn_image")
+            qkv = _Lin(torch.cat([sa["q"].w, sa["k"].w, sa["v"].w]).contiguous(), torch.cat([sa["q"].b, sa["k"].b, sa["v"].b]).contiguous())
+            self.ma_layers.append(dict(qkv=qkv, sa_out=sa["out"], ca=ca, n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"), n3=self._ln(l + ".norm3"),
+                                       fc1=self._lin(l + ".linear1"), fc2=self._lin(l + ".linear2")))
+        self.ma_norm = self._ln("memory_attention.norm")
+
+    def _sine_pos(self, H, W, num_pos_feats):
+        """PositionEmbeddingSine (position_encoding.py:79-112): a constant table per feature size -> [H*W, C] fp32."""
+        npf = num_pos_feats // 2
+        y = torch.arange(1, H + 1, dtype=F32, device=self.dev).view(H, 1).repeat(1, W)
+        x = torch.arange(1, W + 1, dtype=F32, device=self.dev).view(1, W).repeat(H, 1)
+        y = y / (y[-1:, :] + 1e-6) * (2 * math.pi)
+        x = x / (x[:, -1:] + 1e-6) * (2 * math.pi)
+        dim_t = torch.arange(npf, dtype=F32, device=self.dev)
+        dim_t = 10000.0 ** (2 * (dim_t // 2) / npf)
+        px, py = x[:, :, None] / dim_t, y[:, :, None] / dim_t
+        px = torch.stack((px[:, :, 0::2].sin(), px[:, :, 1::2].cos()), dim=3).flatten(2)
+        py = torch.stack((py[:, :, 0::2].sin(), py[:, :, 1::2].cos()), dim=3).flatten(2)
+        return torch.cat((py, px), dim=2).reshape(H * W, num_pos_feats).contiguous()
+
+    # ------------------------------------------------------------------------------------------------ image encoder
+    def _hiera_block(self, x, blk, n, H, W):
+        """MultiScaleBlock.forward backbones/hieradet.py:136-168. x fp32 [n*H*W, dim] -> (fp32 [n*H'*W', dim_out], H', W')."""
+        dim, dim_out, heads, window, qs = blk["spec"]
+        hd = dim_out // heads
+        xn = ops.norm(x, *blk["n1"], eps=1e-6)
+        if dim != dim_out:
+            sc = ops.gemm(xn, blk["dproj"].w, bias=blk["dproj"].b, out_dtype=F32)
+            if qs:
+                sc = ops.pool2x2(sc, n, H, W, is_max=True)
+        else:
+            sc = x
+        qkv = ops.gemm(xn, blk["qkv"].w, bias=blk["qkv"].b)  # [rows, 3*dim_out] = (3, heads, hd)
+        rows = n * H * W
+        q, k, v = (qkv[:, j * dim_out:(j + 1) * dim_out].unflatten(1, (heads, hd)) for j in range(3))
+        Hq, Wq = H, W
+        if qs:
+            q = ops.pool2x2(qkv[:, :dim_out], n, H, W, is_max=True).unflatten(1, (heads, hd))
+            Hq, Wq = H // 2, W // 2
+        if window > 0:
+            wq = window // 2 if qs else window
+            nwx, nwy = W // window, H // window
+            o = ops.attention(q[None], k[None], v[None], scale=hd ** -0.5, q_win=(wq, Wq, nwx, nwy), k_win=(window, W, nwx, nwy))
+        else:
+            o = ops.attention(q.unflatten(0, (n, Hq * Wq)), k.unflatten(0, (n, H * W)), v.unflatten(0, (n, H * W)), scale=hd ** -0.5)
+        o = o.reshape(n * Hq * Wq, dim_out)
+        x = ops.gemm(o, blk["proj"].w, bias=blk["proj"].b, resid=sc, out_dtype=F32)
+        xn = ops.norm(x, *blk["n2"], eps=1e-6)
+        h = ops.gemm(xn, blk["fc1"].w, bias=blk["fc1"].b, act="gelu")
+        x = ops.gemm(h, blk["fc2"].w, bias=blk["fc2"].b, resid=x, out=x)
+        return x, Hq, Wq
+
+    def forward_image(self, img: torch.Tensor) -> dict:
+        """SAM2Base.forward_image sam2_base.py:465-477 (Hiera hieradet.py:279-295 + FpnNeck image_encoder.py:101-133 + conv_s0/s1).
+        img [n,3,S,S] fp32 -> {"s0": bf16 [n*(S/4)^2, 32], "s1": bf16 [n*(S/8)^2, 64], "top": fp32 [n*(S/16)^2, 256]}"""
+        cfg = self.cfg
+        n = img.shape[0]
+        assert img.shape[1:] == (3, cfg.image_size, cfg.image_size) and img.is_cuda
+        img = img.contiguous()
+        g = cfg.image_size // 4
+        x = torch.empty((n * g * g, cfg.embed_dim), device=self.dev, dtype=F32)
+        for i in range(n):  # pos-embed residual is per image
+            cols, _, _ = ops.im2col(img[i:i + 1], 7, 4, 3, self.pe_kpad)
+            ops.gemm(cols, self.patch.w, bias=self.patch.b, resid=self.hiera_pos, out=x[i * g * g:(i + 1) * g * g])
+        H = W = g
+        stage_out = []
+        ends = cfg.stage_ends
+        for i, blk in enumerate(self.blocks):
+            x, H, W = self._hiera_block(x, blk, n, H, W)
+            if i in ends:
+                stage_out.append((ops.cast(x, BF), H, W))
+        (x0, H0, W0), (x1, H1, W1), (x2, H2, W2), (x3, H3, W3) = stage_out
+        lat3 = ops.gemm(x3, self.neck3.w, bias=self.neck3.b, out_dtype=F32)
+        lat2 = ops.gemm(x2, self.neck2.w, bias=self.neck2.b, out_dtype=F32)
+        top = ops.upsample2x_add(lat2, lat3, n, H3, W3)
+        s1 = ops.gemm(x1, self.s1.w, bias=self.s1.b)
+        s0 = ops.gemm(x0, self.s0.w, bias=self.s0.b)
+        return dict(s0=s0, s1=s1, top=top)
+
+    # ------------------------------------------------------------------------------------------------ mask decoder
+    def _attn(self, w, q_in, k_in, v_in, B, Nq, Nk, resid=None):
+        """Attention.forward sam/transformer.py:233-260 on bf16 [B*N, C] inputs -> fp32 [B*Nq, C] (+ residual)."""
+        H = self.cfg.dec_heads
+        q = ops.gemm(q_in, w["q"].w, bias=w["q"].b)
+        k = ops.gemm(k_in, w["k"].w, bias=w["k"].b)
+        v = ops.gemm(v_in, w["v"].w, bias=w["v"].b)
+        d = q.shape[1] // H
+        o = ops.attention(q.view(B, Nq, H, d), k.view(B, Nk, H, d), v.view(B, Nk, H, d), scale=d ** -0.5)
+        return ops.gemm(o.view(B * Nq, H * d), w["out"].w, bias=w["out"].b, resid=resid, out_dtype=F32)
+
+    def _mlp3(self, layers, x_bf, final_act=None):
+        h = ops.gemm(x_bf, layers[0].w, bias=layers[0].b, act="relu")
+        h = ops.gemm(h, layers[1].w, bias=layers[1].b, act="relu")
+        return ops.gemm(h, layers[2].w, bias=layers[2].b, act=final_act, out_dtype=F32)
+
+    def mask_decoder(self, pix: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, sparse: torch.Tensor, debug: dict | None = None):
+        """PromptEncoder dense part + MaskDecoder.predict_masks (sam/mask_decoder.py:167-245), TwoWayTransformer
+        (sam/transformer.py:63-115, 160-193). pix fp32 [B*HW, C] image embedding (one row block per object), s0/s1 the
+        high-res maps of the ONE image shared by the B objects, sparse fp32 [B, Ns, C].
+        Returns all-4 masks fp32 [B,4,(4fs)^2], iou [B,4] (sigmoid), mask tokens fp32 [B,4,C], object score logits [B,1]."""
+        cfg, HW, C = self.cfg, self.HW, self.cfg.d_model
+        B = sparse.shape[0]
+        tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(-1, C).contiguous()
+        Nt = tokens.shape[0] // B
+        keys = ops.add(pix, self.no_mask_embed)                       # src = image_embeddings + dense (no_mask_embed)
+        queries = tokens
+        k_pe = v_k = None
+        for i, L in enumerate(self.dec_layers):
+            if i == 0:
+                qb = ops.cast(queries, BF)
+                queries = self._attn(L["sa"], qb, qb, qb, B, Nt, Nt)
+            else:
+                q = ops.add(queries, tokens, out_dtype=BF)
+                queries = self._attn(L["sa"], q, q, ops.cast(queries, BF), B, Nt, Nt, resid=queries)
+            queries = ops.norm(queries, *L["n1"], eps=1e-5, out_dtype=F32)
+            q = ops.add(queries, tokens, out_dtype=BF)
+            k_pe = ops.add(keys, self.dense_pe, out_dtype=BF)
+            v_k = ops.cast(keys, BF)
+            queries = ops.norm(self._attn(L["t2i"], q, k_pe, v_k, B, Nt, HW, resid=queries), *L["n2"], eps=1e-5, out_dtype=F32)
+            h = ops.gemm(ops.cast(queries, BF), L["fc1"].w, bias=L["fc1"].b, act="relu")
+            queries = ops.norm(ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=queries, out_dtype=F32), *L["n3"], eps=1e-5, out_dtype=F32)
+            q = ops.add(queries, tokens, out_dtype=BF)
+            keys = ops.norm(self._attn(L["i2t"], k_pe, q, ops.cast(queries, BF), B, HW, Nt, resid=keys), *L["n4"], eps=1e-5, out_dtype=F32)
+        q = ops.add(queries, tokens, out_dtype=BF)
+        k_pe = ops.add(keys, self.dense_pe, out_dtype=BF)
+        v_k = ops.cast(keys, BF)
+        queries = ops.norm(self._attn(self.dec_final, q, k_pe, v_k, B, Nt, HW, resid=queries), *self.dec_nf, eps=1e-5, out_dtype=F32)
+        hs = queries.view(B, Nt, C)
+        # upscaling: ConvT(k2,s2) as GEMM + pixel-shuffle epilogue (+feat_s1, LayerNorm2d, GELU), then again (+feat_s0, GELU)
+        fs = cfg.feat_size
+        g1 = ops.gemm(v_k, self.up1.w, out_dtype=F32)
+        up1 = ops.convt2x2_epilogue(g1, self.up1.b, s1, self.up_ln[0], self.up_ln[1], 1e-6, B, fs, fs, C // 4, feat_bcast=True)
+        g2 = ops.gemm(up1, self.up2.w, out_dtype=F32)
+        up2 = ops.convt2x2_epilogue(g2, self.up2.b, s0, None, None, 0.0, B, 2 * fs, 2 * fs, C // 8, feat_bcast=True)
+        # hypernetwork MLPs, batched over the 4 mask tokens
+        mt = hs[:, 2:6]                                                # [B,4,C]
+        h = ops.cast(mt.transpose(0, 1).contiguous(), BF)              # [4,B,C]
+        h = ops.gemm(h, self.hyper[0].w, bias=self.hyper[0].b, act="relu")
+        h = ops.gemm(h, self.hyper[1].w, bias=self.hyper[1].b, act="relu")
+        hyper_in = ops.gemm(h, self.hyper[2].w, bias=self.hyper[2].b).transpose(0, 1).contiguous()   # [B,4,C/8] bf16
+        masks = ops.gemm(hyper_in, up2.view(B, -1, C // 8), out_dtype=F32)                             # [B,4,(4fs)^2]
+        if debug is not None:
+            debug.update(hs=hs, keys=keys, up1=up1, up2=up2, hyper_in=hyper_in)
+        iou = self._mlp3(self.iou_head, ops.cast(hs[:, 1].contiguous(), BF), final_act="sigmoid")
+        obj = self._mlp3(self.obj_head, ops.cast(hs[:, 0].contiguous(), BF))
+        return masks, iou, mt, obj
+
+    def forward_sam_heads(self, pix, s0, s1, text_embeds: torch.Tensor | None, B: int):
+        """SAM2Base._forward_sam_heads sam2_base.py:251-411 for the prompt kinds on the VideoGLaMM path (padding points + optional
+        text token), multimask output with best-IoU selection."""
+        sparse = self.not_a_point[None].expand(B, 2, -1)
+        if text_embeds is not None:
+            sparse = torch.cat([sparse, text_embeds.to(F32)], dim=1)
+        masks, iou, mt, obj = self.mask_decoder(pix, s0, s1, sparse)
+        side = 4 * self.cfg.feat_size
+        masks, iou, toks = masks[:, 1:], iou[:, 1:], mt[:, 1:]
+        is_obj = obj > 0                                                                    # [B,1]
+        low_multi = torch.where(is_obj[:, :, None], masks, torch.full_like(masks, NO_OBJ_SCORE))
+        best = torch.argmax(iou, dim=-1)
+        bi = torch.arange(B, device=self.dev)
+        low = low_multi[bi, best].reshape(B, side, side).contiguous()
+        tok = toks[bi, best].contiguous()
+        ptr = self._mlp3(self.obj_ptr_proj, ops.cast(tok, BF))
+        lam = is_obj.float()
+        ptr = lam * ptr + (1 - lam) * self.no_obj_ptr
+        return dict(low_res_masks=low, obj_ptr=ptr, ious=iou, object_score_logits=obj, low_res_multimasks=low_multi.view(B, 3, side, side))
+
+    # ------------------------------------------------------------------------------------------------ memory encoder
+    def encode_memory(self, top: torch.Tensor, low_res_masks: torch.Tensor, binarize: bool) -> torch.Tensor:
+        """_encode_new_memory sam2_base.py:666-704 + MemoryEncoder.forward memory_encoder.py:159-182.
+        top fp32 [HW, C] (raw top-level feature of the frame), low_res_masks fp32 [B, 4fs, 4fs] -> maskmem bf16 [B, HW, mem_dim]."""
+        cfg, C = self.cfg, self.cfg.d_model
+        B, S = low_res_masks.shape[0], cfg.image_size
+        m = ops.bilinear(low_res_masks, S, S, mode=2 if binarize else 1, scale=cfg.sigmoid_scale_for_mem_enc, bias=cfg.sigmoid_bias_for_mem_enc)
+        m = m.view(B * S * S, 1)
+        side = S
+        for j, d in enumerate(self.ds):
+            m = ops.conv3x3s2_ln_gelu(m, d["w"], d["b"], d["ln"][0], d["ln"][1], 1e-6, B, side, side, d["cin"], d["cout"],
+                                      out_dtype=BF if j == 3 else F32)
+            side //= 2
+        m = ops.gemm(m, self.ds_out.w, bias=self.ds_out.b, out_dtype=F32)                                # [B*HW, C]
+        px = ops.gemm(ops.cast(top, BF), self.pix_proj.w, bias=self.pix_proj.b, out_dtype=F32)           # [HW, C] shared by objects
+        x = ops.add(m, px)
+        fs = cfg.feat_size
+        for f in self.fuser:
+            y = ops.dwconv(x, f["dw"], f["dwb"], B, fs, fs, 7)
+            yn = ops.norm(y, *f["ln"], eps=1e-6)
+            h = ops.gemm(yn, f["pw1"].w, bias=f["pw1"].b, act="gelu")
+            x = ops.gemm(h, f["pw2"].w, bias=f["pw2"].b, col_scale=f["gamma"], resid=x, out=x)
+        out = ops.gemm(ops.cast(x, BF), self.mem_out.w, bias=self.mem_out.b)                              # bf16 (sam2_video_predictor.py:967)
+        return out.view(B, self.HW, cfg.mem_dim)
+
+    # ------------------------------------------------------------------------------------------------ memory attention
+    def memory_attention(self, top: torch.Tensor, B: int, memory: torch.Tensor, mem_pos: torch.Tensor, n_ptr_tokens: int) -> torch.Tensor:
+        """MemoryAttention.forward memory_attention.py:119-169 / MemoryAttentionLayer :58-99 / RoPEAttention sam/transformer.py:285-327.
+        top fp32 [HW, C]; memory bf16 [B, Nk, mem_dim]; mem_pos fp32 [Nk, mem_dim] (shared by objects) -> fp32 [B*HW, C]."""
+        cfg, C, HW = self.cfg, self.cfg.d_model, self.HW
+        fs = cfg.feat_size
+        Nk = memory.shape[1]
+        n_rope = Nk - n_ptr_tokens
+        x = ops.add(top, self.pos_top, alpha=0.1, rows=B * HW)                                           # curr + 0.1*curr_pos, tiled over objects
+        mem2 = memory.reshape(B * Nk, cfg.mem_dim)
+        k_in = ops.add(mem2, mem_pos, out_dtype=BF)
+        for L in self.ma_layers:
+            t = ops.norm(x, *L["n1"], eps=1e-5)
+            qkv = ops.gemm(t, L["qkv"].w, bias=L["qkv"].b)                                                 # [B*HW, 3C]
+            ops.rope2d_(qkv[:, :C], C, fs, fs)
+            ops.rope2d_(qkv[:, C:2 * C], C, fs, fs)
+            q, k, v = (qkv[:, j * C:(j + 1) * C].view(B, HW, 1, C) for j in range(3))
+            o = ops.attention(q, k, v, scale=C ** -0.5)
+            x = ops.gemm(o.view(B * HW, C), L["sa_out"].w, bias=L["sa_out"].b, resid=x, out=x)
+            t = ops.norm(x, *L["n2"], eps=1e-5)
+            ca = L["ca"]
+            q = ops.gemm(t, ca["q"].w, bias=ca["q"].b)
+            ops.rope2d_(q, C, fs, fs)
+            kk = ops.gemm(k_in, ca["k"].w, bias=ca["k"].b).view(B, Nk, C)
+            for b in range(B):
+                ops.rope2d_(kk[b, :n_rope], C, fs, fs)                                                    # rope_k_repeat: position = row % HW
+            vv = ops.gemm(mem2, ca["v"].w, bias=ca["v"].b)
+            o = ops.attention(q.view(B, HW, 1, C), kk.view(B, Nk, 1, C), vv.view(B, Nk, 1, C), scale=C ** -0.5)
+            x = ops.gemm(o.view(B * HW, C), ca["out"].w, bias=ca["out"].b, resid=x, out=x)
+            t = ops.norm(x, *L["n3"], eps=1e-5)
+            h = ops.gemm(t, L["fc1"].w, bias=L["fc1"].b, act="relu")
+            x = ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=x, out=x)
+        return ops.norm(x, *self.ma_norm, eps=1e-5, out_dtype=F32)
+
+    def _memory_bank(self, t: int, cond: dict, non_cond: dict, num_frames: int, B: int):
+        """_prepare_memory_conditioned_features sam2_base.py:495-664 (forward tracking, stride 1): conditioning frame(s) at t_pos 0,
+        the 6 previous frames, then up to 16 object pointers split into C/mem_dim tokens each."""
+        cfg = self.cfg
+        mems, poss = [], []
+        sel = [(0, o) for o in cond.values()] + [(tp, non_cond.get(t - (cfg.num_maskmem - tp))) for tp in range(1, cfg.num_maskmem)]
+        for tp, prev in sel:
+            if prev is None:
+                continue
+            mems.append(prev.maskmem)
+            poss.append(self.mem_pos_slot[cfg.num_maskmem - tp - 1])
+        ptrs = [o.obj_ptr for ti, o in cond.items() if ti <= t]
+        for d in range(1, min(num_frames, cfg.max_obj_ptrs_in_encoder)):
+            if t - d < 0:
+                break
+            o = non_cond.get(t - d)
+            if o is not None:
+                ptrs.append(o.obj_ptr)
+        n_ptr = 0
+        if ptrs:
+            split = cfg.d_model // cfg.mem_dim
+            op = torch.stack(ptrs, dim=1).reshape(B, len(ptrs) * split, cfg.mem_dim)   # [B, P*4, mem_dim]
+            mems.append(op.to(BF))
+            poss.append(torch.zeros((op.shape[1], cfg.mem_dim), device=self.dev))
+            n_ptr = op.shape[1]
+        return torch.cat(mems, dim=1).contiguous(), torch.cat(poss, dim=0).contiguous(), n_ptr
+
+    # ------------------------------------------------------------------------------------------------ video session
+    @torch.no_grad()
+    def run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False, collect: dict | None = None):
+        """The VideoGLaMM video-branch session (VideoGLaMM.py:846-875 -> sam2_video_predictor.py init_state_from_tensor :109-180,
+        add_new_text :416-495 on frame 0 per object, propagate_in_video :745-827 incl. preflight :675-729).
+        images [T,3,S,S] fp32 cuda; text_embeds [n_obj,1,C]. Returns per frame [n_obj,H,W]: fp32 logits (binary=False) or uint8 (x>0)."""
+        cfg = self.cfg
+        T, B = images.shape[0], text_embeds.shape[0]
+        HW, C = self.HW, cfg.d_model
+        Hv, Wv = video_hw
+        feats = [self.forward_image(images[t:t + 1].float()) for t in range(T)]  # no temporal dependence: encode up front
+        f0 = feats[0]
+        pix0 = ops.add(f0["top"], self.no_mem_embed)                               # init cond frame: + no_mem_embed (sam2_base.py:641-645)
+        per_obj = [self.forward_sam_heads(pix0, f0["s0"], f0["s1"], text_embeds[o:o + 1], 1) for o in range(B)]
+        low = torch.cat([r["low_res_masks"] for r in per_obj], 0)
+        ptr = torch.cat([r["obj_ptr"] for r in per_obj], 0)
+        cond = {0: FrameMem(low, ptr, self.encode_memory(f0["top"], low, binarize=True))}
+        non_cond: dict[int, FrameMem] = {}
+        outs = []
+        for t in range(T):
+            if t in cond:
+                pred = cond[t].pred_masks
+            else:
+                f = feats[t]
+                memory, mem_pos, n_ptr = self._memory_bank(t, cond, non_cond, T, B)
+                pix = self.memory_attention(f["top"], B, memory, mem_pos, n_ptr)
+                r = self.forward_sam_heads(pix, f["s0"], f["s1"], None, B)
+                pred = r["low_res_masks"]
+                non_cond[t] = FrameMem(pred, r["obj_ptr"], self.encode_memory(f["top"], pred, binarize=False))
+                if collect is not None:
+                    collect.setdefault("pix_feat_with_mem", {})[t] = pix
+                for old in [k for k in non_cond if k < t - max(cfg.num_maskmem, cfg.max_obj_ptrs_in_encoder)]:
+                    non_cond[old].maskmem = None                                   # ring buffer: nothing older is ever read again
+            if collect is not None:
+                collect.setdefault("low_res", {})[t] = pred
+            outs.append(ops.bilinear(pred, Hv, Wv, mode=3 if binary else 0))
+        return outs
