@@ -10,6 +10,7 @@ literally; we stub the former and make the latter the identity. No reference sou
 from __future__ import annotations
 
 import importlib
+import importlib.machinery
 import os
 import re
 import sys
@@ -74,6 +75,7 @@ def install_shims() -> None:
 
     def mod(name, **attrs):
         m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)  # transformers probes find_spec() on optional deps
         m.__dict__.update(attrs)
         sys.modules[name] = m
         return m

@@ -183,3 +183,74 @@ def make_sam2_state_dict(cfg: Sam2Cfg, seed: int = 1234, obj_score_bias: float =
     sd = make_state_dict(sam2_param_shapes(cfg), seed)
     sd["sam_mask_decoder.pred_obj_score_head.layers.2.bias"] += obj_score_bias
     return sd
+
+
+def lmm_param_shapes(cfg) -> "OrderedDict[str, tuple]":
+    """Key -> shape for the LMM side of VideoGLaMMForCausalLM: Phi-3 (HF names), projectors,
+    text_hidden_fcs, InternVideo2 vision encoder (keys used at inference) and the HF CLIP vision tower."""
+    s: OrderedDict[str, tuple] = OrderedDict()
+    ph, cl, iv = cfg.phi, cfg.clip, cfg.iv2
+    H = ph.hidden
+    s["model.embed_tokens.weight"] = (ph.vocab, H)
+    for l in range(ph.layers):
+        p = f"model.layers.{l}"
+        s[p + ".self_attn.qkv_proj.weight"] = (3 * H, H)
+        s[p + ".self_attn.o_proj.weight"] = (H, H)
+        s[p + ".mlp.gate_up_proj.weight"] = (2 * ph.inter, H)
+        s[p + ".mlp.down_proj.weight"] = (H, ph.inter)
+        s[p + ".input_layernorm.weight"] = (H,)
+        s[p + ".post_attention_layernorm.weight"] = (H,)
+    s["model.norm.weight"] = (H,)
+    s["lm_head.weight"] = (ph.vocab, H)
+    for name, din in (("model.mm_projector", iv.width), ("model.image_mm_projector", cl.width)):
+        _lin(s, name + ".0", H, din)
+        for j in range(1, cfg.proj_depth):
+            _lin(s, f"{name}.{2 * j}", H, H)
+    _lin(s, "model.text_hidden_fcs.0.0", H, H)
+    _lin(s, "model.text_hidden_fcs.0.2", cfg.out_dim, H)
+    e = "model.vision_tower.vision_encoder"
+    g2 = iv.grid ** 2
+    s[e + ".cls_token"] = (1, 1, iv.width)
+    s[e + ".pos_embed"] = (1, 1 + iv.frames * g2, iv.width)
+    s[e + ".img_pos_embed"] = (1, 1 + g2, iv.width)
+    s[e + ".patch_embed.proj.weight"] = (iv.width, 3, 1, iv.patch, iv.patch)
+    s[e + ".patch_embed.proj.bias"] = (iv.width,)
+    for i in range(iv.depth):
+        b = f"{e}.blocks.{i}"
+        s[b + ".norm1.weight"] = (iv.width,)
+        s[b + ".attn.qkv.weight"] = (3 * iv.width, iv.width)
+        _lin(s, b + ".attn.proj", iv.width, iv.width)
+        s[b + ".attn.q_norm.weight"] = (iv.width,)
+        s[b + ".attn.k_norm.weight"] = (iv.width,)
+        s[b + ".ls1.gamma"] = (iv.width,)
+        s[b + ".norm2.weight"] = (iv.width,)
+        _lin(s, b + ".mlp.fc1", iv.mlp, iv.width)
+        _lin(s, b + ".mlp.fc2", iv.width, iv.mlp)
+        s[b + ".ls2.gamma"] = (iv.width,)
+    v = "model.image_vision_tower.vision_tower.vision_model"
+    s[v + ".embeddings.class_embedding"] = (cl.width,)
+    s[v + ".embeddings.patch_embedding.weight"] = (cl.width, 3, cl.patch, cl.patch)
+    s[v + ".embeddings.position_embedding.weight"] = (1 + cl.grid ** 2, cl.width)
+    _norm(s, v + ".pre_layrnorm", cl.width)
+    for i in range(cl.layers):
+        l = f"{v}.encoder.layers.{i}"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            _lin(s, f"{l}.self_attn.{n}", cl.width, cl.width)
+        _norm(s, l + ".layer_norm1", cl.width)
+        _lin(s, l + ".mlp.fc1", cl.mlp, cl.width)
+        _lin(s, l + ".mlp.fc2", cl.width, cl.mlp)
+        _norm(s, l + ".layer_norm2", cl.width)
+    _norm(s, v + ".post_layernorm", cl.width)
+    return s
+
+
+def make_lmm_state_dict(cfg, seed: int = 1234):
+    return make_state_dict(lmm_param_shapes(cfg), seed)
+
+
+def make_videoglamm_state_dict(lmm_cfg, sam_cfg: Sam2Cfg, seed: int = 1234, obj_score_bias: float = 4.0):
+    """Full VideoGLaMMForCausalLM state dict: LMM keys + SAM2 under `model.visual_model.` (VideoGLaMM.py:107-145)."""
+    sd = make_lmm_state_dict(lmm_cfg, seed)
+    for k, v in make_sam2_state_dict(sam_cfg, seed + 1, obj_score_bias).items():
+        sd["model.visual_model." + k] = v
+    return sd

@@ -1,0 +1,85 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference modules (imported from /root/reference through
+oracle/ref_harness.py; HF transformers classes for CLIP / Phi-3) on seeded synthetic weights and inputs.
+Run here (CPU, reference present):  python tests/golden/make_golden.py
+The fixtures travel to the GPU box; tests/test_oracle_golden.py checks oracle/*.py against them without the reference."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import lmm as M, ref_harness as H, sam2 as O, weights as Wt  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+SAM2_TINY_OVERRIDES = ["++model.image_size=256", "++model.image_encoder.trunk.embed_dim=32", "++model.image_encoder.trunk.stages=[1,2,3,1]",
+                       "++model.image_encoder.trunk.global_att_blocks=[4]", "++model.image_encoder.neck.backbone_channel_list=[256,128,64,32]",
+                       "++model.memory_attention.num_layers=2"]
+
+
+def ref_sam2(tiny=True):
+    H.install_shims()
+    from model.segment_anything_2.sam2.build_sam import build_sam2_video_predictor
+    ref = build_sam2_video_predictor("sam2_hiera_l.yaml", ckpt_path=None, device=None, hydra_overrides_extra=SAM2_TINY_OVERRIDES if tiny else []).float().eval()
+    return H.patch_predictor_cpu(ref)
+
+
+def sam2_video_golden():
+    cfg = O.Sam2Cfg(**O.TINY)
+    ref = ref_sam2()
+    out = {}
+    for name, bias, T, nobj in (("present", 4.0, 9, 2), ("absent", -100.0, 2, 1)):
+        sd = Wt.make_sam2_state_dict(cfg, 1234, obj_score_bias=bias)
+        ref.load_state_dict(sd, strict=True)
+        torch.manual_seed(5678)
+        images, text = torch.randn(T, 3, cfg.image_size, cfg.image_size), torch.randn(nobj, 1, 256)
+        with torch.inference_mode():
+            st = ref.init_state_from_tensor(images, 60, 100)
+            for o in range(nobj):
+                ref.add_new_text(st, 0, o, text[o:o + 1])
+            masks = torch.stack([m for _, _, m in ref.propagate_in_video(st)])
+        out[name] = masks.numpy()
+    np.savez_compressed(os.path.join(OUT, "sam2_tiny_video.npz"), **out)
+    print("sam2_tiny_video", {k: v.shape for k, v in out.items()})
+
+
+def towers_golden():
+    H.install_shims()
+    from model.videogpt_plus.model.internvideo.internvideo2 import PretrainInternVideo2
+    from transformers import CLIPVisionConfig, CLIPVisionModel, Phi3Config, Phi3ForCausalLM
+    cfg = M.make_cfg(**M.TINY_LMM)
+    sd = Wt.make_lmm_state_dict(cfg, 1)
+    iv, c, p = cfg.iv2, cfg.clip, cfg.phi
+    ref = PretrainInternVideo2(in_chans=3, img_size=iv.image_size, patch_size=iv.patch, embed_dim=iv.width, depth=iv.depth, num_heads=iv.heads,
+                               mlp_ratio=iv.mlp / iv.width, clip_embed_dim=32, attn_pool_num_heads=4, qkv_bias=False, drop_path_rate=0.25, init_values=1e-5,
+                               qk_normalization=True, use_flash_attn=False, use_fused_rmsnorm=False, use_fused_mlp=False, layerscale_no_force_fp32=False,
+                               num_frames=4, tubelet_size=1, sep_pos_embed=False, sep_image_video_pos_embed=True, clip_teacher_embed_dim=32,
+                               clip_teacher_final_dim=16, clip_return_layer=1, clip_student_return_interval=1).eval()
+    pre = "model.vision_tower.vision_encoder."
+    r = ref.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=False)
+    assert not r.unexpected_keys and all(k.startswith(("clip_", "final_clip")) for k in r.missing_keys)
+    torch.manual_seed(0)
+    xv = torch.randn(2, 4, 3, iv.image_size, iv.image_size)
+    xc = torch.randn(4, 3, c.image_size, c.image_size)
+    ids = torch.randint(0, p.vocab, (1, 37))
+    hf = CLIPVisionModel(CLIPVisionConfig(hidden_size=c.width, intermediate_size=c.mlp, num_hidden_layers=c.layers, num_attention_heads=c.heads,
+                                          image_size=c.image_size, patch_size=c.patch, hidden_act="quick_gelu")).eval()
+    pre = "model.image_vision_tower.vision_tower."
+    hf.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+    hfp = Phi3ForCausalLM(Phi3Config(vocab_size=p.vocab, hidden_size=p.hidden, intermediate_size=p.inter, num_hidden_layers=p.layers,
+                                     num_attention_heads=p.heads, num_key_value_heads=p.heads, rms_norm_eps=p.eps, rope_theta=p.rope_theta, sliding_window=None,
+                                     max_position_embeddings=4096, original_max_position_embeddings=4096, pad_token_id=0, attn_implementation="eager")).eval()
+    hfp.load_state_dict({k: v for k, v in sd.items() if k.startswith("model.layers") or k in ("model.embed_tokens.weight", "model.norm.weight", "lm_head.weight")},
+                        strict=True)
+    with torch.no_grad():
+        a = ref(xv.permute(0, 2, 1, 3, 4), None, False, x_vis_return_idx=-2, x_vis_only=True)
+        b = hf(xc, output_hidden_states=True).hidden_states[-2][:, 1:]
+        lg = hfp(input_ids=ids, use_cache=False).logits[0]
+    np.savez_compressed(os.path.join(OUT, "towers_tiny.npz"), iv2=a.numpy(), clip=b.numpy(), phi3_logits=lg.numpy(), ids=ids.numpy())
+    print("towers_tiny", a.shape, b.shape, lg.shape)
+
+
+if __name__ == "__main__":
+    sam2_video_golden()
+    towers_golden()

@@ -1,0 +1,40 @@
+"""Oracle vs the LIVE reference modules (needs /root/reference; skipped on the GPU box). Also checks that the synthetic
+state dicts carry exactly the reference's keys/shapes (strict load)."""
+import pytest
+import torch
+
+from oracle import ref_harness as H, sam2 as O, weights as Wt
+
+pytestmark = [pytest.mark.reference, pytest.mark.skipif(not H.available(), reason="reference tree not present")]
+
+
+def test_sam2_state_dict_contract_and_video_parity():
+    import sys
+    sys.path.insert(0, __import__("os").path.join(__import__("os").path.dirname(__file__), "golden"))
+    from make_golden import ref_sam2
+    cfg = O.Sam2Cfg(**O.TINY)
+    ref = ref_sam2(tiny=True)
+    sd = Wt.make_sam2_state_dict(cfg, 77)
+    rsd = ref.state_dict()
+    assert set(sd) == set(rsd)
+    assert all(tuple(sd[k].shape) == tuple(rsd[k].shape) for k in sd)
+    ref.load_state_dict(sd, strict=True)
+    torch.manual_seed(3)
+    images, text = torch.randn(3, 3, cfg.image_size, cfg.image_size), torch.randn(2, 1, 256)
+    with torch.inference_mode():
+        st = ref.init_state_from_tensor(images, 48, 64)
+        for o in range(2):
+            ref.add_new_text(st, 0, o, text[o:o + 1])
+        want = torch.stack([m for _, _, m in ref.propagate_in_video(st)])
+        got = torch.stack(O.run_video(sd, cfg, images, text, (48, 64)))
+    assert (got - want).abs().max() < 5e-3 * want.abs().max().clamp_min(1.0)
+
+
+def test_full_size_sam2_key_contract():
+    """Full Hiera-L shapes (no forward): the synthetic table must equal the reference's state_dict layout."""
+    from make_golden import ref_sam2
+    ref = ref_sam2(tiny=False)
+    shapes = Wt.sam2_param_shapes(O.Sam2Cfg())
+    rsd = ref.state_dict()
+    assert set(shapes) == set(rsd)
+    assert all(tuple(shapes[k]) == tuple(rsd[k].shape) for k in shapes)
