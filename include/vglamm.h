@@ -50,6 +50,7 @@ void vg_launch_count_reset(void);
  *   .../sam/mask_decoder.py:221-240).
  * Kernel: TMA (SWIZZLE_128B) -> shared -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
  * Requirements: lda, ldb multiples of 8; A, B 16-byte aligned; K >= 1 (K tail zero-filled by TMA).
+ * batch > 1 with strideB == 0 shares one B (weights) across all batch entries.
  * With glu != 0 the N columns are interleaved [16 gate | 16 up] per 32 and the output has N/2 columns.
  */
 typedef struct VgGemm {

@@ -45,3 +45,67 @@ class Sam2Config:
     @property
     def feat_size(self) -> int:
         return self.image_size // 16
+
+
+@dataclass
+class ClipConfig:
+    """HF CLIPVisionConfig fields used (openai/clip-vit-large-patch14-336)."""
+    image_size: int = 336
+    patch: int = 14
+    width: int = 1024
+    layers: int = 24
+    heads: int = 16
+    mlp: int = 4096
+    select_layer: int = -2
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch
+
+
+@dataclass
+class Iv2Config:
+    """InternVideo2-Stage2_1B-224p-f4 vision encoder."""
+    image_size: int = 224
+    patch: int = 14
+    width: int = 1408
+    depth: int = 40
+    heads: int = 16
+    mlp: int = 6144
+    frames: int = 4
+
+    @property
+    def grid(self) -> int:
+        return self.image_size // self.patch
+
+
+@dataclass
+class PhiConfig:
+    """HF Phi3Config fields used (Phi-3-mini-4k-instruct)."""
+    vocab: int = 32064
+    hidden: int = 3072
+    layers: int = 32
+    heads: int = 32
+    inter: int = 8192
+    rope_theta: float = 10000.0
+    eps: float = 1e-5
+    sliding_window: int | None = 2047
+    max_len: int = 4096
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.heads
+
+
+@dataclass
+class LmmConfig:
+    clip: ClipConfig
+    iv2: Iv2Config
+    phi: PhiConfig
+    out_dim: int = 256
+    seg_token_idx: int = 32011
+    proj_depth: int = 2
+
+
+def make_lmm_config(clip: dict | None = None, iv2: dict | None = None, phi: dict | None = None, **kw) -> LmmConfig:
+    return LmmConfig(ClipConfig(**(clip or {})), Iv2Config(**(iv2 or {})), PhiConfig(**(phi or {})), **kw)

@@ -41,6 +41,7 @@ struct GemmParams {
   long long ldr, strideR;
   int resid_f32;
   float alpha;
+  int b_shared;  // B (weights) shared by every batch entry
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -113,7 +114,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_3d(&tmA, &full_bar[stage], sA + stage * Cfg::A_BYTES, kb * BLOCK_K, m_blk * BLOCK_M, b);
-          tma_load_3d(&tmB, &full_bar[stage], sB + stage * Cfg::B_BYTES, kb * BLOCK_K, n_blk * BN, b);
+          tma_load_3d(&tmB, &full_bar[stage], sB + stage * Cfg::B_BYTES, kb * BLOCK_K, n_blk * BN, p.b_shared ? 0 : b);
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -405,6 +406,7 @@ static GemmParams to_params(const VgGemm* g) {
   p.bias = g->bias; p.strideBias = g->strideBias; p.act = g->act; p.glu = g->glu; p.col_scale = g->col_scale;
   p.resid = g->resid; p.ldr = g->ldr; p.strideR = g->strideR; p.resid_f32 = g->resid_dtype == VG_F32;
   p.alpha = g->alpha;
+  p.b_shared = (g->batch > 1 && g->strideB == 0) ? 1 : 0;
   return p;
 }
 
@@ -420,7 +422,7 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->M, g->K, g->batch, g->lda, g->strideA, BLOCK_M);
   if (rc) return rc;
-  rc = make_map(&tmB, g->B, g->N, g->K, g->batch, g->ldb, g->strideB, BN);
+  rc = make_map(&tmB, g->B, g->N, g->K, (g->batch > 1 && g->strideB == 0) ? 1 : g->batch, g->ldb, g->strideB, BN);
   if (rc) return rc;
   GemmParams p = to_params(g);
   p.tiles_m = (g->M + BLOCK_M - 1) / BLOCK_M;

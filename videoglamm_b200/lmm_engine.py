@@ -1,0 +1,277 @@
+"""B200 engine for the LMM side of VideoGLaMM's grounded generation: CLIP ViT-L/14-336 + InternVideo2-1B towers, V-L projectors
+and pooling, multimodal splice, Phi-3 prefill + KV-cached greedy decode, [SEG] hidden-state extraction and the L-V projection.
+
+Host orchestration only; activations are produced by libvglamm kernels (videoglamm_b200.ops). Weights come from a state_dict
+with the reference's keys. Unlike the reference (use_cache=False: every new token re-runs both vision
+towers and the full-sequence LLM, VideoGLaMM.py:790-799) the towers run ONCE and decode is KV-cached; results are defined
+against the no-cache forward, which is mathematically identical under causal attention.
+
+Reference call sites cited per method (paths relative to VideoGLaMM/).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .config import ClipConfig, Iv2Config, LmmConfig, PhiConfig
+
+BF, F32 = torch.bfloat16, torch.float32
+IMAGE_TOKEN_INDEX = -200
+
+
+@dataclass
+class _Lin:
+    w: torch.Tensor
+    b: torch.Tensor | None
+
+
+class _Packer:
+    def __init__(self, sd: dict, dev: torch.device):
+        self.sd, self.dev = sd, dev
+
+    def t(self, k):
+        return self.sd[k].detach().to(self.dev, F32)
+
+    def lin(self, p, kpad: int | None = None) -> _Lin:
+        w = self.t(p + ".weight")
+        w = w.reshape(w.shape[0], -1)
+        if kpad is not None and kpad != w.shape[1]:
+            wp = torch.zeros(w.shape[0], kpad, device=self.dev)
+            wp[:, : w.shape[1]] = w
+            w = wp
+        b = self.sd.get(p + ".bias")
+        return _Lin(w.to(BF).contiguous(), None if b is None else b.detach().to(self.dev, F32).contiguous())
+
+    def cat_lin(self, ps) -> _Lin:
+        ls = [self.lin(p) for p in ps]
+        return _Lin(torch.cat([l.w for l in ls]).contiguous(), torch.cat([l.b for l in ls]).contiguous() if ls[0].b is not None else None)
+
+    def vec(self, k):
+        return self.t(k).reshape(-1).contiguous()
+
+
+def _patchify_gemm(images: torch.Tensor, patch: int, w: _Lin, kpad: int, out_rows: torch.Tensor, resid: torch.Tensor):
+    """Non-overlapping patch conv as im2col + GEMM, one image group at a time; out_rows/resid are [rows, width] views."""
+    cols, _, _ = ops.im2col(images, patch, patch, 0, kpad)
+    ops.gemm(cols, w.w, bias=w.b, resid=resid, out=out_rows)
+
+
+class ClipTower:
+    """HF CLIPVisionModel as used by CLIPVisionTower.forward/feature_select model/videogpt_plus/model/multimodal_encoder/clip_encoder.py:34-72."""
+
+    def __init__(self, pk: _Packer, p: str, cfg: ClipConfig):
+        self.cfg, v = cfg, p + ".vision_model"
+        self.kpad = (3 * cfg.patch ** 2 + 7) // 8 * 8
+        self.patch = pk.lin(v + ".embeddings.patch_embedding", self.kpad)
+        pos = pk.t(v + ".embeddings.position_embedding.weight")
+        self.cls_row = (pk.t(v + ".embeddings.class_embedding").reshape(1, -1) + pos[:1]).contiguous()
+        self.pos_patches = pos[1:].contiguous()
+        self.pre = (pk.vec(v + ".pre_layrnorm.weight"), pk.vec(v + ".pre_layrnorm.bias"))
+        self.n_run = cfg.layers + 1 + cfg.select_layer
+        self.layers = []
+        for i in range(self.n_run):
+            l = f"{v}.encoder.layers.{i}"
+            self.layers.append(dict(ln1=(pk.vec(l + ".layer_norm1.weight"), pk.vec(l + ".layer_norm1.bias")),
+                                    qkv=pk.cat_lin([f"{l}.self_attn.{n}_proj" for n in "qkv"]), out=pk.lin(l + ".self_attn.out_proj"),
+                                    ln2=(pk.vec(l + ".layer_norm2.weight"), pk.vec(l + ".layer_norm2.bias")),
+                                    fc1=pk.lin(l + ".mlp.fc1"), fc2=pk.lin(l + ".mlp.fc2")))
+
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        """images [T,3,S,S] fp32 -> fp32 [T, 1+g^2, width] (hidden_states[select_layer]; the caller drops the CLS row)."""
+        cfg = self.cfg
+        T, W, N = images.shape[0], cfg.width, 1 + cfg.grid ** 2
+        x = torch.empty((T, N, W), device=images.device, dtype=F32)
+        x[:, 0] = self.cls_row
+        for t in range(T):
+            _patchify_gemm(images[t:t + 1].contiguous(), cfg.patch, self.patch, self.kpad, x[t, 1:], self.pos_patches)
+        x = x.view(T * N, W)
+        x = ops.norm(x, *self.pre, eps=1e-5, out_dtype=F32)
+        hd = W // cfg.heads
+        for L in self.layers:
+            h = ops.norm(x, *L["ln1"], eps=1e-5)
+            qkv = ops.gemm(h, L["qkv"].w, bias=L["qkv"].b).view(T, N, 3, cfg.heads, hd)
+            o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=hd ** -0.5)
+            x = ops.gemm(o.view(T * N, W), L["out"].w, bias=L["out"].b, resid=x, out=x)
+            h = ops.norm(x, *L["ln2"], eps=1e-5)
+            h = ops.gemm(h, L["fc1"].w, bias=L["fc1"].b, act="quick_gelu")
+            x = ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=x, out=x)
+        return x.view(T, N, W)
+
+
+class Iv2Tower:
+    """PretrainInternVideo2.forward(x_vis_only=True, x_vis_return_idx=-2) model/videogpt_plus/model/internvideo/internvideo2.py:585-651
+    with Block :306-310, Attention._naive_attn :190-209 (q/k RMSNorm over the full width), LayerScale :148-163."""
+
+    def __init__(self, pk: _Packer, p: str, cfg: Iv2Config):
+        self.cfg, e = cfg, p + ".vision_encoder"
+        self.kpad = (3 * cfg.patch ** 2 + 7) // 8 * 8
+        self.patch = pk.lin(e + ".patch_embed.proj", self.kpad)
+        pos = pk.t(e + ".pos_embed")[0]
+        self.cls_row = (pk.t(e + ".cls_token").reshape(1, -1) + pos[:1]).contiguous()
+        self.pos_patches = pos[1:].contiguous()
+        self.blocks = []
+        for i in range(cfg.depth - 1):  # the reference breaks after block depth-2
+            b = f"{e}.blocks.{i}"
+            self.blocks.append(dict(n1=pk.vec(b + ".norm1.weight"), qkv=pk.lin(b + ".attn.qkv"), qn=pk.vec(b + ".attn.q_norm.weight"),
+                                    kn=pk.vec(b + ".attn.k_norm.weight"), proj=pk.lin(b + ".attn.proj"), ls1=pk.vec(b + ".ls1.gamma"),
+                                    n2=pk.vec(b + ".norm2.weight"), fc1=pk.lin(b + ".mlp.fc1"), fc2=pk.lin(b + ".mlp.fc2"), ls2=pk.vec(b + ".ls2.gamma")))
+
+    def __call__(self, chunks: torch.Tensor) -> torch.Tensor:
+        """chunks [n,4,3,S,S] fp32 -> fp32 [n, 1+4*g^2, width]"""
+        cfg = self.cfg
+        n, W = chunks.shape[0], cfg.width
+        N = 1 + cfg.frames * cfg.grid ** 2
+        x = torch.empty((n, N, W), device=chunks.device, dtype=F32)
+        x[:, 0] = self.cls_row
+        for c in range(n):  # Conv3d(1 x p x p) == per-frame 2D patch conv; the 4 frames of a chunk are consecutive token blocks
+            _patchify_gemm(chunks[c].contiguous(), cfg.patch, self.patch, self.kpad, x[c, 1:], self.pos_patches)
+        x = x.view(n * N, W)
+        hd = W // cfg.heads
+        for B in self.blocks:
+            h = ops.norm(x, B["n1"], eps=1e-6, rms=True)
+            qkv = ops.gemm(h, B["qkv"].w)
+            ops.norm(qkv[:, :W], B["qn"], eps=1e-6, rms=True, out=qkv[:, :W])
+            ops.norm(qkv[:, W:2 * W], B["kn"], eps=1e-6, rms=True, out=qkv[:, W:2 * W])
+            q5 = qkv.view(n, N, 3, cfg.heads, hd)
+            o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
+            x = ops.gemm(o.view(n * N, W), B["proj"].w, bias=B["proj"].b, col_scale=B["ls1"], resid=x, out=x)
+            h = ops.norm(x, B["n2"], eps=1e-6, rms=True)
+            h = ops.gemm(h, B["fc1"].w, bias=B["fc1"].b, act="gelu")
+            x = ops.gemm(h, B["fc2"].w, bias=B["fc2"].b, col_scale=B["ls2"], resid=x, out=x)
+        return x.view(n, N, W)
+
+
+class LmmEngine:
+    def __init__(self, sd: dict, cfg: LmmConfig, device: str = "cuda"):
+        self.cfg, self.dev = cfg, torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("LmmEngine needs a CUDA device (there is no CPU path)")
+        pk = _Packer(sd, self.dev)
+        self.clip = ClipTower(pk, "model.image_vision_tower.vision_tower", cfg.clip)
+        self.iv2 = Iv2Tower(pk, "model.vision_tower", cfg.iv2)
+        self.vid_proj = [pk.lin(f"model.mm_projector.{2 * j}") for j in range(cfg.proj_depth)]
+        self.ctx_proj = [pk.lin(f"model.image_mm_projector.{2 * j}") for j in range(cfg.proj_depth)]
+        self.fc = [pk.lin("model.text_hidden_fcs.0.0"), pk.lin("model.text_hidden_fcs.0.2")]
+        ph = cfg.phi
+        self.embed = pk.t("model.embed_tokens.weight").to(BF).contiguous()
+        self.lm_head = pk.lin("lm_head")
+        self.final_norm = pk.vec("model.norm.weight")
+        self.layers = []
+        I = ph.inter
+        for l in range(ph.layers):
+            p = f"model.layers.{l}"
+            gu = pk.t(p + ".mlp.gate_up_proj.weight")
+            # interleave [16 gate | 16 up] row blocks so the GEMM epilogue computes silu(gate)*up in registers (include/vglamm.h, glu)
+            gu = torch.stack([gu[:I].view(I // 16, 16, -1), gu[I:].view(I // 16, 16, -1)], dim=1).reshape(2 * I, -1)
+            self.layers.append(dict(n1=pk.vec(p + ".input_layernorm.weight"), qkv=pk.lin(p + ".self_attn.qkv_proj"), o=pk.lin(p + ".self_attn.o_proj"),
+                                    n2=pk.vec(p + ".post_attention_layernorm.weight"), gu=gu.to(BF).contiguous(), down=pk.lin(p + ".mlp.down_proj")))
+        self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
+
+    # ------------------------------------------------------------------------------------------------ vision side
+    def _project(self, x3: torch.Tensor, layers) -> torch.Tensor:
+        """mlpNx_gelu projector (multimodal_projector/builder.py:38-46) on a [B, n, width] fp32 view (CLS already sliced off)."""
+        B, n, W = x3.shape
+        a = torch.empty((B, n, W), device=self.dev, dtype=BF)
+        for b in range(B):
+            ops.add(x3[b], None, out=a[b])
+        h = a.view(B * n, W)
+        for j, L in enumerate(layers):
+            last = j == len(layers) - 1
+            h = ops.gemm(h, L.w, bias=L.b, act=None if last else "gelu", out_dtype=F32 if last else BF)
+        return h
+
+    def visual_tokens(self, images: torch.Tensor, context_images: torch.Tensor) -> torch.Tensor:
+        """encode_videos model/videogpt_plus/model/arch.py:121-151 + project(input_type="video") :164-191:
+        -> fp32 [T*(gc/2)^2 + T*(gv/2)^2, hidden], context block first."""
+        cfg = self.cfg
+        T = images.shape[0]
+        assert T % cfg.iv2.frames == 0, "encoder frames must be a multiple of CHUNK_SIZE=4 (arch.py:133)"
+        vid = self.iv2(images.view(T // cfg.iv2.frames, cfg.iv2.frames, *images.shape[1:]))[:, 1:]
+        ctx = self.clip(context_images)[:, 1:]
+        gv, gc = cfg.iv2.grid, cfg.clip.grid
+        v = self._project(vid, self.vid_proj)                       # [T*gv^2, hidden] (chunk-major == frame-major)
+        v = ops.pool2x2(v, T, gv, gv, is_max=False)
+        c = self._project(ctx, self.ctx_proj)
+        c = ops.pool2x2(c, T, gc, gc, is_max=False)
+        return torch.cat([c, v], 0)
+
+    # ------------------------------------------------------------------------------------------------ Phi-3
+    def _alloc_cache(self, max_len: int):
+        ph = self.cfg.phi
+        if self.kv is None or self.kv[0].shape[0] < max_len:
+            self.kv = [torch.empty((max_len, 3 * ph.hidden), device=self.dev, dtype=BF) for _ in range(ph.layers)]
+
+    def _llm(self, x: torch.Tensor, pos0: int) -> torch.Tensor:
+        """HF Phi3Model.forward (called at language_model/phi3.py:72-81) on rows [pos0, pos0+n) given a cache holding rows [0,pos0).
+        x fp32 [n, hidden] (modified in place as the residual stream) -> final-norm hidden fp32 [n, hidden]."""
+        ph = self.cfg.phi
+        n, H, hd, D = x.shape[0], ph.heads, ph.head_dim, ph.hidden
+        pos = torch.arange(pos0, pos0 + n, device=self.dev, dtype=torch.int32)
+        end = pos0 + n
+        for l, L in enumerate(self.layers):
+            cache = self.kv[l]
+            h = ops.norm(x, L["n1"], eps=ph.eps, rms=True)
+            rows = cache[pos0:end]
+            ops.gemm(h, L["qkv"].w, out=rows)
+            ops.rope_neox_(rows, pos, 2 * H, hd, ph.rope_theta)
+            q = rows[:, :D].unflatten(1, (H, hd))[None]
+            k = cache[:end, D:2 * D].unflatten(1, (H, hd))[None]
+            v = cache[:end, 2 * D:].unflatten(1, (H, hd))[None]
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0)
+            x = ops.gemm(o.view(n, D), L["o"].w, resid=x, out=x)
+            h = ops.norm(x, L["n2"], eps=ph.eps, rms=True)
+            h = ops.gemm(h, L["gu"], glu=True, act="silu")
+            x = ops.gemm(h, L["down"].w, resid=x, out=x)
+        return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
+
+    def embed_prompt(self, input_ids: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
+        """prepare_inputs_labels_for_multimodal arch.py:283-379 (video case): embed(ids before the -200 run) + visual + embed(rest)."""
+        ids = input_ids.reshape(-1)
+        idx = torch.where(ids == IMAGE_TOKEN_INDEX)[0]
+        start, end = int(idx[0]), int(idx[-1])
+        parts = []
+        if start > 0:
+            parts.append(ops.embedding(self.embed, ids[:start].contiguous()))
+        parts.append(vis)
+        if end + 1 < ids.numel():
+            parts.append(ops.embedding(self.embed, ids[end + 1:].contiguous()))
+        return torch.cat(parts, 0).contiguous()
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.Tensor, images: torch.Tensor, context_images: torch.Tensor, max_new_tokens: int, eos_ids=(),
+                 forced: dict | None = None, return_debug: bool = False):
+        """Steps (A)-(D) of VideoGLaMM_SAM2.inference_video_branch VideoGLaMM.py:782-831 with greedy decoding:
+        returns (output_ids int64 [1, L_txt+N] incl. -200 sentinels, pred_embeddings fp32 [n_seg, out_dim]).
+        The hidden state that PREDICTED each [SEG] (mask shifted by one, :803-806) is the final-norm hidden of the step that emitted it."""
+        cfg = self.cfg
+        vis = self.visual_tokens(images, context_images)
+        x = self.embed_prompt(input_ids, vis)
+        L0 = x.shape[0]
+        self._alloc_cache(L0 + max_new_tokens + 1)
+        hidden = self._llm(x, 0)
+        h_last = hidden[-1:].contiguous()
+        new_ids, seg_hidden = [], []
+        dbg = dict(prefill_hidden=hidden, logits=[]) if return_debug else None
+        for step in range(max_new_tokens):
+            logits = ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32)
+            nxt = int(ops.argmax(logits)[0])
+            if return_debug:
+                dbg["logits"].append(logits)
+            if forced and step in forced:
+                nxt = forced[step]
+            new_ids.append(nxt)
+            if nxt == cfg.seg_token_idx:
+                seg_hidden.append(h_last)
+            if nxt in eos_ids or step == max_new_tokens - 1:
+                break
+            e = ops.embedding(self.embed, torch.tensor([nxt], device=self.dev, dtype=torch.int64))
+            h_last = self._llm(e, L0 + step)
+        out_ids = torch.cat([input_ids.reshape(1, -1), torch.tensor([new_ids], device=input_ids.device, dtype=torch.int64)], dim=1)
+        if seg_hidden:
+            hs = ops.cast(torch.cat(seg_hidden, 0), BF)
+            emb = ops.gemm(ops.gemm(hs, self.fc[0].w, bias=self.fc[0].b, act="relu"), self.fc[1].w, bias=self.fc[1].b, out_dtype=F32)
+        else:
+            emb = torch.zeros((0, cfg.out_dim), device=self.dev)
+        return (out_ids, emb, dbg) if return_debug else (out_ids, emb)

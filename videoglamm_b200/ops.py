@@ -41,8 +41,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
     batched = a.dim() == 3
     if batched:
         Bt, M, K = a.shape
-        assert w.dim() == 3 and w.shape[0] == Bt
-        N = w.shape[1]
+        assert (w.dim() == 3 and w.shape[0] == Bt) or w.dim() == 2  # 2D w: shared by every batch entry
+        N = w.shape[-2]
     else:
         assert a.dim() == 2 and w.dim() == 2
         Bt, (M, K), N = 1, a.shape, w.shape[0]
@@ -53,7 +53,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
     assert out.stride(-1) == 1 and out.shape[-1] == n_out and out.shape[-2] == M
     g = L.VgGemm()
     g.A, g.lda, g.strideA = a.data_ptr(), a.stride(-2), a.stride(0) if batched else 0
-    g.B, g.ldb, g.strideB = w.data_ptr(), w.stride(-2), w.stride(0) if batched else 0
+    g.B, g.ldb, g.strideB = w.data_ptr(), w.stride(-2), w.stride(0) if (batched and w.dim() == 3) else 0
     g.C, g.ldc, g.strideC = out.data_ptr(), out.stride(-2), out.stride(0) if batched else 0
     g.M, g.N, g.K, g.batch = M, N, K, Bt
     g.out_dtype = _dt(out.dtype)
@@ -67,7 +67,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
         g.col_scale = col_scale.data_ptr()
     if resid is not None:
         assert resid.stride(-1) == 1 and resid.shape[-1] == n_out and resid.shape[-2] == M
-        g.resid, g.ldr, g.strideR, g.resid_dtype = resid.data_ptr(), resid.stride(-2), resid.stride(0) if batched else 0, _dt(resid.dtype)
+        g.resid, g.ldr, g.strideR, g.resid_dtype = resid.data_ptr(), resid.stride(-2), resid.stride(0) if (batched and resid.dim() == 3) else 0, _dt(resid.dtype)
     g.alpha = alpha
     g.force_block_n = force_block_n
     fn = L.lib().vg_gemm_naive if naive else L.lib().vg_gemm
