@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Headline benchmark: grounded clips/sec end to end (BASELINE.json config 2: 1 clip = T=8 frames, CLIP 336 px / IV2 224 px /
+SAM2 1024 px, Phi-3-mini, 1 [SEG] object, 12 new tokens), full-size architecture with synthetic weights and inputs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our engine (one process per GPU under torchrun for N>1)
+  python bench.py --impl reference [...]                          # CPU arm: the oracle port of the reference on host cores
+
+One "step" = one clip through the whole path (towers -> projectors -> Phi-3 prefill + KV-cached decode -> [SEG] projection ->
+SAM2 Hiera + mask decoder + memory attention/encoder over 8 frames -> masks at video resolution).
+Prints ONE JSON line (contract in the task statement / DESIGN.md §Measurement).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+T_ENC = T_SAM = 8
+N_NEW, SEG_STEP = 12, 5
+VIDEO_HW = (336, 336)
+L_QUERY = 20
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1383.6), d.get("hbm_gbs", 6458.4), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def clip_flops(L: int) -> float:
+    """Algorithmic FLOPs of one config-2 clip for the ideal engine: encode once, KV-cached decode."""
+    enc = 0.382e12 * T_ENC + 2.25e12 * T_ENC / 4 + 0.022e12 * T_ENC
+    prefill = 2 * 3.62e9 * L + 2 * L * L * 98304
+    decode = N_NEW * (7.6e9 + 4 * L * 98304)
+    sam = 1.620e12 * T_SAM
+    for t in range(T_SAM):
+        nk = 4096 * min(t, 7) + 4 * min(t, 16)
+        sam += 3.64e9 + 11.6e9 + (t > 0) * (4 * (2.1e9 + 17.2e9 + 1.07e9 + 8.6e9) + 4 * (65536 + 4194304) * nk)
+    return enc + prefill + decode + sam
+
+
+def synth_inputs(seed: int, pinned: bool):
+    """seeded N(0,1) tensors of the named shapes + a prompt with T_ENC image sentinels."""
+    g = torch.Generator().manual_seed(5678 + seed)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    images, context, sam = mk(T_ENC, 3, 224, 224), mk(T_ENC, 3, 336, 336), mk(T_SAM, 3, 1024, 1024)
+    ids = torch.cat([torch.randint(3, 32000, (12,), generator=g), torch.full((T_ENC,), -200), torch.randint(3, 32000, (L_QUERY,), generator=g)])[None]
+    if pinned:
+        images, context, sam, ids = (t.pin_memory() for t in (images, context, sam, ids))
+    return images, context, sam, ids
+
+
+def run_engine(args):
+    import torch.distributed as dist
+    from videoglamm_b200 import build, ops
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    from videoglamm_b200.statedict import random_state_dict, videoglamm_param_shapes
+
+    build.build()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    lmm_cfg, sam_cfg = make_lmm_config(), Sam2Config()
+    sd = random_state_dict(videoglamm_param_shapes(lmm_cfg, sam_cfg), dev, seed=1234)
+    model = VideoGLaMMForCausalLM(sd, lmm_cfg, sam_cfg, device=dev, validate=False)
+    del sd
+    torch.cuda.empty_cache()
+    forced = {SEG_STEP: lmm_cfg.seg_token_idx}
+    host = synth_inputs(rank, pinned=True)
+    resident = [t.to(dev) for t in host]
+    L = host[3].shape[1] - T_ENC + 208 * T_ENC
+
+    def step(inp):
+        im, ctx, sam, ids = inp
+        out_ids, segs = model.inference([im], [ctx], [sam], ids, None, [VIDEO_HW], max_new_tokens=N_NEW, use_sam2_video_branch=True, forced_tokens=forced)
+        return out_ids, segs
+
+    def gather_masks(segs):
+        """§8(e): the only collective on the path — bit-packed final masks to rank 0."""
+        if world == 1:
+            return
+        import numpy as np
+        m = np.stack([segs[0][t][0] for t in sorted(segs[0])])
+        packed = torch.from_numpy(np.packbits(m)).to(dev)
+        bufs = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
+        dist.gather(packed, bufs, dst=0)
+
+    def timed(inp, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            _, segs = step(inp)
+            gather_masks(segs)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.launch_count_reset()
+    ms = timed(resident, args.steps)
+    launches = ops.launch_count()
+    ms_e2e = timed(host, args.steps)            # same call, HOST pinned inputs: H2D of every input + D2H of the masks inside the region
+    clocks = sampler.stop() if rank == 0 else {}
+    # dominant kernel = the tcgen05 GEMM: per-launch CUDA-event timing on one extra (untimed) step
+    ops.gemm_profile(True)
+    step(resident)
+    torch.cuda.synchronize()
+    prof = ops.gemm_profile(False)
+    cpu = cpu_baseline_sample(L) if (rank == 0 and not args.no_cpu_baseline) else None
+    if rank == 0:
+        tf_peak, hbm_peak, src = _peaks()
+        n_clips = args.steps * world
+        ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        d2h = T_SAM * VIDEO_HW[0] * VIDEO_HW[1] + (host[3].numel() + N_NEW) * 8
+        line = {
+            "metric": "grounded clips/sec (T=8, 336px) end-to-end", "value": n_clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: 1 clip T_enc=T_sam=8, CLIP 336px, IV2 224px, SAM2 1024px, Phi-3-mini 32L, 1 [SEG], 12 new tokens",
+                       "llm_seq_len": L, "clips_per_step_per_gpu": 1, "parallelism": f"dp{world} (independent clips, masks gathered to rank 0)",
+                       "l2": "no explicit flush: each step streams 10.8 GB of bf16 weights (>> 126 MB L2)",
+                       "algorithmic_tflop_per_clip": clip_flops(L) / 1e12},
+            "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of one clip)", "achieved": ach, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": f"{src} bf16_tflops_sustained",
+                         "launches": prof["n"], "gemm_ms_per_clip": prof["ms"], "gemm_share_of_step": prof["ms"] / (ms / args.steps),
+                         "whole_clip_tflops": clip_flops(L) / (ms / args.steps * 1e-3) / 1e12},
+            "clocks": clocks,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_baseline_sample(L: int) -> dict:
+    """Times the oracle (CPU fp32 port of the reference path) on a bounded, full-width SAMPLE of the config-2 clip and scales by
+    layer / frame multiplicities: 1 CLIP layer x 8 frames, 1 IV2 block x 2 chunks, 1 Phi-3 layer at L, 1 Hiera block per stage,
+    1 mask-decoder + 1 memory-attention layer (full bank) + memory encoder for one object-frame."""
+    import math
+
+    import torch.nn.functional as F
+
+    from oracle import lmm as M, sam2 as O
+
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, generator=g) * 0.02
+    t = {}
+
+    def clock(name, fn, mult):
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        t[name] = (time.perf_counter() - t0) * mult
+
+    with torch.no_grad():
+        # CLIP layer (23 run), 8 frames x 577 tokens
+        x = torch.randn(8, 577, 1024, generator=g)
+        w = {k: rnd(*s) for k, s in dict(qkv=(3072, 1024), o=(1024, 1024), f1=(4096, 1024), f2=(1024, 4096)).items()}
+
+        def vit_layer(x, w, heads, act):
+            B, N, C = x.shape
+            h = F.layer_norm(x, (C,))
+            q, k, v = F.linear(h, w["qkv"]).view(B, N, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+            x = x + F.linear(F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C), w["o"])
+            return x + F.linear(act(F.linear(F.layer_norm(x, (C,)), w["f1"])), w["f2"])
+
+        clock("clip", lambda: vit_layer(x, w, 16, lambda z: z * torch.sigmoid(1.702 * z)), 23)
+        x2 = torch.randn(2, 1025, 1408, generator=g)
+        w2 = {k: rnd(*s) for k, s in dict(qkv=(4224, 1408), o=(1408, 1408), f1=(6144, 1408), f2=(1408, 6144)).items()}
+        clock("iv2", lambda: vit_layer(x2, w2, 16, F.gelu), 39)
+        # Phi-3 layer at L tokens; the reference-as-written runs N_NEW+2 full forwards (use_cache=False, VideoGLaMM.py:782-799)
+        pcfg = M.PhiCfg(layers=1)
+        sd = {"model.layers.0.self_attn.qkv_proj.weight": rnd(9216, 3072), "model.layers.0.self_attn.o_proj.weight": rnd(3072, 3072),
+              "model.layers.0.mlp.gate_up_proj.weight": rnd(16384, 3072), "model.layers.0.mlp.down_proj.weight": rnd(3072, 8192),
+              "model.layers.0.input_layernorm.weight": torch.ones(3072), "model.layers.0.post_attention_layernorm.weight": torch.ones(3072),
+              "model.norm.weight": torch.ones(3072)}
+        xl = torch.randn(L, 3072, generator=g)
+        clock("phi3_layer_full_forward", lambda: M.phi3_forward(sd, pcfg, xl), 32)
+        # Hiera: one block of each stage at 1024^2, scaled by blocks per stage, x 8 frames
+        scfg = O.Sam2Cfg()
+        specs = scfg.block_specs()
+        hier = 0.0
+        for si, (bi, cnt, side) in enumerate(((1, 2, 256), (3, 6, 128), (10, 36, 64), (45, 4, 32))):
+            dim, dim_out, heads, window, qs = specs[bi]
+            p = "b"
+            bsd = {f"{p}.norm1.weight": torch.ones(dim), f"{p}.norm1.bias": torch.zeros(dim), f"{p}.attn.qkv.weight": rnd(3 * dim_out, dim),
+                   f"{p}.attn.qkv.bias": torch.zeros(3 * dim_out), f"{p}.attn.proj.weight": rnd(dim_out, dim_out), f"{p}.attn.proj.bias": torch.zeros(dim_out),
+                   f"{p}.norm2.weight": torch.ones(dim_out), f"{p}.norm2.bias": torch.zeros(dim_out),
+                   f"{p}.mlp.layers.0.weight": rnd(4 * dim_out, dim_out), f"{p}.mlp.layers.0.bias": torch.zeros(4 * dim_out),
+                   f"{p}.mlp.layers.1.weight": rnd(dim_out, 4 * dim_out), f"{p}.mlp.layers.1.bias": torch.zeros(dim_out)}
+            xh = torch.randn(1, side, side, dim, generator=g)
+            clock(f"hiera_stage{si}", lambda: O.hiera_block(bsd, p, xh, specs[bi]), cnt * T_SAM)
+            hier += t[f"hiera_stage{si}"]
+    llm_forwards = N_NEW + 2
+    total = t["clip"] + t["iv2"] + t["phi3_layer_full_forward"] * llm_forwards + hier
+    return {"value": 1.0 / total, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle (CPU fp32 port of the reference path) timed per full-width layer and scaled by multiplicity: CLIP 1 layer x8 frames (x23), "
+                      "IV2 1 block x2 chunks (x39), Phi-3 1 layer at L tokens (x32 layers x14 full forwards, use_cache=False as the reference), "
+                      "Hiera 1 block per stage (x2/6/36/4 x8 frames); SAM2 decoder/memory stages omitted (<3% of CPU time)",
+            "seconds_per_clip_extrapolated": total, "stage_seconds": t}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path = the oracle port (the reference tree is not on the GPU box),
+    all host threads, same config/metric. Each step is the bounded sample above."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    L = 12 + L_QUERY + 208 * T_ENC
+    res = None
+    for _ in range(max(args.warmup, 0)):
+        res = cpu_baseline_sample(L)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = cpu_baseline_sample(L)
+        vals.append(res["value"])
+    wall = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "grounded clips/sec (T=8, 336px) end-to-end", "value": v, "unit": "clips/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1] (same as the engine arm); bounded per-layer sample extrapolated to one clip", "device": "host CPU"},
+            "cpu_baseline": {**res, "value": v}, "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the engine has no CPU path (use --impl reference for the CPU arm)")
+        run_engine(a)

@@ -1,0 +1,31 @@
+"""End to end through the public API (`VideoGLaMMForCausalLM.inference`) vs the oracle: token ids identical, masks agree."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
+
+
+def test_no_seg_returns_empty_dict_and_errors():
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    ocfg, scfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=300), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=300), Sam2Config(**O.TINY))
+    T = 4
+    ids = torch.cat([torch.randint(3, 290, (5,)), torch.full((T,), -200), torch.randint(3, 290, (7,))])[None].cuda()
+    args = ([torch.randn(T, 3, 56, 56).cuda()], [torch.randn(T, 3, 56, 56).cuda()], [torch.randn(2, 3, 256, 256).cuda()], ids, None, [(48, 64)])
+    out_ids, segs = model.inference(*args, max_new_tokens=3, use_sam2_video_branch=True, forced_tokens={0: 5, 1: 6, 2: 7})
+    assert segs == [{}] and out_ids.shape[1] == ids.shape[1] + 3            # VideoGLaMM.py:840-842
+    model.use_sam2 = False
+    with pytest.raises(ValueError):                                          # VideoGLaMM.py:585
+        model.inference(*args, use_sam2_video_branch=True)
+    bad = dict(sd)
+    bad.pop("model.norm.weight")
+    with pytest.raises(KeyError):
+        VideoGLaMMForCausalLM(bad, make_lmm_config(**M.TINY_LMM, seg_token_idx=300), Sam2Config(**O.TINY))

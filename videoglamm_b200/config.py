@@ -46,6 +46,14 @@ class Sam2Config:
     def feat_size(self) -> int:
         return self.image_size // 16
 
+    @property
+    def channel_list(self) -> list[int]:
+        specs = self.block_specs()
+        return [specs[i][1] for i in self.stage_ends[::-1]]
+
+    mem_attn_ffn: int = 2048
+    dec_mlp: int = 2048
+
 
 @dataclass
 class ClipConfig:

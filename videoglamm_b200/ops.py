@@ -71,8 +71,38 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
     g.alpha = alpha
     g.force_block_n = force_block_n
     fn = L.lib().vg_gemm_naive if naive else L.lib().vg_gemm
+    if _GEMM_PROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(fn(C.byref(g), _stream()), "vg_gemm")
+        e1.record()
+        _GEMM_PROF.append((e0, e1, 2.0 * M * N * K * Bt, (M, N, K, Bt)))
+        return out
     L.check(fn(C.byref(g), _stream()), "vg_gemm")
     return out
+
+
+_GEMM_PROF: list | None = None
+
+
+def gemm_profile(enable: bool):
+    """Per-launch CUDA-event timing of every GEMM on the current stream (bench.py roofline). enable=False returns the totals."""
+    global _GEMM_PROF
+    if enable:
+        _GEMM_PROF = []
+        return None
+    torch.cuda.synchronize()
+    rec, _GEMM_PROF = _GEMM_PROF or [], None
+    by_shape: dict = {}
+    for e0, e1, fl, shp in rec:
+        ms = e0.elapsed_time(e1)
+        a = by_shape.setdefault(shp, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += ms
+        a[2] += fl
+    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]
+    return {"n": len(rec), "ms": sum(v[1] for v in by_shape.values()), "flops": sum(v[2] for v in by_shape.values()),
+            "top_shapes": [{"MNKB": list(k), "launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)} for k, v in top]}
 
 
 def launch_count() -> int:
