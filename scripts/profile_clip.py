@@ -1,0 +1,48 @@
+"""One full-size config-2 clip between cudaProfilerStart/Stop (for `ncu --profile-from-start off`)."""
+import os, sys, json
+import torch
+sys.path.insert(0, ".")
+import bench
+from videoglamm_b200 import ops
+from videoglamm_b200.config import Sam2Config, make_lmm_config
+from videoglamm_b200.model import VideoGLaMMForCausalLM
+from videoglamm_b200.statedict import random_state_dict, videoglamm_param_shapes
+lmm_cfg, sam_cfg = make_lmm_config(), Sam2Config()
+sd = random_state_dict(videoglamm_param_shapes(lmm_cfg, sam_cfg), "cuda", seed=1234)
+model = VideoGLaMMForCausalLM(sd, lmm_cfg, sam_cfg, validate=False); del sd
+inp = [t.cuda() for t in bench.synth_inputs(0, pinned=False)]
+forced = {bench.SEG_STEP: lmm_cfg.seg_token_idx}
+def step():
+    return model.inference([inp[0]], [inp[1]], [inp[2]], inp[3], None, [bench.VIDEO_HW], max_new_tokens=bench.N_NEW, use_sam2_video_branch=True, forced_tokens=forced)
+n_warm = int(os.environ.get("WARM", 2))
+for _ in range(n_warm): step()
+torch.cuda.synchronize()
+if os.environ.get("STAGES"):
+    # coarse per-stage CUDA-event timing
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    dev = "cuda"
+    marks = []
+    def mark(name):
+        e = ev(); e.record(); marks.append((name, e))
+    mark("start")
+    vis_iv2 = model.lmm.iv2(inp[0].view(2, 4, 3, 224, 224)); mark("iv2")
+    vis_clip = model.lmm.clip(inp[1]); mark("clip")
+    vis = model.lmm.visual_tokens(inp[0], inp[1]); mark("visual_tokens(all again)")
+    x = model.lmm.embed_prompt(inp[3], vis); model.lmm._alloc_cache(x.shape[0] + 20)
+    h = model.lmm._llm(x, 0); mark("phi3_prefill")
+    e = ops.embedding(model.lmm.embed, torch.tensor([5], device=dev))
+    for i in range(12):
+        hh = model.lmm._llm(e.clone(), x.shape[0] + i)
+        lg = ops.gemm(ops.cast(hh, torch.bfloat16), model.lmm.lm_head.w, out_dtype=torch.float32); ops.argmax(lg)
+    mark("phi3_decode_x12")
+    feats = [model.sam.forward_image(inp[2][t:t+1]) for t in range(8)]; mark("hiera_x8")
+    emb = torch.randn(1, 1, 256, device=dev)
+    out = model.sam.run_video(inp[2], emb, bench.VIDEO_HW, binary=True); mark("sam2_run_video(incl hiera)")
+    torch.cuda.synchronize()
+    for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+        print(f"{n1:32s} {e0.elapsed_time(e1):9.3f} ms")
+else:
+    torch.cuda.cudart().cudaProfilerStart()
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()

@@ -247,3 +247,37 @@ def test_rope_embedding_argmax():
     lg = torch.randn(6, 32064, device=DEV)
     lg[2, 77] = lg[2, 9000] = 50.0
     assert torch.equal(ops.argmax(lg), lg.argmax(-1))
+
+
+@pytest.mark.parametrize("M", [1, 3, 8])
+def test_skinny_gemm_decode_path(M):
+    """M <= 8 takes the HBM-streaming warp-per-column kernel: same epilogue contract as the tcgen05 path."""
+    K, N = 3072, 1024
+    a = torch.randn(M, K, device=DEV).bfloat16()
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias, cs, res = torch.randn(N, device=DEV), torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    y = ops.gemm(a, w, bias=bias, act="gelu", col_scale=cs, resid=res, out_dtype=torch.float32, alpha=0.5)
+    assert rel(y, F.gelu(0.5 * (a.float() @ w.float().T) + bias) * cs + res) < 1e-5
+    y = ops.gemm(a, w, glu=True, act="silu", out_dtype=torch.float32)
+    r = (a.float() @ w.float().T).reshape(M, -1, 2, 16)
+    assert rel(y, (F.silu(r[:, :, 0]) * r[:, :, 1]).reshape(M, -1)) < 1e-5
+    assert rel(ops.gemm(a, w, out_dtype=torch.float32), ops.gemm(a, w, out_dtype=torch.float32, force_block_n=64)) < 1e-5
+    big = (torch.randn(16384, 3072, device=DEV) / 55).bfloat16()
+    assert rel(ops.gemm(a, big, out_dtype=torch.bfloat16), a.float() @ big.float().T) < 4e-3
+
+
+@pytest.mark.parametrize("H,Nk,D,window", [(32, 1709, 96, 0), (32, 3000, 96, 2047), (4, 256, 64, 0), (1, 5000, 256, 0), (8, 999, 72, 100)])
+def test_attention_single_query_decode(H, Nk, D, window):
+    q = torch.randn(1, 1, H, D, device=DEV).bfloat16()
+    k = torch.randn(1, Nk, H, D, device=DEV).bfloat16()
+    v = torch.randn(1, Nk, H, D, device=DEV).bfloat16()
+    o = ops.attention(q, k, v, causal=True, window=window)
+    assert rel(o, sdpa_ref(q, k, v, D ** -0.5, True, window)) < 4e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 3072), (3, 1408), (100, 1024), (2047, 600)])
+def test_norm_block_per_row_path(rows, cols):
+    x = torch.randn(rows, cols, device=DEV) * 2 + 0.5
+    w, b = torch.randn(cols, device=DEV), torch.randn(cols, device=DEV)
+    assert rel(ops.norm(x, w, b, eps=1e-5, out_dtype=torch.float32), F.layer_norm(x, (cols,), w, b, 1e-5)) < 1e-5
+    assert rel(ops.norm(x, w, eps=1e-5, rms=True, out_dtype=torch.float32), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w) < 1e-5

@@ -196,6 +196,88 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- single-query attention (LLM decode)
+// HBM/L2-bound: one block per (head, batch); each warp walks 32-key groups: lane-per-key QK^T (no shuffles in the dot product),
+// warp-level online softmax, then lane-per-feature PV with the probabilities staged in shared memory; warps merged at the end.
+template <int DMAX>
+__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
+  constexpr int NW = 8, EPL = DMAX / 32;  // features per lane in the PV phase
+  __shared__ float s_q[DMAX];
+  __shared__ float s_p[NW][32];
+  __shared__ float s_o[NW][DMAX];
+  __shared__ float s_m[NW], s_l[NW];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* qp = p.q + b * p.q_bs + h * p.q_hs;
+  const __nv_bfloat16* kb = p.k + b * p.k_bs + h * p.k_hs;
+  const __nv_bfloat16* vb = p.v + b * p.v_bs + h * p.v_hs;
+  for (int d = tid; d < DMAX; d += 256) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
+  __syncthreads();
+  int k_begin = 0;
+  if (p.window > 0) k_begin = max(0, p.Nk - 1 - p.window);
+  float m_run = -INFINITY, l_run = 0.f, o[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) o[e] = 0.f;
+  const int chunks = p.D >> 3;
+  for (int g0 = k_begin + warp * 32; g0 < p.Nk; g0 += NW * 32) {
+    const int j = g0 + lane;
+    float sc = -INFINITY;
+    if (j < p.Nk) {
+      const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * p.k_rs);
+      float acc = 0.f;
+      for (int c = 0; c < chunks; ++c) {
+        const uint4 kv = __ldg(kr + c);
+        const float* qq = s_q + c * 8;
+        acc = fmaf(bf16_lo(kv.x), qq[0], acc); acc = fmaf(bf16_hi(kv.x), qq[1], acc);
+        acc = fmaf(bf16_lo(kv.y), qq[2], acc); acc = fmaf(bf16_hi(kv.y), qq[3], acc);
+        acc = fmaf(bf16_lo(kv.z), qq[4], acc); acc = fmaf(bf16_hi(kv.z), qq[5], acc);
+        acc = fmaf(bf16_lo(kv.w), qq[6], acc); acc = fmaf(bf16_hi(kv.w), qq[7], acc);
+      }
+      sc = acc;
+    }
+    const float m_new = fmaxf(m_run, warp_max(sc));
+    const float pj = (j < p.Nk) ? __expf(sc - m_new) : 0.f;
+    const float alpha = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+    l_run = l_run * alpha + warp_sum(pj);
+    m_run = m_new;
+    s_p[warp][lane] = pj;
+    __syncwarp();
+    const int nvalid = min(32, p.Nk - g0);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) o[e] *= alpha;
+    for (int jj = 0; jj < nvalid; ++jj) {
+      const float pv = s_p[warp][jj];
+      const __nv_bfloat16* vr = vb + static_cast<long long>(g0 + jj) * p.v_rs;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int d = lane + e * 32;
+        if (d < p.D) o[e] = fmaf(pv, __bfloat162float(vr[d]), o[e]);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    s_m[warp] = m_run;
+    s_l[warp] = l_run;
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) s_o[warp][lane + e * 32] = o[e];
+  __syncthreads();
+  float m_all = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) m_all = fmaxf(m_all, s_m[w]);
+  float l_all = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) l_all += (s_m[w] == -INFINITY) ? 0.f : s_l[w] * __expf(s_m[w] - m_all);
+  __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
+  for (int d = tid; d < p.D; d += 256) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
+    op[d] = __float2bfloat16(l_all > 0.f ? acc / l_all : 0.f);
+  }
+}
+
 template <int DP>
 static int launch_attn(const AttnParams& p, cudaStream_t s) {
   constexpr int LD = DP + 8;
@@ -236,6 +318,15 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
   p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && a->Nk >= 256) {  // decode: causal is a no-op for the newest query
+    dim3 grid(a->H, a->B);
+    if (a->D <= 128)
+      attn_decode_kernel<128><<<grid, 256, 0, s>>>(p);
+    else
+      attn_decode_kernel<256><<<grid, 256, 0, s>>>(p);
+    count_launch();
+    return check_launch("attn_decode_kernel");
+  }
   if (a->D <= 32) return launch_attn<32>(p, s);
   if (a->D <= 64) return launch_attn<64>(p, s);
   if (a->D <= 80) return launch_attn<80>(p, s);

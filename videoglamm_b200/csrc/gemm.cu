@@ -2,7 +2,7 @@
 //   warp 0 (1 lane)  TMA producer      global --cp.async.bulk.tensor (SWIZZLE_128B)--> smem ring
 //   warp 1 (1 lane)  MMA issuer        tcgen05.mma.cta_group::1.kind::f16, fp32 accumulators in TMEM (double-buffered)
 //   warp 2           TMEM allocator
-//   warps 4..7       epilogue          tcgen05.ld -> bias/act/GLU/scale/residual -> global
+//   warps 4..11      epilogue          tcgen05.ld -> bias/act/GLU/scale/residual -> global (lane quadrant x column half)
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (nn.Linear layout). See include/vglamm.h for the contract.
 #include <mutex>
 #include <unordered_map>
@@ -15,7 +15,7 @@ namespace vg {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
 template <int BN>
 struct GemmCfg {
@@ -83,7 +83,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], 256);
     }
     mbar_fence_init();
   }
@@ -158,11 +158,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue: TMEM -> regs -> global
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quadrant this warp may access
+    // ------------------------------------------------ epilogue: TMEM -> regs -> global (8 warps: lane quadrant x column half)
+    const int ew = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
+    const int half = (warp - 4) >> 2;  // which interleaved set of 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out = p.glu ? p.N / 2 : p.N;
+    const bool unit_alpha = p.alpha == 1.0f;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
@@ -173,8 +175,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      const float* bias = p.bias ? p.bias + b * p.strideBias : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t raw[32];
@@ -182,11 +185,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.alpha;
-        if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (!unit_alpha) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.N) v[j] += __ldg(p.bias + b * p.strideBias + col0 + j);
+          for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
+        }
+        const bool full = col0 + 32 <= p.N;  // warp-uniform
+        if (bias != nullptr) {
+          if (full && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
+            const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(bp + j);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+          }
         }
         int ocol0, nvals;
         if (p.glu) {
@@ -202,30 +219,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ocol0 = col0;
           nvals = 32;
         }
+        const int nvalid = min(nvals, n_out - ocol0);
+        const bool vec = nvalid == nvals;  // warp-uniform: whole chunk inside the matrix
         if (p.col_scale != nullptr) {
+          if (vec && ((reinterpret_cast<uintptr_t>(p.col_scale + ocol0) & 15) == 0)) {
+            const float4* sp = reinterpret_cast<const float4*>(p.col_scale + ocol0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvals && ocol0 + j < n_out) v[j] *= __ldg(p.col_scale + ocol0 + j);
+            for (int j = 0; j < 8; ++j) {
+              if (4 * j < nvals) {
+                const float4 ss = __ldg(sp + j);
+                v[4 * j] *= ss.x; v[4 * j + 1] *= ss.y; v[4 * j + 2] *= ss.z; v[4 * j + 3] *= ss.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) v[j] *= __ldg(p.col_scale + ocol0 + j);
+          }
         }
         if (row_ok) {
-          const int nvalid = min(nvals, n_out - ocol0);
           if (p.resid != nullptr) {
             if (p.resid_f32) {
               const float* rp = reinterpret_cast<const float*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+              if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += rp[j];
+                for (int j = 0; j < 8; ++j) {
+                  if (4 * j < nvals) {
+                    const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * j);
+                    v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) v[j] += rp[j];
+              }
             } else {
               const __nv_bfloat16* rp =
                   reinterpret_cast<const __nv_bfloat16*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+              if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+                for (int j = 0; j < 4; ++j) {
+                  if (8 * j < nvals) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(rp + 8 * j);
+                    v[8 * j] += bf16_lo(rr.x); v[8 * j + 1] += bf16_hi(rr.x); v[8 * j + 2] += bf16_lo(rr.y); v[8 * j + 3] += bf16_hi(rr.y);
+                    v[8 * j + 4] += bf16_lo(rr.z); v[8 * j + 5] += bf16_hi(rr.z); v[8 * j + 6] += bf16_lo(rr.w); v[8 * j + 7] += bf16_hi(rr.w);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nvalid) v[j] += __bfloat162float(rp[j]);
+              }
             }
           }
           if (p.out_f32) {
             float* cp = reinterpret_cast<float*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
-            if (nvalid == nvals && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            if (vec && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 if (j < nvals) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -236,7 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           } else {
             __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
-            if (nvalid == nvals && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            if (vec && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8)
                 if (j < nvals)
@@ -264,6 +314,86 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------- skinny GEMM (M <= 8): LLM decode
+// HBM-bound weight streaming: one warp per output column (two weight rows in GLU mode), 128-bit non-allocating loads of the
+// weight row, A rows re-read through L1, fp32 accumulate, warp-shuffle reduction, same epilogue contract as the tcgen05 path.
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& a) {
+  float s = bf16_lo(w.x) * bf16_lo(a.x);
+  s = fmaf(bf16_hi(w.x), bf16_hi(a.x), s);
+  s = fmaf(bf16_lo(w.y), bf16_lo(a.y), s);
+  s = fmaf(bf16_hi(w.y), bf16_hi(a.y), s);
+  s = fmaf(bf16_lo(w.z), bf16_lo(a.z), s);
+  s = fmaf(bf16_hi(w.z), bf16_hi(a.z), s);
+  s = fmaf(bf16_lo(w.w), bf16_lo(a.w), s);
+  s = fmaf(bf16_hi(w.w), bf16_hi(a.w), s);
+  return s;
+}
+
+template <int MR>
+__global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
+                                                   long long ldb, const GemmParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int n_out = p.glu ? p.N / 2 : p.N;
+  if (warp >= n_out) return;
+  const int oc = warp;
+  const int n0 = p.glu ? (oc / 16) * 32 + (oc % 16) : oc;
+  const __nv_bfloat16* w0 = B + static_cast<long long>(n0) * ldb;
+  const __nv_bfloat16* w1 = w0 + 16 * ldb;  // "up" row (GLU only)
+  float acc0[MR], acc1[MR];
+#pragma unroll
+  for (int m = 0; m < MR; ++m) acc0[m] = acc1[m] = 0.f;
+  const int chunks = p.K >> 3;
+#pragma unroll 4
+  for (int c = lane; c < chunks; c += 32) {
+    const uint4 wv0 = ld_stream16(w0 + c * 8);
+    uint4 wv1 = make_uint4(0, 0, 0, 0);
+    if (p.glu) wv1 = ld_stream16(w1 + c * 8);
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      if (m < p.M) {
+        const uint4 av = __ldg(reinterpret_cast<const uint4*>(A + m * lda + c * 8));
+        acc0[m] += dot8(wv0, av);
+        if (p.glu) acc1[m] += dot8(wv1, av);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MR; ++m) {
+    acc0[m] = warp_sum(acc0[m]);
+    if (p.glu) acc1[m] = warp_sum(acc1[m]);
+  }
+  if (lane != 0) return;
+#pragma unroll
+  for (int m = 0; m < MR; ++m) {
+    if (m >= p.M) break;
+    float v = acc0[m] * p.alpha;
+    if (p.bias) v += p.bias[n0];
+    if (p.glu) {
+      float u = acc1[m] * p.alpha;
+      if (p.bias) u += p.bias[n0 + 16];
+      v = apply_act(v, p.act) * u;
+    } else {
+      v = apply_act(v, p.act);
+    }
+    if (p.col_scale) v *= p.col_scale[oc];
+    if (p.resid) {
+      const long long off = static_cast<long long>(m) * p.ldr + oc;
+      v += p.resid_f32 ? reinterpret_cast<const float*>(p.resid)[off] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[off]);
+    }
+    const long long off = static_cast<long long>(m) * p.ldc + oc;
+    if (p.out_f32)
+      reinterpret_cast<float*>(p.C)[off] = v;
+    else
+      reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16(v);
   }
 }
 
@@ -445,6 +575,19 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
       (g->batch > 1 && ((g->strideA % 8) || (g->strideB % 8))))
     return set_error(VG_EINVAL, "vg_gemm: A/B must be 16B aligned with lda/ldb/strides multiples of 8 (lda=%lld ldb=%lld)", g->lda, g->ldb);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (g->M <= 8 && g->batch == 1 && g->force_block_n == 0 && (g->K % 8) == 0) {
+    GemmParams p = to_params(g);
+    const int n_out = g->glu ? g->N / 2 : g->N;
+    const unsigned blocks = (static_cast<unsigned>(n_out) + 7) / 8;
+    const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(g->A);
+    const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(g->B);
+    if (g->M == 1) gemv_kernel<1><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    else if (g->M <= 2) gemv_kernel<2><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    else if (g->M <= 4) gemv_kernel<4><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    else gemv_kernel<8><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    count_launch();
+    return check_launch("gemv_kernel");
+  }
   int bn = g->force_block_n;
   if (bn == 0) {
     const long long tm = (g->M + BLOCK_M - 1) / BLOCK_M;

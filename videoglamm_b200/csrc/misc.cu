@@ -56,6 +56,52 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
   }
 }
 
+// one 256-thread block per row (few, wide rows: LLM decode), values cached in registers, block reduction through smem
+template <int MAXV>
+__global__ void __launch_bounds__(256) norm_block_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, const float* w,
+                                                         const float* b, int cols, float eps, int rms) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const long long xo = static_cast<long long>(row) * ldx, yo = static_cast<long long>(row) * ldy;
+  float v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    v[i] = c < cols ? ld(x, xdt, xo + c) : 0.f;
+    sum += v[i];
+  }
+  auto block_sum = [&](float t) {
+    t = warp_sum(t);
+    __syncthreads();
+    if (lane == 0) red[wid] = t;
+    __syncthreads();
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r += red[i];
+    return r;
+  };
+  float mean = 0.f;
+  if (!rms) mean = block_sum(sum) / cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    const float d = c < cols ? v[i] - mean : 0.f;
+    sq += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(sq) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = tid + i * 256;
+    if (c < cols) {
+      float o = (v[i] - mean) * rstd * w[c];
+      if (b) o += b[c];
+      st(y, ydt, yo + c, o);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ add / cast
 __global__ void add_kernel(const void* a, int adt, long long lda, int a_rows, const void* b, int bdt, long long ldb, int b_rows, float alpha, void* out,
                            int odt, long long ldo, long long rows, int cols) {
@@ -349,6 +395,16 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
   if (!x || !y || !w || rows <= 0 || cols <= 0) return set_error(VG_EINVAL, "vg_norm: bad argument");
   const int warps = 8;
   const unsigned grid = (rows + warps - 1) / warps;
+  if (cols > 512 && cols <= 256 * 16 && rows < 2048) {  // wide rows, not enough of them to fill the chip with one warp each
+    if (cols <= 256 * 4)
+      norm_block_kernel<4><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+    else if (cols <= 256 * 8)
+      norm_block_kernel<8><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+    else
+      norm_block_kernel<16><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+    count_launch();
+    return check_launch("norm_block_kernel");
+  }
   if (cols <= 32 * 4)
     norm_kernel<4><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
   else if (cols <= 32 * 12)

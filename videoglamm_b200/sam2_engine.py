@@ -41,6 +41,7 @@ class Sam2Engine:
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("Sam2Engine needs a CUDA device (there is no CPU path)")
+        self.frames_per_encode = 8
         self._sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
         self._pack()
         del self._sd
@@ -421,7 +422,13 @@ class Sam2Engine:
         T, B = images.shape[0], text_embeds.shape[0]
         HW, C = self.HW, cfg.d_model
         Hv, Wv = video_hw
-        feats = [self.forward_image(images[t:t + 1].float()) for t in range(T)]  # no temporal dependence: encode up front
+        # no temporal dependence in the image encoder: encode all frames up front, `frames_per_encode` at a time (fills GEMM waves)
+        feats = []
+        for t0 in range(0, T, self.frames_per_encode):
+            fb = self.forward_image(images[t0:t0 + self.frames_per_encode].float())
+            nb = fb["top"].shape[0] // self.HW
+            for i in range(nb):
+                feats.append({k: v.view(nb, -1, v.shape[-1])[i] for k, v in fb.items()})
         f0 = feats[0]
         pix0 = ops.add(f0["top"], self.no_mem_embed)                               # init cond frame: + no_mem_embed (sam2_base.py:641-645)
         per_obj = [self.forward_sam_heads(pix0, f0["s0"], f0["s1"], text_embeds[o:o + 1], 1) for o in range(B)]
