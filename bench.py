@@ -94,7 +94,7 @@ def synth_inputs(seed: int, pinned: bool):
 
 def run_engine(args):
     import torch.distributed as dist
-    from videoglamm_b200 import build, ops
+    from videoglamm_b200 import build, ops, parallel as P
     from videoglamm_b200.config import Sam2Config, make_lmm_config
     from videoglamm_b200.model import VideoGLaMMForCausalLM
     from videoglamm_b200.statedict import random_state_dict, videoglamm_param_shapes
@@ -120,15 +120,10 @@ def run_engine(args):
         out_ids, segs = model.inference([im], [ctx], [sam], ids, None, [VIDEO_HW], max_new_tokens=N_NEW, use_sam2_video_branch=True, forced_tokens=forced)
         return out_ids, segs
 
-    def gather_masks(segs):
-        """§8(e): the only collective on the path — bit-packed final masks to rank 0."""
-        if world == 1:
-            return
-        import numpy as np
-        m = np.stack([segs[0][t][0] for t in sorted(segs[0])])
-        packed = torch.from_numpy(np.packbits(m)).to(dev)
-        bufs = [torch.empty_like(packed) for _ in range(world)] if rank == 0 else None
-        dist.gather(packed, bufs, dst=0)
+    def gather_masks(out_ids, segs):
+        """§8(e): the only collective on the path — token ids + bit-packed final masks to rank 0 (videoglamm_b200.parallel)."""
+        if world > 1:
+            P.gather_results([(rank, out_ids, segs[0])], device=dev)
 
     def timed(inp, steps):
         if world > 1:
@@ -137,8 +132,8 @@ def run_engine(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
-            _, segs = step(inp)
-            gather_masks(segs)
+            out_ids, segs = step(inp)
+            gather_masks(out_ids, segs)
         e1.record()
         if world > 1:
             dist.barrier()
