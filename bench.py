@@ -158,6 +158,9 @@ def run_engine(args):
     step(resident)
     torch.cuda.synchronize()
     prof = ops.gemm_profile(False)
+    if rank == 0 and os.environ.get("VG_GEMM_SHAPES"):
+        for row in prof["top_shapes"]:
+            print("gemm shape", row, file=sys.stderr)
     cpu = cpu_baseline_sample(L) if (rank == 0 and not args.no_cpu_baseline) else None
     if rank == 0:
         tf_peak, hbm_peak, src = _peaks()

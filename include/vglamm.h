@@ -91,6 +91,10 @@ typedef struct VgAttention {
   int causal, window;
   int q_win, q_gridw, q_nwx, q_nwy;
   int k_win, k_gridw, k_nwx, k_nwy;
+  void* workspace; long long workspace_bytes;   /* optional fp32 scratch: enables split-K for single-query (decode) attention;
+                                                   B*H*16*(max(D,128)+2)*4 bytes always suffices */
+  const int* nk_dev;                            /* optional (Nq == 1 only): the number of keys is read from this DEVICE int at run time
+                                                   (Nk is then only an upper bound) so a captured decode step can be replayed */
 } VgAttention;
 int vg_attention(const VgAttention* a, void* stream);
 
@@ -145,6 +149,11 @@ int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* s
 int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream);
 /* out[r][:] = table[ids[r]][:] (nn.Embedding), bf16 table -> out dtype */
 int vg_embedding(const void* table, long long ldt, const long long* ids, void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
+/* cache[*pos_dev][col0 : col0+cols] = src[0][col0 : col0+cols] for a bf16 row (KV-cache append at a device-side position, so that
+ * the decode step is position-independent at launch level and can be captured in a CUDA graph and replayed). */
+int vg_row_scatter(const void* src, void* cache, long long ld_cache, const int* pos_dev, int col0, int cols, void* stream);
+/* adds n to the launch counter (replayed CUDA-graph nodes are launches too) */
+void vg_launch_count_add(long long n);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

@@ -17,7 +17,28 @@ def step():
 n_warm = int(os.environ.get("WARM", 2))
 for _ in range(n_warm): step()
 torch.cuda.synchronize()
-if os.environ.get("STAGES"):
+if os.environ.get("E2E_STAGES"):
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        e = [ev() for _ in range(3)]
+        e[0].record()
+        out_ids, emb = model.lmm.generate(inp[3], inp[0], inp[1], bench.N_NEW, forced=forced)
+        e[1].record()
+        frames = model.sam.run_video(inp[2], emb[:, None, :], bench.VIDEO_HW, binary=True)
+        e[2].record(); torch.cuda.synchronize()
+        print(f"lmm.generate {e[0].elapsed_time(e[1]):.2f} ms   sam.run_video {e[1].elapsed_time(e[2]):.2f} ms")
+    import time
+    from videoglamm_b200 import ops as _o
+    vis = model.lmm.visual_tokens(inp[0], inp[1]); torch.cuda.synchronize()
+    for name, fn in (("g_vis", lambda: model.lmm.g_vis((tuple(inp[0].shape), tuple(inp[1].shape)), model.lmm.visual_tokens, images=inp[0], context_images=inp[1])),
+                     ("g_prefill", lambda: model.lmm.g_prefill((1696,), model.lmm._prefill_last, x=torch.zeros(1696, 3072, device="cuda"))),
+                     ("g_decode", lambda: model.lmm.g_decode((2048,), lambda: model.lmm._decode_step(2048), mutable_state=(model.lmm.dec_tok, model.lmm.dec_pos, model.lmm.dec_nk)))):
+        fn(); torch.cuda.synchronize()
+        a, b = ev(), ev(); a.record()
+        for _ in range(5): fn()
+        b.record(); torch.cuda.synchronize()
+        print(f"{name}: {a.elapsed_time(b)/5:.3f} ms")
+elif os.environ.get("STAGES"):
     # coarse per-stage CUDA-event timing
     ev = lambda: torch.cuda.Event(enable_timing=True)
     dev = "cuda"

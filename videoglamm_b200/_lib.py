@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         _lib.vg_last_error.restype = C.c_char_p
         _lib.vg_launch_count.restype = C.c_longlong
         _lib.vg_launch_count_reset.restype = None
+        _lib.vg_launch_count_add.restype = None
+        _lib.vg_launch_count_add.argtypes = [C.c_longlong]
     return _lib
 
 
@@ -58,6 +60,8 @@ class VgAttention(C.Structure):
         ("causal", C.c_int), ("window", C.c_int),
         ("q_win", C.c_int), ("q_gridw", C.c_int), ("q_nwx", C.c_int), ("q_nwy", C.c_int),
         ("k_win", C.c_int), ("k_gridw", C.c_int), ("k_nwx", C.c_int), ("k_nwy", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+        ("nk_dev", C.c_void_p),
     ]
 
 
@@ -65,5 +69,5 @@ class VgAttention(C.Structure):
 SYMBOLS = [
     "vg_last_error", "vg_version", "vg_launch_count", "vg_launch_count_reset", "vg_gemm", "vg_gemm_naive", "vg_attention", "vg_norm",
     "vg_add", "vg_pool2x2", "vg_upsample2x_add", "vg_convt2x2_epilogue", "vg_im2col", "vg_dwconv", "vg_conv3x3s2_ln_gelu", "vg_bilinear",
-    "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax",
+    "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax", "vg_row_scatter", "vg_launch_count_add",
 ]

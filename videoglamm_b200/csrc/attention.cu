@@ -18,6 +18,9 @@ struct AttnParams {
   int causal, window;
   int q_win, q_gridw, q_nwx, q_nwy;  // 2D window addressing for q/o rows (0 = linear)
   int k_win, k_gridw, k_nwx, k_nwy;  // 2D window addressing for k/v rows
+  float* ws;                         // split-K partials for single-query attention
+  int nsplit;
+  const int* nk_dev;                 // optional: number of keys read from device memory (graph-replayable decode)
 };
 
 // row index inside the (batch-strided) tensor for token t of batch entry b
@@ -201,7 +204,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 // HBM/L2-bound: one block per (head, batch); each warp walks 32-key groups: lane-per-key QK^T (no shuffles in the dot product),
 // warp-level online softmax, then lane-per-feature PV with the probabilities staged in shared memory; warps merged at the end.
 template <int DMAX>
-__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
+  if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
   constexpr int NW = 8, EPL = DMAX / 32;  // features per lane in the PV phase
   __shared__ float s_q[DMAX];
   __shared__ float s_p[NW][32];
@@ -215,14 +219,18 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
   __syncthreads();
   int k_begin = 0;
   if (p.window > 0) k_begin = max(0, p.Nk - 1 - p.window);
+  // this block's key range (split-K over blockIdx.z)
+  const int span = (p.Nk - k_begin + p.nsplit - 1) / p.nsplit;
+  const int k_lo = k_begin + blockIdx.z * ((span + 31) / 32 * 32);
+  const int k_hi = min(p.Nk, k_lo + (span + 31) / 32 * 32);
   float m_run = -INFINITY, l_run = 0.f, o[EPL];
 #pragma unroll
   for (int e = 0; e < EPL; ++e) o[e] = 0.f;
   const int chunks = p.D >> 3;
-  for (int g0 = k_begin + warp * 32; g0 < p.Nk; g0 += NW * 32) {
+  for (int g0 = k_lo + warp * 32; g0 < k_hi; g0 += NW * 32) {
     const int j = g0 + lane;
     float sc = -INFINITY;
-    if (j < p.Nk) {
+    if (j < k_hi) {
       const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * p.k_rs);
       float acc = 0.f;
       for (int c = 0; c < chunks; ++c) {
@@ -236,13 +244,13 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
       sc = acc;
     }
     const float m_new = fmaxf(m_run, warp_max(sc));
-    const float pj = (j < p.Nk) ? __expf(sc - m_new) : 0.f;
+    const float pj = (j < k_hi) ? __expf(sc - m_new) : 0.f;
     const float alpha = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
     l_run = l_run * alpha + warp_sum(pj);
     m_run = m_new;
     s_p[warp][lane] = pj;
     __syncwarp();
-    const int nvalid = min(32, p.Nk - g0);
+    const int nvalid = min(32, k_hi - g0);
 #pragma unroll
     for (int e = 0; e < EPL; ++e) o[e] *= alpha;
     for (int jj = 0; jj < nvalid; ++jj) {
@@ -269,11 +277,47 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(const AttnParams p) {
   float l_all = 0.f;
 #pragma unroll
   for (int w = 0; w < NW; ++w) l_all += (s_m[w] == -INFINITY) ? 0.f : s_l[w] * __expf(s_m[w] - m_all);
+  if (p.nsplit > 1) {  // un-normalised partial (m, l, o[D]) for the merge kernel
+    float* wp = p.ws + ((static_cast<long long>(b) * gridDim.x + h) * p.nsplit + blockIdx.z) * (DMAX + 2);
+    if (tid == 0) {
+      wp[0] = m_all;
+      wp[1] = l_all;
+    }
+    for (int d = tid; d < p.D; d += 256) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
+      wp[2 + d] = acc;
+    }
+    return;
+  }
   __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
   for (int d = tid; d < p.D; d += 256) {
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
+    op[d] = __float2bfloat16(l_all > 0.f ? acc / l_all : 0.f);
+  }
+}
+
+template <int DMAX>
+__global__ void attn_decode_merge_kernel(const AttnParams p) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const float* wp = p.ws + (static_cast<long long>(b) * gridDim.x + h) * p.nsplit * (DMAX + 2);
+  float m_all = -INFINITY;
+  for (int s = 0; s < p.nsplit; ++s) m_all = fmaxf(m_all, wp[s * (DMAX + 2)]);
+  float l_all = 0.f;
+  for (int s = 0; s < p.nsplit; ++s) {
+    const float m = wp[s * (DMAX + 2)];
+    l_all += (m == -INFINITY) ? 0.f : wp[s * (DMAX + 2) + 1] * __expf(m - m_all);
+  }
+  __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
+  for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) {
+      const float m = wp[s * (DMAX + 2)];
+      acc += (m == -INFINITY) ? 0.f : wp[s * (DMAX + 2) + 2 + d] * __expf(m - m_all);
+    }
     op[d] = __float2bfloat16(l_all > 0.f ? acc / l_all : 0.f);
   }
 }
@@ -317,14 +361,34 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   p.scale = a->scale; p.causal = a->causal; p.window = a->window;
   p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
   p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
+  p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && a->Nk >= 256) {  // decode: causal is a no-op for the newest query
-    dim3 grid(a->H, a->B);
-    if (a->D <= 128)
+  if (a->nk_dev != nullptr && a->Nq != 1) return set_error(VG_EINVAL, "vg_attention: nk_dev is only supported for single-query attention");
+  if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && (a->Nk >= 256 || a->nk_dev != nullptr)) {  // decode: causal is a no-op for the newest query
+    const int dmax = a->D <= 128 ? 128 : 256;
+    int nsplit = 1;
+    if (a->workspace != nullptr) {
+      nsplit = (a->Nk + 383) / 384;
+      if (nsplit > 16) nsplit = 16;
+      const long long need = static_cast<long long>(a->B) * a->H * nsplit * (dmax + 2) * 4;
+      if (need > a->workspace_bytes) nsplit = 1;
+    }
+    p.ws = static_cast<float*>(a->workspace);
+    p.nsplit = nsplit;
+    dim3 grid(a->H, a->B, nsplit);
+    if (dmax == 128)
       attn_decode_kernel<128><<<grid, 256, 0, s>>>(p);
     else
       attn_decode_kernel<256><<<grid, 256, 0, s>>>(p);
     count_launch();
+    if (nsplit > 1) {
+      dim3 mg(a->H, a->B);
+      if (dmax == 128)
+        attn_decode_merge_kernel<128><<<mg, 128, 0, s>>>(p);
+      else
+        attn_decode_merge_kernel<256><<<mg, 128, 0, s>>>(p);
+      count_launch();
+    }
     return check_launch("attn_decode_kernel");
   }
   if (a->D <= 32) return launch_attn<32>(p, s);

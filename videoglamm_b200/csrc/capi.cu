@@ -28,3 +28,4 @@ extern "C" const char* vg_last_error(void) { return vg::g_err; }
 extern "C" int vg_version(void) { return 1; }
 extern "C" long long vg_launch_count(void) { return vg::g_launches.load(); }
 extern "C" void vg_launch_count_reset(void) { vg::g_launches.store(0); }
+extern "C" void vg_launch_count_add(long long n) { vg::g_launches.fetch_add(n); }

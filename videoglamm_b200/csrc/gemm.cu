@@ -44,9 +44,50 @@ struct GemmParams {
   int b_shared;  // B (weights) shared by every batch entry
 };
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 resolution of the GELU output): ~15 instructions, branch-free,
+// instead of libdevice erff (~100 with divergence), which made GELU epilogues the bottleneck of the MLP GEMMs.
+__device__ __forceinline__ float fast_erf(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float y = 1.0f - poly * t * __expf(-ax * ax);
+  return copysignf(y, x);
+}
+
+template <int N>
+__device__ __forceinline__ void apply_act_vec(float (&v)[32], int act) {
+  // one switch per 32-column chunk (a per-element switch compiled to ~300 cycles/element and made every activated GEMM 4x slower)
+  switch (act) {
+    case VG_ACT_GELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = 0.5f * v[j] * (1.0f + fast_erf(v[j] * 0.70710678118654752f));
+      break;
+    case VG_ACT_QUICKGELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
+      break;
+    case VG_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+      break;
+    case VG_ACT_SILU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+      break;
+    case VG_ACT_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+      break;
+    default: break;
+  }
+}
+
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case VG_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+    case VG_ACT_GELU: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
     case VG_ACT_QUICKGELU: return x / (1.0f + __expf(-1.702f * x));
     case VG_ACT_RELU: return fmaxf(x, 0.0f);
     case VG_ACT_SILU: return x / (1.0f + __expf(-x));
@@ -207,15 +248,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         int ocol0, nvals;
         if (p.glu) {
+          apply_act_vec<16>(v, p.act);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act) * v[16 + j];
+          for (int j = 0; j < 16; ++j) v[j] *= v[16 + j];
           ocol0 = col0 >> 1;
           nvals = 16;
         } else {
-          if (p.act != VG_ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
+          if (p.act != VG_ACT_NONE) apply_act_vec<32>(v, p.act);
           ocol0 = col0;
           nvals = 32;
         }
@@ -338,31 +377,49 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& a) {
   return s;
 }
 
-template <int MR>
+template <int MR, int WPC>  // MR: rows of A held in registers; WPC: warps cooperating on one output column (split along K)
 __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
                                                    long long ldb, const GemmParams p) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  constexpr int U = 8;  // independent 16-byte weight loads in flight per lane
+  __shared__ float s_part[8][2 * MR];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = p.glu ? p.N / 2 : p.N;
-  if (warp >= n_out) return;
-  const int oc = warp;
+  const int oc = (blockIdx.x * 8 + wib) / WPC;
+  const int ks = wib % WPC;  // K slice of this warp
+  const bool active = oc < n_out;
   const int n0 = p.glu ? (oc / 16) * 32 + (oc % 16) : oc;
-  const __nv_bfloat16* w0 = B + static_cast<long long>(n0) * ldb;
+  const __nv_bfloat16* w0 = B + static_cast<long long>(active ? n0 : 0) * ldb;
   const __nv_bfloat16* w1 = w0 + 16 * ldb;  // "up" row (GLU only)
   float acc0[MR], acc1[MR];
 #pragma unroll
   for (int m = 0; m < MR; ++m) acc0[m] = acc1[m] = 0.f;
   const int chunks = p.K >> 3;
-#pragma unroll 4
-  for (int c = lane; c < chunks; c += 32) {
-    const uint4 wv0 = ld_stream16(w0 + c * 8);
-    uint4 wv1 = make_uint4(0, 0, 0, 0);
-    if (p.glu) wv1 = ld_stream16(w1 + c * 8);
+  if (active) {
+    for (int c0 = ks * 32 + lane; c0 < chunks; c0 += 32 * WPC * U) {
+      uint4 wv0[U], wv1[U];
 #pragma unroll
-    for (int m = 0; m < MR; ++m) {
-      if (m < p.M) {
-        const uint4 av = __ldg(reinterpret_cast<const uint4*>(A + m * lda + c * 8));
-        acc0[m] += dot8(wv0, av);
-        if (p.glu) acc1[m] += dot8(wv1, av);
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u * 32 * WPC;
+        wv0[u] = make_uint4(0, 0, 0, 0);
+        wv1[u] = make_uint4(0, 0, 0, 0);
+        if (c < chunks) {
+          wv0[u] = ld_stream16(w0 + c * 8);
+          if (p.glu) wv1[u] = ld_stream16(w1 + c * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = c0 + u * 32 * WPC;
+        if (c < chunks) {
+#pragma unroll
+          for (int m = 0; m < MR; ++m) {
+            if (m < p.M) {
+              const uint4 av = __ldg(reinterpret_cast<const uint4*>(A + m * lda + c * 8));
+              acc0[m] += dot8(wv0[u], av);
+              if (p.glu) acc1[m] += dot8(wv1[u], av);
+            }
+          }
+        }
       }
     }
   }
@@ -371,7 +428,28 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
     acc0[m] = warp_sum(acc0[m]);
     if (p.glu) acc1[m] = warp_sum(acc1[m]);
   }
-  if (lane != 0) return;
+  if (WPC > 1) {
+    if (lane == 0) {
+#pragma unroll
+      for (int m = 0; m < MR; ++m) {
+        s_part[wib][2 * m] = acc0[m];
+        s_part[wib][2 * m + 1] = acc1[m];
+      }
+    }
+    __syncthreads();
+    if (ks != 0) return;
+#pragma unroll
+    for (int m = 0; m < MR; ++m) {
+      acc0[m] = 0.f;
+      acc1[m] = 0.f;
+#pragma unroll
+      for (int j = 0; j < WPC; ++j) {
+        acc0[m] += s_part[wib + j][2 * m];
+        acc1[m] += s_part[wib + j][2 * m + 1];
+      }
+    }
+  }
+  if (lane != 0 || !active) return;
 #pragma unroll
   for (int m = 0; m < MR; ++m) {
     if (m >= p.M) break;
@@ -394,6 +472,19 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
       reinterpret_cast<float*>(p.C)[off] = v;
     else
       reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16(v);
+  }
+}
+
+template <int MR>
+static void launch_gemv(const VgGemm* g, const GemmParams& p, cudaStream_t s) {
+  const int n_out = g->glu ? g->N / 2 : g->N;
+  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(g->A);
+  const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(g->B);
+  // few columns and long rows: split K over 4 warps so enough bytes are in flight to cover HBM latency
+  if (n_out < 6144 && g->K >= 2048) {
+    gemv_kernel<MR, 4><<<(static_cast<unsigned>(n_out) * 4 + 7) / 8, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+  } else {
+    gemv_kernel<MR, 1><<<(static_cast<unsigned>(n_out) + 7) / 8, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
   }
 }
 
@@ -577,14 +668,10 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g->M <= 8 && g->batch == 1 && g->force_block_n == 0 && (g->K % 8) == 0) {
     GemmParams p = to_params(g);
-    const int n_out = g->glu ? g->N / 2 : g->N;
-    const unsigned blocks = (static_cast<unsigned>(n_out) + 7) / 8;
-    const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(g->A);
-    const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(g->B);
-    if (g->M == 1) gemv_kernel<1><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
-    else if (g->M <= 2) gemv_kernel<2><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
-    else if (g->M <= 4) gemv_kernel<4><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
-    else gemv_kernel<8><<<blocks, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    if (g->M == 1) launch_gemv<1>(g, p, s);
+    else if (g->M <= 2) launch_gemv<2>(g, p, s);
+    else if (g->M <= 4) launch_gemv<4>(g, p, s);
+    else launch_gemv<8>(g, p, s);
     count_launch();
     return check_launch("gemv_kernel");
   }

@@ -14,7 +14,7 @@ __device__ __forceinline__ void st(void* p, int dt, long long i, float v) {
   else
     reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }  // exact: small tensors only
 
 static inline unsigned blocks_for(long long n, int threads) { return static_cast<unsigned>((n + threads - 1) / threads); }
 
@@ -354,6 +354,11 @@ __global__ void embedding_kernel(const __nv_bfloat16* table, long long ldt, cons
   st(out, odt, r * ldo + c, __bfloat162float(table[ids[r] * ldt + c]));
 }
 
+__global__ void row_scatter_kernel(const __nv_bfloat16* src, __nv_bfloat16* cache, long long ld, const int* pos, int col0, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cols) cache[static_cast<long long>(*pos) * ld + col0 + i] = src[col0 + i];
+}
+
 // one block (256 threads) per row
 __global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
   const int row = blockIdx.x;
@@ -516,4 +521,12 @@ extern "C" int vg_argmax(const void* x, int x_dtype, long long ldx, long long* o
   argmax_kernel<<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, out, cols);
   count_launch();
   return check_launch("argmax_kernel");
+}
+
+extern "C" int vg_row_scatter(const void* src, void* cache, long long ld_cache, const int* pos_dev, int col0, int cols, void* stream) {
+  if (!src || !cache || !pos_dev || cols <= 0) return set_error(VG_EINVAL, "vg_row_scatter: bad argument");
+  row_scatter_kernel<<<blocks_for(cols, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(cache), ld_cache,
+                                                                pos_dev, col0, cols);
+  count_launch();
+  return check_launch("row_scatter_kernel");
 }

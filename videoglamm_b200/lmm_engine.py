@@ -15,6 +15,7 @@ from dataclasses import dataclass
 import torch
 
 from . import ops
+from .graphs import GraphedStage
 from .config import ClipConfig, Iv2Config, LmmConfig, PhiConfig
 
 BF, F32 = torch.bfloat16, torch.float32
@@ -168,6 +169,12 @@ class LmmEngine:
             self.layers.append(dict(n1=pk.vec(p + ".input_layernorm.weight"), qkv=pk.lin(p + ".self_attn.qkv_proj"), o=pk.lin(p + ".self_attn.o_proj"),
                                     n2=pk.vec(p + ".post_attention_layernorm.weight"), gu=gu.to(BF).contiguous(), down=pk.lin(p + ".mlp.down_proj")))
         self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
+        # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
+        self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
+        self.dec_tok = torch.zeros(1, device=self.dev, dtype=torch.int64)
+        self.dec_pos = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.dec_nk = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        self.dec_qkv = torch.zeros((1, 3 * ph.hidden), device=self.dev, dtype=BF)
 
     # ------------------------------------------------------------------------------------------------ vision side
     def _project(self, x3: torch.Tensor, layers) -> torch.Tensor:
@@ -201,9 +208,44 @@ class LmmEngine:
     def _alloc_cache(self, max_len: int):
         ph = self.cfg.phi
         if self.kv is None or self.kv[0].shape[0] < max_len:
-            self.kv = [torch.empty((max_len, 3 * ph.hidden), device=self.dev, dtype=BF) for _ in range(ph.layers)]
+            n = max(max_len, ph.max_len)                 # allocate once at the model's context length: graphs keep these pointers
+            self.kv = [torch.zeros((n, 3 * ph.hidden), device=self.dev, dtype=BF) for _ in range(ph.layers)]
+            self.g_prefill.entries.clear()
+            self.g_decode.entries.clear()
 
-    def _llm(self, x: torch.Tensor, pos0: int) -> torch.Tensor:
+    def _prefill_last(self, x: torch.Tensor) -> torch.Tensor:
+        """Prefill rows [0, n); returns the final-norm hidden state of the LAST row only ([1, hidden] fp32) — all that decoding needs."""
+        return self._llm(x, 0, last_only=True)
+
+    def _decode_step(self, kv_bound: int):
+        """One KV-cached decode step whose launch sequence does not depend on the position: token id, position and key count live in
+        device memory (dec_tok / dec_pos / dec_nk), the new K/V row is scattered into the cache by a device-indexed copy, and the
+        single-query attention reads its key count from dec_nk. Captured once and replayed for every generated token."""
+        ph = self.cfg.phi
+        H, hd, D = ph.heads, ph.head_dim, ph.hidden
+        x = ops.embedding(self.embed, self.dec_tok)
+        for l, L in enumerate(self.layers):
+            cache = self.kv[l]
+            h = ops.norm(x, L["n1"], eps=ph.eps, rms=True)
+            ops.gemm(h, L["qkv"].w, out=self.dec_qkv)
+            ops.rope_neox_(self.dec_qkv, self.dec_pos, 2 * H, hd, ph.rope_theta)
+            ops.row_scatter(self.dec_qkv, cache, self.dec_pos, D, 2 * D)
+            q = self.dec_qkv[:, :D].unflatten(1, (H, hd))[None]
+            k = cache[:kv_bound, D:2 * D].unflatten(1, (H, hd))[None]
+            v = cache[:kv_bound, 2 * D:].unflatten(1, (H, hd))[None]
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk)
+            x = ops.gemm(o.view(1, D), L["o"].w, resid=x, out=x)
+            h = ops.norm(x, L["n2"], eps=ph.eps, rms=True)
+            h = ops.gemm(h, L["gu"], glu=True, act="silu")
+            x = ops.gemm(h, L["down"].w, resid=x, out=x)
+        h_last = ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
+        nxt = ops.argmax(ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32))
+        self.dec_tok.copy_(nxt)                            # greedy continuation; the host overwrites dec_tok when a token is forced
+        self.dec_pos.add_(1)
+        self.dec_nk.add_(1)
+        return h_last, nxt
+
+    def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False) -> torch.Tensor:
         """HF Phi3Model.forward (called at language_model/phi3.py:72-81) on rows [pos0, pos0+n) given a cache holding rows [0,pos0).
         x fp32 [n, hidden] (modified in place as the residual stream) -> final-norm hidden fp32 [n, hidden]."""
         ph = self.cfg.phi
@@ -224,20 +266,18 @@ class LmmEngine:
             h = ops.norm(x, L["n2"], eps=ph.eps, rms=True)
             h = ops.gemm(h, L["gu"], glu=True, act="silu")
             x = ops.gemm(h, L["down"].w, resid=x, out=x)
+        if last_only:
+            x = x[-1:]
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
 
     def embed_prompt(self, input_ids: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
         """prepare_inputs_labels_for_multimodal arch.py:283-379 (video case): embed(ids before the -200 run) + visual + embed(rest)."""
-        ids = input_ids.reshape(-1)
-        idx = torch.where(ids == IMAGE_TOKEN_INDEX)[0]
+        ids_host = input_ids.reshape(-1).cpu()            # one small D2H per clip; the prompt structure is host control flow
+        idx = torch.where(ids_host == IMAGE_TOKEN_INDEX)[0]
         start, end = int(idx[0]), int(idx[-1])
-        parts = []
-        if start > 0:
-            parts.append(ops.embedding(self.embed, ids[:start].contiguous()))
-        parts.append(vis)
-        if end + 1 < ids.numel():
-            parts.append(ops.embedding(self.embed, ids[end + 1:].contiguous()))
-        return torch.cat(parts, 0).contiguous()
+        text = torch.cat([ids_host[:start], ids_host[end + 1:]]).to(self.dev)
+        emb = ops.embedding(self.embed, text) if text.numel() else torch.zeros((0, self.embed.shape[1]), device=self.dev)
+        return torch.cat([emb[:start], vis, emb[start:]], 0).contiguous()
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, images: torch.Tensor, context_images: torch.Tensor, max_new_tokens: int, eos_ids=(),
@@ -246,28 +286,35 @@ class LmmEngine:
         returns (output_ids int64 [1, L_txt+N] incl. -200 sentinels, pred_embeddings fp32 [n_seg, out_dim]).
         The hidden state that PREDICTED each [SEG] (mask shifted by one, :803-806) is the final-norm hidden of the step that emitted it."""
         cfg = self.cfg
-        vis = self.visual_tokens(images, context_images)
+        vis = self.g_vis((tuple(images.shape), tuple(context_images.shape)), self.visual_tokens, images=images, context_images=context_images)
         x = self.embed_prompt(input_ids, vis)
         L0 = x.shape[0]
         self._alloc_cache(L0 + max_new_tokens + 1)
-        hidden = self._llm(x, 0)
-        h_last = hidden[-1:].contiguous()
+        dbg = None
+        if return_debug:
+            hidden = self._llm(x, 0)
+            h_last = hidden[-1:].contiguous()
+            dbg = dict(prefill_hidden=hidden, logits=[])
+        else:
+            h_last = self.g_prefill((L0,), self._prefill_last, x=x)
         new_ids, seg_hidden = [], []
-        dbg = dict(prefill_hidden=hidden, logits=[]) if return_debug else None
+        kv_bound = min(self.kv[0].shape[0], (L0 + max_new_tokens + 511) // 512 * 512)
+        nxt_dev = ops.argmax(ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32))
         for step in range(max_new_tokens):
-            logits = ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32)
-            nxt = int(ops.argmax(logits)[0])
-            if return_debug:
-                dbg["logits"].append(logits)
+            nxt = int(nxt_dev[0])                           # host sync per token: EOS / [SEG] bookkeeping
             if forced and step in forced:
                 nxt = forced[step]
             new_ids.append(nxt)
             if nxt == cfg.seg_token_idx:
-                seg_hidden.append(h_last)
+                seg_hidden.append(h_last.clone())
             if nxt in eos_ids or step == max_new_tokens - 1:
                 break
-            e = ops.embedding(self.embed, torch.tensor([nxt], device=self.dev, dtype=torch.int64))
-            h_last = self._llm(e, L0 + step)
+            if step == 0:
+                self.dec_pos.fill_(L0)
+                self.dec_nk.fill_(L0 + 1)
+            if step == 0 or (forced and step in forced):
+                self.dec_tok.fill_(nxt)
+            h_last, nxt_dev = self.g_decode((kv_bound,), lambda: self._decode_step(kv_bound), mutable_state=(self.dec_tok, self.dec_pos, self.dec_nk))
         out_ids = torch.cat([input_ids.reshape(1, -1), torch.tensor([new_ids], device=input_ids.device, dtype=torch.int64)], dim=1)
         if seg_hidden:
             hs = ops.cast(torch.cat(seg_hidden, 0), BF)

@@ -100,7 +100,7 @@ def gemm_profile(enable: bool):
         a[0] += 1
         a[1] += ms
         a[2] += fl
-    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:12]
+    top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:40]
     return {"n": len(rec), "ms": sum(v[1] for v in by_shape.values()), "flops": sum(v[2] for v in by_shape.values()),
             "top_shapes": [{"MNKB": list(k), "launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)} for k, v in top]}
 
@@ -114,7 +114,8 @@ def launch_count_reset() -> None:
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, causal: bool = False, window: int = 0,
-              out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None) -> torch.Tensor:
+              out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None,
+              nk_dev: torch.Tensor | None = None) -> torch.Tensor:
     """q [B,Nq,H,D], k/v [B,Nk,H,D] bf16 views (any strides with unit last stride) -> out [B,Nq,H,D] (contiguous unless given).
     q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
     un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
@@ -144,6 +145,12 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
     a.scale = float(scale if scale is not None else D ** -0.5)
     a.causal, a.window = int(causal), int(window)
+    if nk_dev is not None:
+        assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
+        a.nk_dev = nk_dev.data_ptr()
+    if Nq == 1 and q_win is None and Nk >= 768:  # decode: split-K scratch
+        ws = torch.empty((B * H * 16 * (max(D, 128) + 130),), device=q.device, dtype=torch.float32)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     L.check(L.lib().vg_attention(C.byref(a), _stream()), "vg_attention")
     return out
 
@@ -296,3 +303,14 @@ def argmax(x: torch.Tensor) -> torch.Tensor:
     out = torch.empty((x.shape[0],), device=x.device, dtype=torch.int64)
     L.check(L.lib().vg_argmax(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), _ptr(out), x.shape[0], x.shape[1], _stream()), "vg_argmax")
     return out
+
+
+def row_scatter(src: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, col0: int, cols: int) -> None:
+    """cache[pos_dev[0], col0:col0+cols] = src[0, col0:col0+cols] (bf16), position read on the device."""
+    _require_cuda(src, cache, pos_dev)
+    assert src.dtype == cache.dtype == torch.bfloat16 and pos_dev.dtype == torch.int32 and cache.stride(1) == 1
+    L.check(L.lib().vg_row_scatter(_ptr(src), _ptr(cache), C.c_longlong(cache.stride(0)), _ptr(pos_dev), col0, cols, _stream()), "vg_row_scatter")
+
+
+def launch_count_add(n: int) -> None:
+    L.lib().vg_launch_count_add(int(n))

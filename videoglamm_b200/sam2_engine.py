@@ -16,6 +16,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from .graphs import GraphedStage
 from .config import Sam2Config
 
 NO_OBJ_SCORE = -1024.0
@@ -42,6 +43,7 @@ class Sam2Engine:
         if self.dev.type != "cuda":
             raise RuntimeError("Sam2Engine needs a CUDA device (there is no CPU path)")
         self.frames_per_encode = 8
+        self.g_video = GraphedStage("sam2_video")
         self._sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
         self._pack()
         del self._sd
@@ -415,6 +417,16 @@ class Sam2Engine:
     # ------------------------------------------------------------------------------------------------ video session
     @torch.no_grad()
     def run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False, collect: dict | None = None):
+        """Graph-captured entry: the whole session's launch sequence is a function of (T, n_obj, video size) only. Returns a list of
+        per-frame [n_obj, H, W] tensors (views of graph-owned memory, valid until the next call with the same shapes)."""
+        if collect is not None:
+            return self._run_video(images, text_embeds, video_hw, binary, collect)
+        key = (tuple(images.shape), tuple(text_embeds.shape), tuple(video_hw), binary, images.dtype)
+        out = self.g_video(key, lambda images, text_embeds: torch.stack(self._run_video(images, text_embeds, video_hw, binary, None)),
+                           images=images, text_embeds=text_embeds.to(F32))
+        return list(out.unbind(0))
+
+    def _run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False, collect: dict | None = None):
         """The VideoGLaMM video-branch session (VideoGLaMM.py:846-875 -> sam2_video_predictor.py init_state_from_tensor :109-180,
         add_new_text :416-495 on frame 0 per object, propagate_in_video :745-827 incl. preflight :675-729).
         images [T,3,S,S] fp32 cuda; text_embeds [n_obj,1,C]. Returns per frame [n_obj,H,W]: fp32 logits (binary=False) or uint8 (x>0)."""
