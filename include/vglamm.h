@@ -91,8 +91,9 @@ typedef struct VgAttention {
   int causal, window;
   int q_win, q_gridw, q_nwx, q_nwy;
   int k_win, k_gridw, k_nwx, k_nwy;
-  void* workspace; long long workspace_bytes;   /* optional fp32 scratch: enables split-K for single-query (decode) attention;
-                                                   B*H*16*(max(D,128)+2)*4 bytes always suffices */
+  void* workspace; long long workspace_bytes;   /* optional fp32 scratch enabling split-K over keys: single-query (decode) attention needs
+                                                   B*H*16*(max(D,128)+2)*4 bytes; non-causal attention with < 148 query tiles (SAM2 memory
+                                                   attention) uses up to 8*B*H*Nq*(Dpad+2)*4 bytes */
   const int* nk_dev;                            /* optional (Nq == 1 only): the number of keys is read from this DEVICE int at run time
                                                    (Nk is then only an upper bound) so a captured decode step can be replayed */
 } VgAttention;

@@ -92,7 +92,8 @@ def sdpa_ref(q, k, v, scale, causal=False, window=0):
 @pytest.mark.parametrize("B,H,Nq,Nk,D,causal,window", [
     (2, 4, 64, 64, 64, False, 0), (1, 16, 577, 577, 64, False, 0), (1, 16, 1025, 1025, 88, False, 0), (1, 8, 300, 300, 72, False, 0),
     (1, 32, 333, 333, 96, True, 0), (1, 4, 1, 500, 96, True, 0), (1, 4, 700, 700, 96, True, 128), (2, 1, 256, 1100, 256, False, 0),
-    (3, 8, 9, 4096, 16, False, 0), (3, 8, 4096, 9, 16, False, 0), (2, 8, 9, 9, 32, False, 0), (1, 2, 130, 70, 128, False, 0)])
+    (3, 8, 9, 4096, 16, False, 0), (3, 8, 4096, 9, 16, False, 0), (2, 8, 9, 9, 32, False, 0), (1, 2, 130, 70, 128, False, 0),
+    (1, 1, 4096, 8300, 256, False, 0), (2, 2, 300, 5000, 64, False, 0), (1, 1, 70, 2049, 96, False, 0)])  # last three: split-K over keys
 def test_attention(B, H, Nq, Nk, D, causal, window):
     q = torch.randn(B, Nq, H, D, device=DEV).bfloat16()
     k = torch.randn(B, Nk, H, D, device=DEV).bfloat16()

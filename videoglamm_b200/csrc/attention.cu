@@ -43,12 +43,19 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
   __nv_bfloat16* sV = sK + 2 * BN * LD;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q0 = blockIdx.x * BM, h = blockIdx.y, b = blockIdx.z;
+  const int q_tiles = (p.Nq + BM - 1) / BM;
+  const int split = blockIdx.x / q_tiles;  // split-K over keys (nsplit > 1 only for non-causal, low-CTA-count problems)
+  const int q0 = (blockIdx.x - split * q_tiles) * BM, h = blockIdx.y, b = blockIdx.z;
   const int off = p.Nk - p.Nq;  // causal alignment: query i may see keys j <= i + off
   int k_end = p.Nk;
   if (p.causal) k_end = min(p.Nk, q0 + BM + off);
   int k_begin = 0;
   if (p.window > 0) k_begin = max(0, (q0 + off - p.window) / BN * BN);
+  if (p.nsplit > 1) {
+    const int per = ((p.Nk + p.nsplit - 1) / p.nsplit + BN - 1) / BN * BN;
+    k_begin = split * per;
+    k_end = min(p.Nk, k_begin + per);
+  }
   const int ntiles = (k_end - k_begin + BN - 1) / BN;
 
   const bool lin_q = p.q_win == 0, lin_k = p.k_win == 0;
@@ -121,18 +128,26 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
     const int kbase = k_begin + it * BN;
     const int qrow0 = q0 + warp * 16 + g;
     float mx[2] = {-INFINITY, -INFINITY};
+    // interior tiles (all 64 keys valid for all 64 rows) skip the mask arithmetic; block-uniform condition
+    const bool need_mask = (kbase + BN > p.Nk) || (p.causal && (kbase + BN - 1 > q0 + off)) || (p.window > 0 && (kbase < q0 + BM - 1 + off - p.window));
+    if (need_mask) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = kbase + nt * 8 + 2 * t4 + (e & 1);
+          const int row = qrow0 + (e >> 1) * 8;
+          bool ok = col < p.Nk;
+          if (p.causal) ok = ok && (col <= row + off);
+          if (p.window > 0) ok = ok && (col >= row + off - p.window);
+          s[nt][e] = ok ? s[nt][e] : -INFINITY;
+        }
+      }
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = kbase + nt * 8 + 2 * t4 + (e & 1);
-        const int row = qrow0 + (e >> 1) * 8;
-        bool ok = col < p.Nk;
-        if (p.causal) ok = ok && (col <= row + off);
-        if (p.window > 0) ok = ok && (col >= row + off - p.window);
-        s[nt][e] = ok ? s[nt][e] : -INFINITY;
-        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
-      }
+      for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
     }
     float alpha[2], msc[2];
 #pragma unroll
@@ -183,6 +198,24 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
   for (int r = 0; r < 2; ++r) {
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
     l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+  }
+  if (p.nsplit > 1) {  // un-normalised partial rows: [split][b][h][row][DP + 2] = {m, l, o[DP]}
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = q0 + warp * 16 + g + r * 8;
+      if (row >= p.Nq) continue;
+      float* wp = p.ws + ((((static_cast<long long>(split) * p.B + b) * p.H + h) * p.Nq) + row) * (DP + 2);
+      if (t4 == 0) {
+        wp[0] = m_run[r] * p.scale;  // scaled logit units
+        wp[1] = l_run[r];
+      }
+#pragma unroll
+      for (int nt = 0; nt < DP / 8; ++nt) {
+        wp[2 + nt * 8 + 2 * t4] = o_acc[nt][2 * r];
+        wp[2 + nt * 8 + 2 * t4 + 1] = o_acc[nt][2 * r + 1];
+      }
+    }
+    return;
   }
   __nv_bfloat16* ob = p.o + (lin_q ? b * p.o_bs : 0) + h * p.o_hs;
 #pragma unroll
@@ -322,19 +355,64 @@ __global__ void attn_decode_merge_kernel(const AttnParams p) {
   }
 }
 
+// one warp per (b, h, row): combine nsplit partials
 template <int DP>
-static int launch_attn(const AttnParams& p, cudaStream_t s) {
+__global__ void flash_attn_merge_kernel(const AttnParams p) {
+  const long long gw = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
+  if (gw >= rows) return;
+  const int row = static_cast<int>(gw % p.Nq);
+  const int h = static_cast<int>((gw / p.Nq) % p.H);
+  const int b = static_cast<int>(gw / (static_cast<long long>(p.Nq) * p.H));
+  float m_all = -INFINITY;
+  for (int s = 0; s < p.nsplit; ++s) m_all = fmaxf(m_all, p.ws[(static_cast<long long>(s) * rows + gw) * (DP + 2)]);
+  float l_all = 0.f, wgt[16];
+  for (int s = 0; s < p.nsplit; ++s) {
+    const float* wp = p.ws + (static_cast<long long>(s) * rows + gw) * (DP + 2);
+    wgt[s] = (wp[0] == -INFINITY) ? 0.f : __expf(wp[0] - m_all);
+    l_all += wp[1] * wgt[s];
+  }
+  const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+  __nv_bfloat16* orow = p.o + b * p.o_bs + h * p.o_hs + static_cast<long long>(row) * p.o_rs;
+  for (int d = lane; d < p.D; d += 32) {
+    float acc = 0.f;
+    for (int s = 0; s < p.nsplit; ++s) acc += p.ws[(static_cast<long long>(s) * rows + gw) * (DP + 2) + 2 + d] * wgt[s];
+    orow[d] = __float2bfloat16(acc * inv);
+  }
+}
+
+template <int DP>
+static int launch_attn(AttnParams p, cudaStream_t s, void* workspace, long long workspace_bytes) {
   constexpr int LD = DP + 8;
   constexpr int smem = (64 * LD + 4 * 64 * LD) * 2;
+  const int q_tiles = (p.Nq + 63) / 64;
+  const long long ctas = static_cast<long long>(q_tiles) * p.H * p.B;
+  p.nsplit = 1;
+  if (workspace != nullptr && !p.causal && p.window == 0 && p.q_win == 0 && p.k_win == 0 && ctas < 148 && p.Nk >= 2048) {
+    int ns = static_cast<int>((2 * 148 + ctas - 1) / ctas);
+    if (ns > 8) ns = 8;
+    if (ns > p.Nk / 1024) ns = p.Nk / 1024;
+    const long long need = static_cast<long long>(ns) * p.B * p.H * p.Nq * (DP + 2) * 4;
+    if (ns > 1 && need <= workspace_bytes) {
+      p.nsplit = ns;
+      p.ws = static_cast<float*>(workspace);
+    }
+  }
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(flash_attn_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(VG_ECUDA, "attention smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((p.Nq + 63) / 64, p.H, p.B);
+  dim3 grid(q_tiles * p.nsplit, p.H, p.B);
   flash_attn_kernel<DP><<<grid, 128, smem, s>>>(p);
   count_launch();
+  if (p.nsplit > 1) {
+    const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
+    flash_attn_merge_kernel<DP><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+    count_launch();
+  }
   return check_launch("flash_attn_kernel");
 }
 
@@ -391,11 +469,11 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
     }
     return check_launch("attn_decode_kernel");
   }
-  if (a->D <= 32) return launch_attn<32>(p, s);
-  if (a->D <= 64) return launch_attn<64>(p, s);
-  if (a->D <= 80) return launch_attn<80>(p, s);
-  if (a->D <= 96) return launch_attn<96>(p, s);
-  if (a->D <= 128) return launch_attn<128>(p, s);
-  if (a->D <= 256) return launch_attn<256>(p, s);
+  if (a->D <= 32) return launch_attn<32>(p, s, a->workspace, a->workspace_bytes);
+  if (a->D <= 64) return launch_attn<64>(p, s, a->workspace, a->workspace_bytes);
+  if (a->D <= 80) return launch_attn<80>(p, s, a->workspace, a->workspace_bytes);
+  if (a->D <= 96) return launch_attn<96>(p, s, a->workspace, a->workspace_bytes);
+  if (a->D <= 128) return launch_attn<128>(p, s, a->workspace, a->workspace_bytes);
+  if (a->D <= 256) return launch_attn<256>(p, s, a->workspace, a->workspace_bytes);
   return set_error(VG_ENOSUP, "vg_attention: head dim %d > 256", a->D);
 }

@@ -221,6 +221,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
+        // L2 prefetch of this thread's residual line for the NEXT chunk (the residual add is latency-bound, see profiles/)
+        if (p.resid != nullptr && row_ok && c + 2 < BN / 32) {
+          const int ncol = (p.glu ? (col0 + 64) >> 1 : col0 + 64);
+          if (ncol < n_out) {
+            const char* np = reinterpret_cast<const char*>(p.resid) +
+                             ((b * p.strideR + static_cast<long long>(row) * p.ldr + ncol) << (p.resid_f32 ? 2 : 1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+          }
+        }
         uint32_t raw[32];
         tmem_ld32(taddr + c * 32, raw);
         tmem_ld_wait();

@@ -286,6 +286,50 @@ __global__ void conv3x3s2_ln_gelu_kernel(const void* x, int xdt, const float* wt
   }
 }
 
+// small-channel variant: one THREAD per output pixel, all COUT channels + LayerNorm + GELU in registers (the warp-per-pixel kernel
+// leaves 28 of 32 lanes idle when cout = 4)
+template <int CIN, int COUT>
+__global__ void conv3x3s2_ln_gelu_small_kernel(const void* x, int xdt, const float* __restrict__ wt, const float* __restrict__ bias,
+                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, void* y, int ydt, int n,
+                                               int h, int w) {
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int oh = h / 2, ow = w / 2;
+  if (pix >= static_cast<long long>(n) * oh * ow) return;
+  const int ox = static_cast<int>(pix % ow);
+  const int oy = static_cast<int>((pix / ow) % oh);
+  const int img = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
+  float acc[COUT];
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) acc[co] = bias[co];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = 2 * ox - 1 + kx;
+      if (ix < 0 || ix >= w) continue;
+      const long long xb = ((static_cast<long long>(img) * h + iy) * w + ix) * CIN;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float xv = ld(x, xdt, xb + ci);
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) acc[co] = fmaf(xv, wt[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[co]);
+      }
+    }
+  }
+  float mean = 0.f;
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) mean += acc[co];
+  mean /= COUT;
+  float var = 0.f;
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) var += (acc[co] - mean) * (acc[co] - mean);
+  const float rstd = rsqrtf(var / COUT + eps);
+#pragma unroll
+  for (int co = 0; co < COUT; ++co) st(y, ydt, pix * COUT + co, gelu_erf((acc[co] - mean) * rstd * ln_w[co] + ln_b[co]));
+}
+
 __global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n) * oh * ow) return;
@@ -480,6 +524,16 @@ extern "C" int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, 
                                     float eps, void* y, int y_dtype, int n, int h, int wd, int cin, int cout, void* stream) {
   if (!x || !w || !bias || !ln_w || !ln_b || !y || cout > 256 || (h & 1) || (wd & 1)) return set_error(VG_EINVAL, "vg_conv3x3s2_ln_gelu: bad argument");
   const long long pix = static_cast<long long>(n) * (h / 2) * (wd / 2);
+  if (cin == 1 && cout == 4) {
+    conv3x3s2_ln_gelu_small_kernel<1, 4><<<blocks_for(pix, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
+    count_launch();
+    return check_launch("conv3x3s2_ln_gelu_small_kernel");
+  }
+  if (cin == 4 && cout == 16) {
+    conv3x3s2_ln_gelu_small_kernel<4, 16><<<blocks_for(pix, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
+    count_launch();
+    return check_launch("conv3x3s2_ln_gelu_small_kernel");
+  }
   conv3x3s2_ln_gelu_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin, cout);
   count_launch();
   return check_launch("conv3x3s2_ln_gelu_kernel");

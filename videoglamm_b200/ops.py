@@ -148,6 +148,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     if nk_dev is not None:
         assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
         a.nk_dev = nk_dev.data_ptr()
+    if q_win is None and not causal and Nq > 1 and Nk >= 2048 and B * H * ((Nq + 63) // 64) < 148:
+        # few query tiles, many keys (SAM2 memory attention): split-K scratch for up to 8 partials
+        dp = 32 if D <= 32 else 64 if D <= 64 else 80 if D <= 80 else 96 if D <= 96 else 128 if D <= 128 else 256
+        ws = torch.empty((8 * B * H * Nq * (dp + 2),), device=q.device, dtype=torch.float32)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if Nq == 1 and q_win is None and Nk >= 768:  # decode: split-K scratch
         ws = torch.empty((B * H * 16 * (max(D, 128) + 130),), device=q.device, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
