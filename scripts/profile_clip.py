@@ -17,7 +17,33 @@ def step():
 n_warm = int(os.environ.get("WARM", 2))
 for _ in range(n_warm): step()
 torch.cuda.synchronize()
-if os.environ.get("E2E_STAGES"):
+if os.environ.get("SAM_STAGES"):
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    sam = model.sam
+    emb = torch.randn(1, 1, 256, device="cuda")
+    T = 8
+    tm = {}
+    def timeit(name, fn):
+        a, b = ev(), ev(); a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+        tm[name] = tm.get(name, 0.0) + a.elapsed_time(b); return r
+    for rep in range(2):
+        tm.clear()
+        fb = timeit("hiera+fpn x8", lambda: sam.forward_image(inp[2].float()))
+        feats = [{k: v.view(8, -1, v.shape[-1])[i] for k, v in fb.items()} for i in range(8)]
+        f0 = feats[0]
+        pix0 = ops.add(f0["top"], sam.no_mem_embed)
+        r0 = timeit("sam_heads(frame0)", lambda: sam.forward_sam_heads(pix0, f0["s0"], f0["s1"], emb, 1))
+        from videoglamm_b200.sam2_engine import FrameMem
+        cond = {0: FrameMem(r0["low_res_masks"], r0["obj_ptr"], timeit("encode_memory", lambda: sam.encode_memory(f0["top"], r0["low_res_masks"], True)))}
+        non = {}
+        for t in range(1, T):
+            f = feats[t]
+            memory, mem_pos, n_ptr = sam._memory_bank(t, cond, non, T, 1)
+            pix = timeit("memory_attention", lambda: sam.memory_attention(f["top"], 1, memory, mem_pos, n_ptr))
+            r = timeit("sam_heads", lambda: sam.forward_sam_heads(pix, f["s0"], f["s1"], None, 1))
+            non[t] = FrameMem(r["low_res_masks"], r["obj_ptr"], timeit("encode_memory", lambda: sam.encode_memory(f["top"], r["low_res_masks"], False)))
+    print({k: round(v, 2) for k, v in tm.items()})
+elif os.environ.get("E2E_STAGES"):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     for rep in range(2):
         e = [ev() for _ in range(3)]

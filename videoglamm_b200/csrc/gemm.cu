@@ -24,7 +24,9 @@ struct GemmCfg {
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 128/256/512 are powers of two
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 8 * 4096;             // per epilogue warp: one 32-row TMA-store box (<= 128 B per row)
+  static constexpr int VEC_BYTES = 2 /*acc stages*/ * BN * 4;  // bias of the tile being drained
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256 /*barriers*/;  // base is 1024-aligned (checked)
 };
 
 struct GemmParams {
@@ -42,6 +44,8 @@ struct GemmParams {
   int resid_f32;
   float alpha;
   int b_shared;  // B (weights) shared by every batch entry
+  int use_tma_store;  // C leaves through per-warp smem boxes + bulk tensor stores
+  int tma_reduce;     // residual aliases C: TMA reduce-add instead of load + add + store
 };
 
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 resolution of the GELU output): ~15 instructions, branch-free,
@@ -98,13 +102,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    const GemmParams p) {
   using Cfg = GemmCfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023) != 0) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base
   uint8_t* sA = smem;
   uint8_t* sB = smem + Cfg::STAGES * Cfg::A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  float* s_vec = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);  // [acc][BN] bias
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::VEC_BYTES);
   uint64_t* empty_bar = full_bar + Cfg::STAGES;
   uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -116,6 +123,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.use_tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) {
@@ -141,6 +149,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
   const int total_tiles = tiles_per_batch * p.batch;
 
+  // Register rebalancing (the three control warps + spare form warpgroup 0 and need few registers; the two epilogue warpgroups hold a
+  // 32-column accumulator chunk plus a prefetched residual chunk): 128*56 + 256*224 = 64512 <= 65536.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
@@ -198,38 +210,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------ epilogue: TMEM -> regs -> global (8 warps: lane quadrant x column half)
-    const int ew = warp & 3;          // TMEM lane quadrant this warp may access (warp id % 4)
-    const int half = (warp - 4) >> 2;  // which interleaved set of 32-column chunks
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ------------------------------------------------ epilogue: TMEM -> regs -> (smem -> TMA store | global) ; 8 warps
+    // Each warp owns a TMEM lane quadrant (warp % 4) and every other 32-column chunk. Results leave through a per-warp swizzled
+    // shared-memory box and ONE bulk tensor store (or reduce-add, when the residual aliases the output) issued by lane 0:
+    // thread-per-row st.global touched 32 lines per instruction and capped the epilogue at ~18 GB/s per SM (profiles/r01_gemm_epilogue.md).
+    const int ew = warp & 3;
+    const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out = p.glu ? p.N / 2 : p.N;
     const bool unit_alpha = p.alpha == 1.0f;
+    uint8_t* stg = staging + (warp - 4) * 4096;
+    const int esz = p.out_f32 ? 4 : 2;
+    const int nvals_c = p.glu ? 16 : 32;
+    const int row_bytes = nvals_c * esz;                         // 128 / 64 / 32: equals the TMA swizzle span
+    const int sw_mask = (row_bytes >> 4) - 1;
+    const int sw = (lane >> (row_bytes == 128 ? 0 : (row_bytes == 64 ? 1 : 2))) & sw_mask;  // XOR applied to the 16-byte chunk index
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
       const int n_blk = r / p.tiles_m;
       const int m_blk = r - n_blk * p.tiles_m;
+      // stage the tile's bias in shared memory BEFORE waiting for the accumulator (latency overlaps the MMA main loop)
+      float* s_bias = s_vec + acc * BN;
+      if (p.bias != nullptr) {
+        const int et = threadIdx.x - 128;
+        for (int j = et; j < BN; j += 256) {
+          const int col = n_blk * BN + j;
+          s_bias[j] = col < p.N ? __ldg(p.bias + b * p.strideBias + col) : 0.f;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int row = m_blk * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
-      const float* bias = p.bias ? p.bias + b * p.strideBias : nullptr;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
-        // L2 prefetch of this thread's residual line for the NEXT chunk (the residual add is latency-bound, see profiles/)
-        if (p.resid != nullptr && row_ok && c + 2 < BN / 32) {
-          const int ncol = (p.glu ? (col0 + 64) >> 1 : col0 + 64);
-          if (ncol < n_out) {
-            const char* np = reinterpret_cast<const char*>(p.resid) +
-                             ((b * p.strideR + static_cast<long long>(row) * p.ldr + ncol) << (p.resid_f32 ? 2 : 1));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
-          }
-        }
         uint32_t raw[32];
         tmem_ld32(taddr + c * 32, raw);
         tmem_ld_wait();
@@ -240,19 +263,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= p.alpha;
         }
-        const bool full = col0 + 32 <= p.N;  // warp-uniform
-        if (bias != nullptr) {
-          if (full && ((reinterpret_cast<uintptr_t>(bias + col0) & 15) == 0)) {
-            const float4* bp = reinterpret_cast<const float4*>(bias + col0);
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + c * 32);  // broadcast shared loads
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(bp + j);
-              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(bias + col0 + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = bp[j];
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
           }
         }
         int ocol0, nvals;
@@ -268,83 +284,88 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           nvals = 32;
         }
         const int nvalid = min(nvals, n_out - ocol0);
-        const bool vec = nvalid == nvals;  // warp-uniform: whole chunk inside the matrix
         if (p.col_scale != nullptr) {
-          if (vec && ((reinterpret_cast<uintptr_t>(p.col_scale + ocol0) & 15) == 0)) {
-            const float4* sp = reinterpret_cast<const float4*>(p.col_scale + ocol0);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (4 * j < nvals) {
-                const float4 ss = __ldg(sp + j);
-                v[4 * j] *= ss.x; v[4 * j + 1] *= ss.y; v[4 * j + 2] *= ss.z; v[4 * j + 3] *= ss.w;
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] *= __ldg(p.col_scale + ocol0 + j);
+        }
+        // residual that does NOT alias the output: thread-per-row loads (rare; aliasing residuals use the TMA reduce-add below)
+        if (p.resid != nullptr && !p.tma_reduce && row_ok) {
+          const long long roff = b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+          if (p.resid_f32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + roff;
+            if (nvalid == nvals && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (4 * j < nvals) {
+                  const float4 q = *reinterpret_cast<const float4*>(rp + 4 * j);
+                  v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+                }
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nvalid) v[j] += rp[j];
             }
           } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + roff;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nvalid) v[j] *= __ldg(p.col_scale + ocol0 + j);
+              if (j < nvalid) v[j] += __bfloat162float(rp[j]);
           }
         }
-        if (row_ok) {
-          if (p.resid != nullptr) {
-            if (p.resid_f32) {
-              const float* rp = reinterpret_cast<const float*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
-              if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+        if (p.use_tma_store) {
+          // the previous bulk store of this warp must have finished READING the staging box before it is overwritten
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          uint8_t* srow = stg + lane * row_bytes;
+          if (p.out_f32) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  if (4 * j < nvals) {
-                    const float4 rr = *reinterpret_cast<const float4*>(rp + 4 * j);
-                    v[4 * j] += rr.x; v[4 * j + 1] += rr.y; v[4 * j + 2] += rr.z; v[4 * j + 3] += rr.w;
-                  }
-                }
-              } else {
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < nvals) *reinterpret_cast<float4*>(srow + ((j ^ sw) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) v[j] += rp[j];
-              }
+            for (int j = 0; j < 4; ++j)
+              if (8 * j < nvals)
+                *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                                             pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            const int r0 = m_blk * BLOCK_M + ew * 32;
+            if (p.tma_reduce) {
+              asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(smem_u32(stg)), "r"(ocol0), "r"(r0), "r"(b)
+                           : "memory");
             } else {
-              const __nv_bfloat16* rp =
-                  reinterpret_cast<const __nv_bfloat16*>(p.resid) + b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
-              if (vec && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  if (8 * j < nvals) {
-                    const uint4 rr = *reinterpret_cast<const uint4*>(rp + 8 * j);
-                    v[8 * j] += bf16_lo(rr.x); v[8 * j + 1] += bf16_hi(rr.x); v[8 * j + 2] += bf16_lo(rr.y); v[8 * j + 3] += bf16_hi(rr.y);
-                    v[8 * j + 4] += bf16_lo(rr.z); v[8 * j + 5] += bf16_hi(rr.z); v[8 * j + 6] += bf16_lo(rr.w); v[8 * j + 7] += bf16_hi(rr.w);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (j < nvalid) v[j] += __bfloat162float(rp[j]);
-              }
+              asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tmC)),
+                           "r"(smem_u32(stg)), "r"(ocol0), "r"(r0), "r"(b)
+                           : "memory");
             }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (row_ok) {
+          // fallback (unaligned C / ldc): thread-per-row scalar stores, aliasing residual added here
+          const long long coff = b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
+          if (p.resid != nullptr && p.tma_reduce) {
+            const long long roff = b * p.strideR + static_cast<long long>(row) * p.ldr + ocol0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid)
+                v[j] += p.resid_f32 ? reinterpret_cast<const float*>(p.resid)[roff + j] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.resid)[roff + j]);
           }
           if (p.out_f32) {
-            float* cp = reinterpret_cast<float*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
-            if (vec && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            float* cp = reinterpret_cast<float*>(p.C) + coff;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (j < nvals) *reinterpret_cast<float4*>(cp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) cp[j] = v[j];
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) cp[j] = v[j];
           } else {
-            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + b * p.strideC + static_cast<long long>(row) * p.ldc + ocol0;
-            if (vec && (reinterpret_cast<uintptr_t>(cp) & 15) == 0) {
+            __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + coff;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                if (j < nvals)
-                  *reinterpret_cast<uint4*>(cp + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                                 pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < nvalid) cp[j] = __float2bfloat16(v[j]);
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < nvalid) cp[j] = __float2bfloat16(v[j]);
           }
         }
       }
@@ -355,6 +376,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_phase ^= 1;
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all bulk stores of this warp complete before exit
   }
 
   tc_fence_before();
@@ -558,9 +580,10 @@ struct MapKey {
   const void* ptr;
   long long ld, stride;
   int rows, cols, batch, box_rows;
+  int kind = 0;  // 0: bf16 operand (box 64 x box_rows, SWIZZLE_128B); else (elem_bytes << 8 | box_cols) for output boxes
   bool operator==(const MapKey& o) const {
     return ptr == o.ptr && ld == o.ld && stride == o.stride && rows == o.rows && cols == o.cols && batch == o.batch &&
-           box_rows == o.box_rows;
+           box_rows == o.box_rows && kind == o.kind;
   }
 };
 struct MapKeyHash {
@@ -573,15 +596,50 @@ struct MapKeyHash {
     mix(static_cast<size_t>(k.cols));
     mix(static_cast<size_t>(k.batch));
     mix(static_cast<size_t>(k.box_rows));
+    mix(static_cast<size_t>(k.kind));
     return h;
   }
 };
 
 // bf16 [batch][rows][ld] (cols valid per row) -> 3D tiled map with box {64, box_rows, 1}, 128B swizzle, zero OOB fill.
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// Output map: [batch][rows][ld] of `esz`-byte elements, box {box_cols, 32, 1}; the shared-memory side is swizzled with a span equal to
+// the box row (128/64/32 bytes) so that thread-per-row 16-byte writes into the box are bank-conflict-free.
+static int make_out_map(CUtensorMap* out, const void* ptr, int rows, int cols, int batch, long long ld, long long stride, int esz, int box_cols) {
+  MapKey key{ptr, ld, stride, rows, cols, batch, 32, (esz << 8) | box_cols};
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) {
+      *out = it->second;
+      return VG_OK;
+    }
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(batch)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld) * esz, static_cast<cuuint64_t>(batch > 1 ? stride : static_cast<long long>(rows) * ld) * esz};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  const int row_bytes = box_cols * esz;
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = enc(out, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled (output) failed (%d): rows=%d cols=%d ld=%lld", (int)r, rows, cols, ld);
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    if (g_map_cache.size() > 65536) g_map_cache.clear();
+    g_map_cache.emplace(key, *out);
+  }
+  return VG_OK;
+}
+
 static int make_map(CUtensorMap* out, const void* ptr, int rows, int cols, int batch, long long ld, long long stride, int box_rows) {
-  static std::mutex mu;
-  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
-  MapKey key{ptr, ld, stride, rows, cols, batch, box_rows};
+  std::mutex& mu = g_map_mu;
+  auto& cache = g_map_cache;
+  MapKey key{ptr, ld, stride, rows, cols, batch, box_rows, 0};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -637,6 +695,8 @@ static GemmParams to_params(const VgGemm* g) {
   p.resid = g->resid; p.ldr = g->ldr; p.strideR = g->strideR; p.resid_f32 = g->resid_dtype == VG_F32;
   p.alpha = g->alpha;
   p.b_shared = (g->batch > 1 && g->strideB == 0) ? 1 : 0;
+  p.use_tma_store = 0;
+  p.tma_reduce = 0;
   return p;
 }
 
@@ -657,9 +717,22 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   GemmParams p = to_params(g);
   p.tiles_m = (g->M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (g->N + BN - 1) / BN;
+  // Output path: bulk tensor stores need a 16-byte aligned base and 16-byte multiple strides. A residual that aliases the output
+  // (the in-place residual-stream update every transformer block does) becomes a TMA reduce-add; any other residual is added in registers.
+  const int esz = g->out_dtype == VG_F32 ? 4 : 2;
+  const int n_out = g->glu ? g->N / 2 : g->N;
+  const bool aliased = g->resid != nullptr && g->resid == g->C && g->ldr == g->ldc && (g->batch == 1 || g->strideR == g->strideC) &&
+                       g->resid_dtype == g->out_dtype;
+  p.tma_reduce = aliased ? 1 : 0;
+  p.use_tma_store = ((reinterpret_cast<uintptr_t>(g->C) & 15) == 0) && ((g->ldc * esz) % 16 == 0) && (g->batch == 1 || (g->strideC * esz) % 16 == 0);
+  CUtensorMap tmC = tmA;  // placeholder when the fallback path is taken
+  if (p.use_tma_store) {
+    rc = make_out_map(&tmC, g->C, g->M, n_out, g->batch, g->ldc, g->strideC, esz, g->glu ? 16 : 32);
+    if (rc) return rc;
+  }
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * g->batch;
   const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tcgen05_kernel");
 }

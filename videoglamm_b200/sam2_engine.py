@@ -207,7 +207,7 @@ class Sam2Engine:
         else:
             o = ops.attention(q.unflatten(0, (n, Hq * Wq)), k.unflatten(0, (n, H * W)), v.unflatten(0, (n, H * W)), scale=hd ** -0.5)
         o = o.reshape(n * Hq * Wq, dim_out)
-        x = ops.gemm(o, blk["proj"].w, bias=blk["proj"].b, resid=sc, out_dtype=F32)
+        x = ops.gemm(o, blk["proj"].w, bias=blk["proj"].b, resid=sc, out=sc)  # in place: aliasing residual -> TMA reduce-add epilogue
         xn = ops.norm(x, *blk["n2"], eps=1e-6)
         h = ops.gemm(xn, blk["fc1"].w, bias=blk["fc1"].b, act="gelu")
         x = ops.gemm(h, blk["fc2"].w, bias=blk["fc2"].b, resid=x, out=x)
@@ -249,7 +249,7 @@ class Sam2Engine:
         v = ops.gemm(v_in, w["v"].w, bias=w["v"].b)
         d = q.shape[1] // H
         o = ops.attention(q.view(B, Nq, H, d), k.view(B, Nk, H, d), v.view(B, Nk, H, d), scale=d ** -0.5)
-        return ops.gemm(o.view(B * Nq, H * d), w["out"].w, bias=w["out"].b, resid=resid, out_dtype=F32)
+        return ops.gemm(o.view(B * Nq, H * d), w["out"].w, bias=w["out"].b, resid=resid, out=resid, out_dtype=F32)  # in place when residual
 
     def _mlp3(self, layers, x_bf, final_act=None):
         h = ops.gemm(x_bf, layers[0].w, bias=layers[0].b, act="relu")
@@ -281,7 +281,7 @@ class Sam2Engine:
             v_k = ops.cast(keys, BF)
             queries = ops.norm(self._attn(L["t2i"], q, k_pe, v_k, B, Nt, HW, resid=queries), *L["n2"], eps=1e-5, out_dtype=F32)
             h = ops.gemm(ops.cast(queries, BF), L["fc1"].w, bias=L["fc1"].b, act="relu")
-            queries = ops.norm(ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=queries, out_dtype=F32), *L["n3"], eps=1e-5, out_dtype=F32)
+            queries = ops.norm(ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=queries, out=queries), *L["n3"], eps=1e-5, out_dtype=F32)
             q = ops.add(queries, tokens, out_dtype=BF)
             keys = ops.norm(self._attn(L["i2t"], k_pe, q, ops.cast(queries, BF), B, HW, Nt, resid=keys), *L["n4"], eps=1e-5, out_dtype=F32)
         q = ops.add(queries, tokens, out_dtype=BF)
