@@ -1,0 +1,36 @@
+"""The two-stream clip pipeline returns exactly what clip-by-clip `inference` returns."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pipeline_matches_sequential_inference():
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    from videoglamm_b200.pipeline import ClipPipeline
+    seg = 300
+    ocfg, scfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=seg), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=seg), Sam2Config(**O.TINY))
+    clips = []
+    for i in range(5):
+        g = torch.Generator().manual_seed(100 + i)
+        T = 4
+        clips.append(dict(images=torch.randn(T, 3, 56, 56, generator=g), context_images=torch.randn(T, 3, 56, 56, generator=g),
+                          images_for_sam=torch.randn(3, 3, 256, 256, generator=g),
+                          input_ids=torch.cat([torch.randint(3, 290, (5,), generator=g), torch.full((T,), -200), torch.randint(3, 290, (7,), generator=g)])[None],
+                          original_size=(48, 64)))
+    forced = {1: seg, 3: seg}
+    seq = [model.inference([c["images"]], [c["context_images"]], [c["images_for_sam"]], c["input_ids"].cuda(), None, [c["original_size"]],
+                           max_new_tokens=5, use_sam2_video_branch=True, forced_tokens=forced) for c in clips]
+    seq = [(ids.cpu().clone(), {t: {o: m.copy() for o, m in fr.items()} for t, fr in segs[0].items()}) for ids, segs in seq]
+    out = ClipPipeline(model).run(clips, 5, forced_tokens=forced)
+    for (ids_a, seg_a), (ids_b, seg_b) in zip(seq, out):
+        assert torch.equal(ids_a, ids_b.cpu())
+        assert sorted(seg_a) == sorted(seg_b)
+        for t in seg_a:
+            for o in seg_a[t]:
+                assert np.array_equal(seg_a[t][o], seg_b[t][o])

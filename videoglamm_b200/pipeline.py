@@ -1,0 +1,82 @@
+"""Two-stage software pipeline over independent clips for throughput serving: the LMM stage (towers, prefill, latency-bound decode) of clip
+i+1 runs on one CUDA stream while the SAM2 stage (tensor-bound Hiera / memory attention) of clip i runs on another. Each stage has its own
+host thread (the decode loop syncs with the host once per token) and its own CUDA-graph pools. Results are identical to
+`VideoGLaMMForCausalLM.inference` called clip by clip — only the interleaving on the device differs."""
+from __future__ import annotations
+
+import queue
+import threading
+
+import numpy as np
+import torch
+
+
+class ClipPipeline:
+    def __init__(self, model, depth: int = 2):
+        self.model = model
+        self.depth = depth
+        self.s_lmm = torch.cuda.Stream(device=model.device)
+        self.s_sam = torch.cuda.Stream(device=model.device)
+
+    @torch.no_grad()
+    def run(self, clips: list[dict], max_new_tokens: int, forced_tokens: dict | None = None) -> list[tuple]:
+        """clips: [{"images", "context_images", "images_for_sam", "input_ids", "original_size"}] (host or device tensors).
+        Returns [(output_ids, segments)] in order; segments as in `inference` ({frame: {obj: bool ndarray}})."""
+        m = self.model
+        dev = torch.device("cuda", self.model.device.index if self.model.device.index is not None else torch.cuda.current_device())
+        q: queue.Queue = queue.Queue(maxsize=self.depth)
+        results: list = [None] * len(clips)
+        errors: list = []
+
+        def lmm_stage():
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(self.s_lmm):
+                    for i, c in enumerate(clips):
+                        ids = c["input_ids"].to(dev, non_blocking=True)
+                        out_ids, emb = m.lmm.generate(ids, c["images"].to(dev, torch.float32, non_blocking=True),
+                                                      c["context_images"].to(dev, torch.float32, non_blocking=True), max_new_tokens,
+                                                      eos_ids=tuple(m.config.eos_token_id), forced=forced_tokens)
+                        emb = emb.clone()
+                        emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
+                        ev = torch.cuda.Event()
+                        ev.record(self.s_lmm)
+                        q.put((i, out_ids, emb, ev))
+            except Exception as e:  # surface, don't swallow (the reference's eval loops silently skip failures)
+                errors.append(e)
+            finally:
+                q.put(None)
+
+        def sam_stage():
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(self.s_sam):
+                    while True:
+                        item = q.get()
+                        if item is None:
+                            return
+                        i, out_ids, emb, ev = item
+                        self.s_sam.wait_event(ev)
+                        if emb.shape[0] == 0:
+                            results[i] = (out_ids, {})
+                            continue
+                        H, W = clips[i]["original_size"]
+                        frames = m.sam.run_video(clips[i]["images_for_sam"].to(dev, non_blocking=True), emb[:, None, :], (int(H), int(W)), binary=True)
+                        stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)
+                        results[i] = (out_ids, {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])})
+            except Exception as e:
+                errors.append(e)
+                while q.get() is not None:
+                    pass
+
+        cur = torch.cuda.current_stream(dev)
+        self.s_lmm.wait_stream(cur)
+        self.s_sam.wait_stream(cur)
+        ta, tb = threading.Thread(target=lmm_stage), threading.Thread(target=sam_stage)
+        ta.start(); tb.start()
+        ta.join(); tb.join()
+        cur.wait_stream(self.s_lmm)
+        cur.wait_stream(self.s_sam)
+        if errors:
+            raise errors[0]
+        return results
