@@ -66,6 +66,9 @@ typedef struct VgGemm {
   const void* resid; long long ldr; long long strideR; int resid_dtype; /* optional residual, may alias C */
   float alpha;
   int force_block_n;                               /* 0 = auto, else 64/128/256 (tests) */
+  int a_dtype;                                     /* VG_BF16 (default) | VG_F32: fp32 A, only for M <= 8 (decode) */
+  float a_rms_eps;                                 /* with fp32 A: rows are RMS-normalised on the fly, x*rsqrt(mean(x^2)+eps)
+                                                      (the norm weight must be folded into B); 0 is a valid eps */
 } VgGemm;
 int vg_gemm(const VgGemm* g, void* stream);
 /* Same contract, one thread per output element, fp32 accumulate in k order. Test/diagnostic reference ON DEVICE. */
@@ -94,6 +97,8 @@ typedef struct VgAttention {
   void* workspace; long long workspace_bytes;   /* optional fp32 scratch enabling split-K over keys: single-query (decode) attention needs
                                                    B*H*16*(max(D,128)+2)*4 bytes; non-causal attention with < 148 query tiles (SAM2 memory
                                                    attention) uses up to 8*B*H*Nq*(Dpad+2)*4 bytes */
+  int ws_has_counters;                          /* the LAST B*H ints of `workspace` are zero-initialised ticket counters owned by the
+                                                   library (kept zero between calls): single-query split-K then merges in-kernel */
   const int* nk_dev;                            /* optional (Nq == 1 only): the number of keys is read from this DEVICE int at run time
                                                    (Nk is then only an upper bound) so a captured decode step can be replayed */
 } VgAttention;
@@ -153,6 +158,9 @@ int vg_embedding(const void* table, long long ldt, const long long* ids, void* o
 /* cache[*pos_dev][col0 : col0+cols] = src[0][col0 : col0+cols] for a bf16 row (KV-cache append at a device-side position, so that
  * the decode step is position-independent at launch level and can be captured in a CUDA graph and replayed). */
 int vg_row_scatter(const void* src, void* cache, long long ld_cache, const int* pos_dev, int col0, int cols, void* stream);
+/* Decode-step helper (one launch instead of RoPE + two scatters): rotate-half RoPE at position *pos_dev on the q and k heads of the
+ * packed bf16 row qkv[0 : 3*H*hd] in place, then cache[*pos_dev][H*hd : 3*H*hd] = (k, v). */
+int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, const int* pos_dev, int n_heads, int head_dim, float theta, void* stream);
 /* adds n to the launch counter (replayed CUDA-graph nodes are launches too) */
 void vg_launch_count_add(long long n);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */

@@ -282,3 +282,38 @@ def test_norm_block_per_row_path(rows, cols):
     w, b = torch.randn(cols, device=DEV), torch.randn(cols, device=DEV)
     assert rel(ops.norm(x, w, b, eps=1e-5, out_dtype=torch.float32), F.layer_norm(x, (cols,), w, b, 1e-5)) < 1e-5
     assert rel(ops.norm(x, w, eps=1e-5, rms=True, out_dtype=torch.float32), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,glu", [(1, 9216, 3072, False), (1, 16384, 3072, True), (1, 3072, 8192, False), (3, 1024, 512, False), (1, 32064, 3072, False)])
+def test_skinny_gemm_fused_rmsnorm(M, N, K, glu):
+    """fp32 A rows RMS-normalised inside the weight-streaming kernel (norm weight folded into W by the caller)."""
+    x = torch.randn(M, K, device=DEV) * 3
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    xn = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)
+    ref = xn @ w.float().T
+    if glu:
+        r = ref.reshape(M, -1, 2, 16)
+        ref = (F.silu(r[:, :, 0]) * r[:, :, 1]).reshape(M, -1)
+    y = ops.gemm(x, w, glu=glu, act="silu" if glu else None, out_dtype=torch.float32, a_rms_eps=1e-5)
+    assert rel(y, ref) < 1e-5
+
+
+def test_rope_kv_append_and_fused_merge_decode_attention():
+    H, hd, max_len = 8, 96, 2100
+    D = H * hd
+    cache = torch.randn(max_len, 3 * D, device=DEV).bfloat16()
+    row = torch.randn(1, 3 * D, device=DEV).bfloat16()
+    pos = torch.tensor([1500], device=DEV, dtype=torch.int32)
+    ref_row = ops.rope_neox_(row.clone(), pos, 2 * H, hd, 10000.0)
+    q_in = row.clone()
+    ops.rope_kv_append_(q_in, cache, pos, H, hd, 10000.0)
+    assert torch.equal(q_in[:, :D], ref_row[:, :D])
+    assert torch.equal(cache[1500, D:], ref_row[0, D:])
+    nk = torch.tensor([1501], device=DEV, dtype=torch.int32)
+    ws = ops.decode_workspace(1, H, hd, DEV)
+    q = q_in[:, :D].unflatten(1, (H, hd))[None]
+    k, v = cache[:2048, D:2 * D].unflatten(1, (H, hd))[None], cache[:2048, 2 * D:].unflatten(1, (H, hd))[None]
+    for _ in range(3):  # ticket counters must self-clean between launches
+        o = ops.attention(q, k, v, causal=True, nk_dev=nk, decode_ws=ws)
+        assert rel(o, sdpa_ref(q, k[:, :1501], v[:, :1501], hd ** -0.5, True, 0)) < 4e-3
+    assert int(ws[-H:].abs().sum()) == 0

@@ -28,6 +28,7 @@ class VgGemm(C.Structure):
         ("resid", C.c_void_p), ("ldr", C.c_longlong), ("strideR", C.c_longlong), ("resid_dtype", C.c_int),
         ("alpha", C.c_float),
         ("force_block_n", C.c_int),
+        ("a_dtype", C.c_int), ("a_rms_eps", C.c_float),
     ]
 
 
@@ -60,7 +61,7 @@ class VgAttention(C.Structure):
         ("causal", C.c_int), ("window", C.c_int),
         ("q_win", C.c_int), ("q_gridw", C.c_int), ("q_nwx", C.c_int), ("q_nwy", C.c_int),
         ("k_win", C.c_int), ("k_gridw", C.c_int), ("k_nwx", C.c_int), ("k_nwy", C.c_int),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("ws_has_counters", C.c_int),
         ("nk_dev", C.c_void_p),
     ]
 
@@ -69,5 +70,5 @@ class VgAttention(C.Structure):
 SYMBOLS = [
     "vg_last_error", "vg_version", "vg_launch_count", "vg_launch_count_reset", "vg_gemm", "vg_gemm_naive", "vg_attention", "vg_norm",
     "vg_add", "vg_pool2x2", "vg_upsample2x_add", "vg_convt2x2_epilogue", "vg_im2col", "vg_dwconv", "vg_conv3x3s2_ln_gelu", "vg_bilinear",
-    "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax", "vg_row_scatter", "vg_launch_count_add",
+    "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax", "vg_row_scatter", "vg_launch_count_add", "vg_rope_kv_append",
 ]

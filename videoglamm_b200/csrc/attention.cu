@@ -21,6 +21,7 @@ struct AttnParams {
   float* ws;                         // split-K partials for single-query attention
   int nsplit;
   const int* nk_dev;                 // optional: number of keys read from device memory (graph-replayable decode)
+  int* counters;                     // optional [B*H] zeroed ints: the last split block of a (b,h) merges in-kernel (no merge launch)
 };
 
 // row index inside the (batch-strided) tensor for token t of batch entry b
@@ -322,6 +323,36 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
       for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
       wp[2 + d] = acc;
     }
+    if (p.counters == nullptr) return;  // separate merge kernel follows
+    // fused merge: the last block to finish for this (b, h) combines all partials (threadfence + atomic ticket)
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(p.counters + b * gridDim.x + h, 1);
+      s_last = (prev == p.nsplit - 1);
+      if (s_last) p.counters[b * gridDim.x + h] = 0;  // self-cleaning for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = p.ws + (static_cast<long long>(b) * gridDim.x + h) * p.nsplit * (DMAX + 2);
+    float mm = -INFINITY;
+    for (int sidx = 0; sidx < p.nsplit; ++sidx) mm = fmaxf(mm, __ldcg(base + sidx * (DMAX + 2)));
+    float ll = 0.f;
+    for (int sidx = 0; sidx < p.nsplit; ++sidx) {
+      const float m = __ldcg(base + sidx * (DMAX + 2));
+      ll += (m == -INFINITY) ? 0.f : __ldcg(base + sidx * (DMAX + 2) + 1) * __expf(m - mm);
+    }
+    __nv_bfloat16* opm = p.o + b * p.o_bs + h * p.o_hs;
+    for (int d = tid; d < p.D; d += 256) {
+      float acc = 0.f;
+      for (int sidx = 0; sidx < p.nsplit; ++sidx) {
+        const float m = __ldcg(base + sidx * (DMAX + 2));
+        acc += (m == -INFINITY) ? 0.f : __ldcg(base + sidx * (DMAX + 2) + 2 + d) * __expf(m - mm);
+      }
+      opm[d] = __float2bfloat16(ll > 0.f ? acc / ll : 0.f);
+    }
     return;
   }
   __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
@@ -439,7 +470,7 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   p.scale = a->scale; p.causal = a->causal; p.window = a->window;
   p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
   p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
-  p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev);
+  p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev); p.counters = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->nk_dev != nullptr && a->Nq != 1) return set_error(VG_EINVAL, "vg_attention: nk_dev is only supported for single-query attention");
   if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && (a->Nk >= 256 || a->nk_dev != nullptr)) {  // decode: causal is a no-op for the newest query
@@ -448,18 +479,20 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
     if (a->workspace != nullptr) {
       nsplit = (a->Nk + 383) / 384;
       if (nsplit > 16) nsplit = 16;
-      const long long need = static_cast<long long>(a->B) * a->H * nsplit * (dmax + 2) * 4;
+      const long long need = static_cast<long long>(a->B) * a->H * nsplit * (dmax + 2) * 4 + (a->ws_has_counters ? static_cast<long long>(a->B) * a->H * 4 : 0);
       if (need > a->workspace_bytes) nsplit = 1;
     }
     p.ws = static_cast<float*>(a->workspace);
     p.nsplit = nsplit;
+    if (nsplit > 1 && a->ws_has_counters)  // zeroed ticket counters live in the last B*H ints of the workspace
+      p.counters = reinterpret_cast<int*>(static_cast<char*>(a->workspace) + a->workspace_bytes - static_cast<long long>(a->B) * a->H * 4);
     dim3 grid(a->H, a->B, nsplit);
     if (dmax == 128)
       attn_decode_kernel<128><<<grid, 256, 0, s>>>(p);
     else
       attn_decode_kernel<256><<<grid, 256, 0, s>>>(p);
     count_launch();
-    if (nsplit > 1) {
+    if (nsplit > 1 && p.counters == nullptr) {
       dim3 mg(a->H, a->B);
       if (dmax == 128)
         attn_decode_merge_kernel<128><<<mg, 128, 0, s>>>(p);

@@ -4,6 +4,7 @@
 //   warp 2           TMEM allocator
 //   warps 4..11      epilogue          tcgen05.ld -> bias/act/GLU/scale/residual -> global (lane quadrant x column half)
 // C[M,N] = A[M,K] * B[N,K]^T, both operands K-major (nn.Linear layout). See include/vglamm.h for the contract.
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -408,11 +409,13 @@ __device__ __forceinline__ float dot8(const uint4& w, const uint4& a) {
   return s;
 }
 
-template <int MR, int WPC>  // MR: rows of A held in registers; WPC: warps cooperating on one output column (split along K)
-__global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ A, long long lda, const __nv_bfloat16* __restrict__ B,
-                                                   long long ldb, const GemmParams p) {
-  constexpr int U = 8;  // independent 16-byte weight loads in flight per lane
-  __shared__ float s_part[8][2 * MR];
+template <int MR, int WPC, int U, bool AF32>
+// MR: rows of A; WPC: warps cooperating on one output column (split along K); U: independent 16-byte weight loads in flight per lane;
+// AF32: A is the fp32 residual stream and the row's RMS normalisation (x * rsqrt(mean(x^2) + eps), norm weight folded into B at load
+// time) is fused: the sum of squares is accumulated from the same A loads the dot product needs.
+__global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ Av, long long lda, const __nv_bfloat16* __restrict__ B, long long ldb,
+                                                   const GemmParams p, float rms_eps) {
+  __shared__ float s_part[8][3 * MR];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = p.glu ? p.N / 2 : p.N;
   const int oc = (blockIdx.x * 8 + wib) / WPC;
@@ -421,9 +424,9 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
   const int n0 = p.glu ? (oc / 16) * 32 + (oc % 16) : oc;
   const __nv_bfloat16* w0 = B + static_cast<long long>(active ? n0 : 0) * ldb;
   const __nv_bfloat16* w1 = w0 + 16 * ldb;  // "up" row (GLU only)
-  float acc0[MR], acc1[MR];
+  float acc0[MR], acc1[MR], ssq[MR];
 #pragma unroll
-  for (int m = 0; m < MR; ++m) acc0[m] = acc1[m] = 0.f;
+  for (int m = 0; m < MR; ++m) acc0[m] = acc1[m] = ssq[m] = 0.f;
   const int chunks = p.K >> 3;
   if (active) {
     for (int c0 = ks * 32 + lane; c0 < chunks; c0 += 32 * WPC * U) {
@@ -445,9 +448,23 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
 #pragma unroll
           for (int m = 0; m < MR; ++m) {
             if (m < p.M) {
-              const uint4 av = __ldg(reinterpret_cast<const uint4*>(A + m * lda + c * 8));
-              acc0[m] += dot8(wv0[u], av);
-              if (p.glu) acc1[m] += dot8(wv1[u], av);
+              if (AF32) {
+                const float4* ap = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Av) + m * lda + c * 8);
+                const float4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+                ssq[m] += a0.x * a0.x + a0.y * a0.y + a0.z * a0.z + a0.w * a0.w + a1.x * a1.x + a1.y * a1.y + a1.z * a1.z + a1.w * a1.w;
+                const uint4 w = wv0[u];
+                acc0[m] += bf16_lo(w.x) * a0.x + bf16_hi(w.x) * a0.y + bf16_lo(w.y) * a0.z + bf16_hi(w.y) * a0.w + bf16_lo(w.z) * a1.x +
+                           bf16_hi(w.z) * a1.y + bf16_lo(w.w) * a1.z + bf16_hi(w.w) * a1.w;
+                if (p.glu) {
+                  const uint4 g = wv1[u];
+                  acc1[m] += bf16_lo(g.x) * a0.x + bf16_hi(g.x) * a0.y + bf16_lo(g.y) * a0.z + bf16_hi(g.y) * a0.w + bf16_lo(g.z) * a1.x +
+                             bf16_hi(g.z) * a1.y + bf16_lo(g.w) * a1.z + bf16_hi(g.w) * a1.w;
+                }
+              } else {
+                const uint4 av = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(Av) + m * lda + c * 8));
+                acc0[m] += dot8(wv0[u], av);
+                if (p.glu) acc1[m] += dot8(wv1[u], av);
+              }
             }
           }
         }
@@ -458,25 +475,27 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
   for (int m = 0; m < MR; ++m) {
     acc0[m] = warp_sum(acc0[m]);
     if (p.glu) acc1[m] = warp_sum(acc1[m]);
+    if (AF32) ssq[m] = warp_sum(ssq[m]);
   }
   if (WPC > 1) {
     if (lane == 0) {
 #pragma unroll
       for (int m = 0; m < MR; ++m) {
-        s_part[wib][2 * m] = acc0[m];
-        s_part[wib][2 * m + 1] = acc1[m];
+        s_part[wib][3 * m] = acc0[m];
+        s_part[wib][3 * m + 1] = acc1[m];
+        s_part[wib][3 * m + 2] = ssq[m];
       }
     }
     __syncthreads();
     if (ks != 0) return;
 #pragma unroll
     for (int m = 0; m < MR; ++m) {
-      acc0[m] = 0.f;
-      acc1[m] = 0.f;
+      acc0[m] = acc1[m] = ssq[m] = 0.f;
 #pragma unroll
       for (int j = 0; j < WPC; ++j) {
-        acc0[m] += s_part[wib + j][2 * m];
-        acc1[m] += s_part[wib + j][2 * m + 1];
+        acc0[m] += s_part[wib + j][3 * m];
+        acc1[m] += s_part[wib + j][3 * m + 1];
+        ssq[m] += s_part[wib + j][3 * m + 2];
       }
     }
   }
@@ -484,10 +503,11 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
 #pragma unroll
   for (int m = 0; m < MR; ++m) {
     if (m >= p.M) break;
-    float v = acc0[m] * p.alpha;
+    const float nrm = AF32 ? rsqrtf(ssq[m] / p.K + rms_eps) * p.alpha : p.alpha;
+    float v = acc0[m] * nrm;
     if (p.bias) v += p.bias[n0];
     if (p.glu) {
-      float u = acc1[m] * p.alpha;
+      float u = acc1[m] * nrm;
       if (p.bias) u += p.bias[n0 + 16];
       v = apply_act(v, p.act) * u;
     } else {
@@ -506,17 +526,30 @@ __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restri
   }
 }
 
-template <int MR>
+static int gemv_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VG_GEMV_U");
+    v = e ? atoi(e) : 4;
+  }
+  return v;
+}
+
+template <int MR, bool AF32>
 static void launch_gemv(const VgGemm* g, const GemmParams& p, cudaStream_t s) {
   const int n_out = g->glu ? g->N / 2 : g->N;
-  const __nv_bfloat16* A = reinterpret_cast<const __nv_bfloat16*>(g->A);
   const __nv_bfloat16* B = reinterpret_cast<const __nv_bfloat16*>(g->B);
   // few columns and long rows: split K over 4 warps so enough bytes are in flight to cover HBM latency
-  if (n_out < 6144 && g->K >= 2048) {
-    gemv_kernel<MR, 4><<<(static_cast<unsigned>(n_out) * 4 + 7) / 8, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+  const bool split = n_out < 6144 && g->K >= 2048;
+  const unsigned blocks = split ? (static_cast<unsigned>(n_out) * 4 + 7) / 8 : (static_cast<unsigned>(n_out) + 7) / 8;
+  const int u = MR > 2 ? 2 : gemv_variant();
+#define VG_GEMV_LAUNCH(WPC, UU) gemv_kernel<MR, WPC, UU, AF32><<<blocks, 256, 0, s>>>(g->A, g->lda, B, g->ldb, p, g->a_rms_eps)
+  if (split) {
+    if (u >= 8) VG_GEMV_LAUNCH(4, 8); else if (u >= 4) VG_GEMV_LAUNCH(4, 4); else VG_GEMV_LAUNCH(4, 2);
   } else {
-    gemv_kernel<MR, 1><<<(static_cast<unsigned>(n_out) + 7) / 8, 256, 0, s>>>(A, g->lda, B, g->ldb, p);
+    if (u >= 8) VG_GEMV_LAUNCH(1, 8); else if (u >= 4) VG_GEMV_LAUNCH(1, 4); else VG_GEMV_LAUNCH(1, 2);
   }
+#undef VG_GEMV_LAUNCH
 }
 
 // ---------------------------------------------------------------------------------------------- naive reference
@@ -744,16 +777,20 @@ using namespace vg;
 extern "C" int vg_gemm(const VgGemm* g, void* stream) {
   int rc = check_gemm(g);
   if (rc) return rc;
-  if ((g->lda % 8) || (g->ldb % 8) || (reinterpret_cast<uintptr_t>(g->A) & 15) || (reinterpret_cast<uintptr_t>(g->B) & 15) ||
+  if (g->a_dtype == VG_F32 && !(g->M <= 8 && g->batch == 1 && g->force_block_n == 0))
+    return set_error(VG_ENOSUP, "vg_gemm: fp32 A (fused RMSNorm) is only supported on the skinny path (M <= 8, batch 1)");
+  if (((g->lda % 8) && g->a_dtype != VG_F32) || (g->ldb % 8) || (reinterpret_cast<uintptr_t>(g->A) & 15) || (reinterpret_cast<uintptr_t>(g->B) & 15) ||
       (g->batch > 1 && ((g->strideA % 8) || (g->strideB % 8))))
     return set_error(VG_EINVAL, "vg_gemm: A/B must be 16B aligned with lda/ldb/strides multiples of 8 (lda=%lld ldb=%lld)", g->lda, g->ldb);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (g->M <= 8 && g->batch == 1 && g->force_block_n == 0 && (g->K % 8) == 0) {
     GemmParams p = to_params(g);
-    if (g->M == 1) launch_gemv<1>(g, p, s);
-    else if (g->M <= 2) launch_gemv<2>(g, p, s);
-    else if (g->M <= 4) launch_gemv<4>(g, p, s);
-    else launch_gemv<8>(g, p, s);
+    const bool af32 = g->a_dtype == VG_F32;
+    if (af32 && ((g->lda % 4) || (reinterpret_cast<uintptr_t>(g->A) & 15))) return set_error(VG_EINVAL, "vg_gemm: fp32 A must be 16B aligned");
+    if (g->M == 1) { if (af32) launch_gemv<1, true>(g, p, s); else launch_gemv<1, false>(g, p, s); }
+    else if (g->M <= 2) { if (af32) launch_gemv<2, true>(g, p, s); else launch_gemv<2, false>(g, p, s); }
+    else if (g->M <= 4) { if (af32) launch_gemv<4, true>(g, p, s); else launch_gemv<4, false>(g, p, s); }
+    else { if (af32) launch_gemv<8, true>(g, p, s); else launch_gemv<8, false>(g, p, s); }
     count_launch();
     return check_launch("gemv_kernel");
   }

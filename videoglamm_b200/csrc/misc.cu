@@ -403,6 +403,32 @@ __global__ void row_scatter_kernel(const __nv_bfloat16* src, __nv_bfloat16* cach
   if (i < cols) cache[static_cast<long long>(*pos) * ld + col0 + i] = src[col0 + i];
 }
 
+__global__ void rope_kv_append_kernel(__nv_bfloat16* qkv, __nv_bfloat16* cache, long long ld, const int* pos_dev, int H, int hd, float theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = hd / 2, D = H * hd;
+  const int pos = *pos_dev;
+  __nv_bfloat16* crow = cache + static_cast<long long>(pos) * ld;
+  if (i < 2 * H * half) {  // rotate pairs of q (heads 0..H-1) and k (heads H..2H-1)
+    const int j = i % half, hh = i / half;
+    const float inv = powf(theta, -2.0f * j / hd);
+    float sn, cs;
+    sincosf(pos * inv, &sn, &cs);
+    __nv_bfloat16* p = qkv + hh * hd;
+    const float a = __bfloat162float(p[j]), b = __bfloat162float(p[j + half]);
+    const __nv_bfloat16 ra = __float2bfloat16(a * cs - b * sn), rb = __float2bfloat16(b * cs + a * sn);
+    if (hh < H) {
+      p[j] = ra;
+      p[j + half] = rb;
+    } else {
+      crow[hh * hd + j] = ra;  // k goes straight to the cache (columns D..2D)
+      crow[hh * hd + j + half] = rb;
+    }
+  } else if (i < 2 * H * half + D) {  // v: plain copy to columns 2D..3D
+    const int c = 2 * D + (i - 2 * H * half);
+    crow[c] = qkv[c];
+  }
+}
+
 // one block (256 threads) per row
 __global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
   const int row = blockIdx.x;
@@ -583,4 +609,14 @@ extern "C" int vg_row_scatter(const void* src, void* cache, long long ld_cache, 
                                                                 pos_dev, col0, cols);
   count_launch();
   return check_launch("row_scatter_kernel");
+}
+
+extern "C" int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, const int* pos_dev, int n_heads, int head_dim, float theta,
+                                 void* stream) {
+  if (!qkv || !cache || !pos_dev || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_kv_append: bad argument");
+  const int n = n_heads * head_dim * 2;  // q+k pairs (H*hd) + v elements (H*hd)
+  rope_kv_append_kernel<<<blocks_for(n, 256), 256, 0, STREAM>>>(static_cast<__nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(cache), ld_cache, pos_dev,
+                                                                n_heads, head_dim, theta);
+  count_launch();
+  return check_launch("rope_kv_append_kernel");
 }

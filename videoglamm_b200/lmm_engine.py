@@ -157,8 +157,11 @@ class LmmEngine:
         self.fc = [pk.lin("model.text_hidden_fcs.0.0"), pk.lin("model.text_hidden_fcs.0.2")]
         ph = cfg.phi
         self.embed = pk.t("model.embed_tokens.weight").to(BF).contiguous()
-        self.lm_head = pk.lin("lm_head")
         self.final_norm = pk.vec("model.norm.weight")
+        # RMSNorm weights are folded into the following projection (W' = W diag(g), in fp32 before the bf16 rounding): the prefill norm
+        # kernel then runs weight-less and the decode GEMV fuses the whole normalisation (x * rsqrt(mean x^2 + eps)) into its A loads.
+        self.lm_head = _Lin((pk.t("lm_head.weight") * self.final_norm[None]).to(BF).contiguous(), None)
+        self.ones = torch.ones(ph.hidden, device=self.dev)
         self.layers = []
         I = ph.inter
         for l in range(ph.layers):
@@ -166,8 +169,9 @@ class LmmEngine:
             gu = pk.t(p + ".mlp.gate_up_proj.weight")
             # interleave [16 gate | 16 up] row blocks so the GEMM epilogue computes silu(gate)*up in registers (include/vglamm.h, glu)
             gu = torch.stack([gu[:I].view(I // 16, 16, -1), gu[I:].view(I // 16, 16, -1)], dim=1).reshape(2 * I, -1)
-            self.layers.append(dict(n1=pk.vec(p + ".input_layernorm.weight"), qkv=pk.lin(p + ".self_attn.qkv_proj"), o=pk.lin(p + ".self_attn.o_proj"),
-                                    n2=pk.vec(p + ".post_attention_layernorm.weight"), gu=gu.to(BF).contiguous(), down=pk.lin(p + ".mlp.down_proj")))
+            n1, n2 = pk.vec(p + ".input_layernorm.weight"), pk.vec(p + ".post_attention_layernorm.weight")
+            qkv = _Lin((pk.t(p + ".self_attn.qkv_proj.weight") * n1[None]).to(BF).contiguous(), None)
+            self.layers.append(dict(qkv=qkv, o=pk.lin(p + ".self_attn.o_proj"), gu=(gu * n2[None]).to(BF).contiguous(), down=pk.lin(p + ".mlp.down_proj")))
         self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
         self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
@@ -175,6 +179,7 @@ class LmmEngine:
         self.dec_pos = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.dec_nk = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.dec_qkv = torch.zeros((1, 3 * ph.hidden), device=self.dev, dtype=BF)
+        self.dec_ws = ops.decode_workspace(1, ph.heads, ph.head_dim, self.dev)
 
     # ------------------------------------------------------------------------------------------------ vision side
     def _project(self, x3: torch.Tensor, layers) -> torch.Tensor:
@@ -226,24 +231,20 @@ class LmmEngine:
         x = ops.embedding(self.embed, self.dec_tok)
         for l, L in enumerate(self.layers):
             cache = self.kv[l]
-            h = ops.norm(x, L["n1"], eps=ph.eps, rms=True)
-            ops.gemm(h, L["qkv"].w, out=self.dec_qkv)
-            ops.rope_neox_(self.dec_qkv, self.dec_pos, 2 * H, hd, ph.rope_theta)
-            ops.row_scatter(self.dec_qkv, cache, self.dec_pos, D, 2 * D)
+            ops.gemm(x, L["qkv"].w, out=self.dec_qkv, a_rms_eps=ph.eps)                       # input RMSNorm fused
+            ops.rope_kv_append_(self.dec_qkv, cache, self.dec_pos, H, hd, ph.rope_theta)       # RoPE(q,k) + cache append, one launch
             q = self.dec_qkv[:, :D].unflatten(1, (H, hd))[None]
             k = cache[:kv_bound, D:2 * D].unflatten(1, (H, hd))[None]
             v = cache[:kv_bound, 2 * D:].unflatten(1, (H, hd))[None]
-            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk)
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk, decode_ws=self.dec_ws)
             x = ops.gemm(o.view(1, D), L["o"].w, resid=x, out=x)
-            h = ops.norm(x, L["n2"], eps=ph.eps, rms=True)
-            h = ops.gemm(h, L["gu"], glu=True, act="silu")
+            h = ops.gemm(x, L["gu"], glu=True, act="silu", a_rms_eps=ph.eps)                   # post-attention RMSNorm fused
             x = ops.gemm(h, L["down"].w, resid=x, out=x)
-        h_last = ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
-        nxt = ops.argmax(ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32))
+        nxt = self._logits_argmax(x)
         self.dec_tok.copy_(nxt)                            # greedy continuation; the host overwrites dec_tok when a token is forced
         self.dec_pos.add_(1)
         self.dec_nk.add_(1)
-        return h_last, nxt
+        return x, nxt
 
     def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False) -> torch.Tensor:
         """HF Phi3Model.forward (called at language_model/phi3.py:72-81) on rows [pos0, pos0+n) given a cache holding rows [0,pos0).
@@ -254,7 +255,7 @@ class LmmEngine:
         end = pos0 + n
         for l, L in enumerate(self.layers):
             cache = self.kv[l]
-            h = ops.norm(x, L["n1"], eps=ph.eps, rms=True)
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
             rows = cache[pos0:end]
             ops.gemm(h, L["qkv"].w, out=rows)
             ops.rope_neox_(rows, pos, 2 * H, hd, ph.rope_theta)
@@ -263,12 +264,16 @@ class LmmEngine:
             v = cache[:end, 2 * D:].unflatten(1, (H, hd))[None]
             o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0)
             x = ops.gemm(o.view(n, D), L["o"].w, resid=x, out=x)
-            h = ops.norm(x, L["n2"], eps=ph.eps, rms=True)
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
             h = ops.gemm(h, L["gu"], glu=True, act="silu")
             x = ops.gemm(h, L["down"].w, resid=x, out=x)
         if last_only:
-            x = x[-1:]
+            return x[-1:].contiguous()                      # un-normalised residual row: the consumers fuse the final norm
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
+
+    def _logits_argmax(self, x_last: torch.Tensor) -> torch.Tensor:
+        """final RMSNorm (fused, weight folded into lm_head) -> lm_head -> argmax on one residual row [1, hidden] fp32."""
+        return ops.argmax(ops.gemm(x_last, self.lm_head.w, out_dtype=F32, a_rms_eps=self.cfg.phi.eps))
 
     def embed_prompt(self, input_ids: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
         """prepare_inputs_labels_for_multimodal arch.py:283-379 (video case): embed(ids before the -200 run) + visual + embed(rest)."""
@@ -292,21 +297,19 @@ class LmmEngine:
         self._alloc_cache(L0 + max_new_tokens + 1)
         dbg = None
         if return_debug:
-            hidden = self._llm(x, 0)
-            h_last = hidden[-1:].contiguous()
-            dbg = dict(prefill_hidden=hidden, logits=[])
+            raise NotImplementedError("return_debug was removed with the fused decode path; use _llm() directly")
         else:
-            h_last = self.g_prefill((L0,), self._prefill_last, x=x)
+            x_last = self.g_prefill((L0,), self._prefill_last, x=x)
         new_ids, seg_hidden = [], []
         kv_bound = min(self.kv[0].shape[0], (L0 + max_new_tokens + 511) // 512 * 512)
-        nxt_dev = ops.argmax(ops.gemm(ops.cast(h_last, BF), self.lm_head.w, out_dtype=F32))
+        nxt_dev = self._logits_argmax(x_last)
         for step in range(max_new_tokens):
             nxt = int(nxt_dev[0])                           # host sync per token: EOS / [SEG] bookkeeping
             if forced and step in forced:
                 nxt = forced[step]
             new_ids.append(nxt)
-            if nxt == cfg.seg_token_idx:
-                seg_hidden.append(h_last.clone())
+            if nxt == cfg.seg_token_idx:  # the hidden state that predicted [SEG]: final-norm of the residual row that produced it
+                seg_hidden.append(ops.norm(x_last, self.final_norm, eps=cfg.phi.eps, rms=True, out_dtype=F32))
             if nxt in eos_ids or step == max_new_tokens - 1:
                 break
             if step == 0:
@@ -314,7 +317,7 @@ class LmmEngine:
                 self.dec_nk.fill_(L0 + 1)
             if step == 0 or (forced and step in forced):
                 self.dec_tok.fill_(nxt)
-            h_last, nxt_dev = self.g_decode((kv_bound,), lambda: self._decode_step(kv_bound), mutable_state=(self.dec_tok, self.dec_pos, self.dec_nk))
+            x_last, nxt_dev = self.g_decode((kv_bound,), lambda: self._decode_step(kv_bound), mutable_state=(self.dec_tok, self.dec_pos, self.dec_nk))
         out_ids = torch.cat([input_ids.reshape(1, -1), torch.tensor([new_ids], device=input_ids.device, dtype=torch.int64)], dim=1)
         if seg_hidden:
             hs = ops.cast(torch.cat(seg_hidden, 0), BF)

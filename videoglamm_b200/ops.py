@@ -32,11 +32,16 @@ def _require_cuda(*ts: torch.Tensor | None) -> None:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, act: str | None = None, glu: bool = False,
          col_scale: torch.Tensor | None = None, resid: torch.Tensor | None = None, out: torch.Tensor | None = None,
-         out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0, force_block_n: int = 0, naive: bool = False) -> torch.Tensor:
+         out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0, force_block_n: int = 0, naive: bool = False,
+         a_rms_eps: float | None = None) -> torch.Tensor:
     """out = epilogue(alpha * a @ w^T). a: bf16 [M,K] or [B,M,K]; w: bf16 [N,K] or [B,N,K] (nn.Linear layout).
     Rows of `a`/`w` may be strided (last dim contiguous)."""
     _require_cuda(a, w, bias, col_scale, resid, out)
-    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, (a.dtype, w.dtype)
+    if a_rms_eps is not None:  # fp32 A rows, RMS-normalised on the fly (skinny path only)
+        assert a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] <= 8 and not naive
+    else:
+        assert a.dtype == torch.bfloat16, a.dtype
+    assert w.dtype == torch.bfloat16, w.dtype
     assert a.stride(-1) == 1 and w.stride(-1) == 1
     batched = a.dim() == 3
     if batched:
@@ -70,6 +75,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, 
         g.resid, g.ldr, g.strideR, g.resid_dtype = resid.data_ptr(), resid.stride(-2), resid.stride(0) if (batched and resid.dim() == 3) else 0, _dt(resid.dtype)
     g.alpha = alpha
     g.force_block_n = force_block_n
+    if a_rms_eps is not None:
+        g.a_dtype, g.a_rms_eps = L.F32, a_rms_eps
     fn = L.lib().vg_gemm_naive if naive else L.lib().vg_gemm
     if _GEMM_PROF is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -115,7 +122,7 @@ def launch_count_reset() -> None:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, causal: bool = False, window: int = 0,
               out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None,
-              nk_dev: torch.Tensor | None = None) -> torch.Tensor:
+              nk_dev: torch.Tensor | None = None, decode_ws: torch.Tensor | None = None) -> torch.Tensor:
     """q [B,Nq,H,D], k/v [B,Nk,H,D] bf16 views (any strides with unit last stride) -> out [B,Nq,H,D] (contiguous unless given).
     q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
     un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
@@ -153,7 +160,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         dp = 32 if D <= 32 else 64 if D <= 64 else 80 if D <= 80 else 96 if D <= 96 else 128 if D <= 128 else 256
         ws = torch.empty((8 * B * H * Nq * (dp + 2),), device=q.device, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
-    if Nq == 1 and q_win is None and Nk >= 768:  # decode: split-K scratch
+    if decode_ws is not None:  # persistent ZEROED fp32 scratch (see decode_workspace): split-K partials + in-kernel merge tickets
+        assert Nq == 1 and decode_ws.dtype == torch.float32 and decode_ws.is_cuda
+        a.workspace, a.workspace_bytes, a.ws_has_counters = decode_ws.data_ptr(), decode_ws.numel() * 4, 1
+    elif Nq == 1 and q_win is None and Nk >= 768:  # decode: split-K scratch
         ws = torch.empty((B * H * 16 * (max(D, 128) + 130),), device=q.device, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     L.check(L.lib().vg_attention(C.byref(a), _stream()), "vg_attention")
@@ -319,3 +329,15 @@ def row_scatter(src: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, c
 
 def launch_count_add(n: int) -> None:
     L.lib().vg_launch_count_add(int(n))
+
+
+def decode_workspace(B: int, H: int, D: int, device) -> torch.Tensor:
+    """Zero-initialised scratch for single-query attention with in-kernel split-K merge (16 partials per head + B*H ticket counters)."""
+    return torch.zeros((B * H * 16 * (max(D, 128) + 130) + B * H,), device=device, dtype=torch.float32)
+
+
+def rope_kv_append_(qkv: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, n_heads: int, head_dim: int, theta: float) -> None:
+    _require_cuda(qkv, cache, pos_dev)
+    assert qkv.dtype == cache.dtype == torch.bfloat16 and pos_dev.dtype == torch.int32 and qkv.is_contiguous() and cache.stride(1) == 1
+    L.check(L.lib().vg_rope_kv_append(_ptr(qkv), _ptr(cache), C.c_longlong(cache.stride(0)), _ptr(pos_dev), n_heads, head_dim, C.c_float(theta),
+                                      _stream()), "vg_rope_kv_append")
