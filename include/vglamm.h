@@ -161,6 +161,10 @@ int vg_row_scatter(const void* src, void* cache, long long ld_cache, const int* 
 /* Decode-step helper (one launch instead of RoPE + two scatters): rotate-half RoPE at position *pos_dev on the q and k heads of the
  * packed bf16 row qkv[0 : 3*H*hd] in place, then cache[*pos_dev][H*hd : 3*H*hd] = (k, v). */
 int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, const int* pos_dev, int n_heads, int head_dim, float theta, void* stream);
+/* MaskDecoder._dynamic_multimask_via_stability (.../sam2/modeling/sam/mask_decoder.py:247-295): per object, index 0 if the stability score
+ * of mask 0 (area(x > delta) / area(x > -delta), 1 if the union is empty) is >= thresh, else the best-IoU index among masks 1..3.
+ * masks fp32 [n_obj][4][hw], iou fp32 [n_obj][4] -> out_idx int64 [n_obj]. */
+int vg_multimask_select(const float* masks, const float* iou, int n_obj, int hw, float delta, float thresh, long long* out_idx, void* stream);
 /* adds n to the launch counter (replayed CUDA-graph nodes are launches too) */
 void vg_launch_count_add(long long n);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */

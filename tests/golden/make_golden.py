@@ -44,6 +44,29 @@ def sam2_video_golden():
     print("sam2_tiny_video", {k: v.shape for k, v in out.items()})
 
 
+def sam2_framewise_golden():
+    """The reference's modules called in the order VideoGLaMM.py:205-241 (get_visual_embs_sam2) and :690-745 (framewise decode) call them."""
+    cfg = O.Sam2Cfg(**O.TINY)
+    ref = ref_sam2()
+    ref.load_state_dict(Wt.make_sam2_state_dict(cfg, 1234), strict=True)
+    torch.manual_seed(9)
+    images, text = torch.randn(2, 3, 256, 256), torch.randn(3, 1, 256)
+    outs = []
+    with torch.no_grad():
+        for t in range(2):
+            bo = ref.forward_image(images[t:t + 1])
+            _, emb, _, _ = ref._prepare_backbone_features(bo)
+            emb[-1] = emb[-1] + ref.no_mem_embed
+            sizes = [(64, 64), (32, 32), (16, 16)]
+            feats = [f.permute(1, 2, 0).view(1, -1, *s) for f, s in zip(emb[::-1], sizes[::-1])][::-1]
+            sp, de = ref.sam_prompt_encoder(points=None, boxes=None, masks=None, text_embeds=text)
+            low, _, _, _ = ref.sam_mask_decoder(image_embeddings=feats[-1], image_pe=ref.sam_prompt_encoder.get_dense_pe(), sparse_prompt_embeddings=sp,
+                                                dense_prompt_embeddings=de, multimask_output=False, repeat_image=True, high_res_features=feats[:-1])
+            outs.append(torch.nn.functional.interpolate(low.float(), (50, 70), mode="bilinear", align_corners=False))
+    np.savez_compressed(os.path.join(OUT, "sam2_tiny_framewise.npz"), masks=torch.stack(outs).numpy())
+    print("sam2_tiny_framewise", torch.stack(outs).shape)
+
+
 def towers_golden():
     H.install_shims()
     from model.videogpt_plus.model.internvideo.internvideo2 import PretrainInternVideo2
@@ -82,4 +105,5 @@ def towers_golden():
 
 if __name__ == "__main__":
     sam2_video_golden()
+    sam2_framewise_golden()
     towers_golden()

@@ -29,3 +29,27 @@ def test_no_seg_returns_empty_dict_and_errors():
     bad.pop("model.norm.weight")
     with pytest.raises(KeyError):
         VideoGLaMMForCausalLM(bad, make_lmm_config(**M.TINY_LMM, seg_token_idx=300), Sam2Config(**O.TINY))
+
+
+def test_framewise_dispatch_through_public_api():
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    ocfg, scfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=300), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=300), Sam2Config(**O.TINY))
+    torch.manual_seed(3)
+    T = 4
+    images, ctx, sam = torch.randn(T, 3, 56, 56), torch.randn(T, 3, 56, 56), torch.randn(2, 3, 256, 256)
+    ids = torch.cat([torch.randint(3, 290, (5,)), torch.full((T,), -200), torch.randint(3, 290, (7,))])
+    forced = {1: 300}
+    out_ids, segs = model.inference([images.cuda()], [ctx.cuda()], [sam.cuda()], ids[None].cuda(), None, [(48, 64)], max_new_tokens=4,
+                                    use_sam2_video_branch=False, forced_tokens=forced)
+    with torch.no_grad():
+        ids_ref, emb_ref, _ = M.generate(sd, ocfg, ids, images, ctx, 4, forced=forced)
+        ssd = {k[len("model.visual_model."):]: v for k, v in sd.items() if k.startswith("model.visual_model.")}
+        ref = O.run_framewise(ssd, scfg, sam, emb_ref[:, None, :], (48, 64))
+    assert torch.equal(out_ids[0].cpu(), ids_ref)
+    for t in range(2):
+        assert (torch.from_numpy(segs[0][t][0]) == (ref[t][0, 0] > 0)).float().mean() > 0.98

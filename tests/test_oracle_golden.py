@@ -28,6 +28,18 @@ def test_sam2_video_session_matches_reference_golden():
             assert torch.all(out == O.NO_OBJ_SCORE)
 
 
+def test_sam2_framewise_matches_reference_golden():
+    g = np.load(os.path.join(G, "sam2_tiny_framewise.npz"))
+    cfg = O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_sam2_state_dict(cfg, 1234)
+    torch.manual_seed(9)
+    images, text = torch.randn(2, 3, 256, 256), torch.randn(3, 1, 256)
+    with torch.no_grad():
+        out = torch.stack(O.run_framewise(sd, cfg, images, text, (50, 70)))
+    ref = torch.from_numpy(g["masks"])
+    assert out.shape == ref.shape and (out - ref).abs().max() < 1e-4 * ref.abs().max()
+
+
 def test_towers_and_llm_match_reference_golden():
     g = np.load(os.path.join(G, "towers_tiny.npz"))
     cfg = M.make_cfg(**M.TINY_LMM)

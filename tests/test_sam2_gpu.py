@@ -116,3 +116,45 @@ def test_video_session_end_to_end(ctx):
         assert rel(a, b) < 2.5e-2, (t, rel(a, b))
         assert ((a > 0) == (b > 0)).float().mean() > 0.99
         assert torch.equal(gotb[t].cpu().bool(), a > 0)
+
+
+def test_framewise_branch(ctx):
+    """use_sam2_video_branch=False path: text token only, multimask_output=False with the stability fallback, repeat_image."""
+    ocfg, sd, eng = ctx["ocfg"], ctx["sd"], ctx["eng"]
+    torch.manual_seed(4)
+    text = torch.randn(3, 1, 256)
+    ref = O.run_framewise(sd, ocfg, ctx["images"][:2], text, (50, 70))
+    got = eng.run_framewise(ctx["images"][:2].cuda(), text.cuda(), (50, 70))
+    for a, b in zip(got, ref):
+        assert rel(a, b[:, 0]) < 2e-2 and ((a.cpu() > 0) == (b[:, 0] > 0)).float().mean() > 0.99
+
+
+def test_multimask_select_kernel():
+    from videoglamm_b200 import ops
+    torch.manual_seed(5)
+    masks = torch.randn(6, 4, 4096, device="cuda")
+    masks[0, 0] = masks[0, 0].abs() + 1.0      # stable: all > delta
+    masks[1, 0] = 0.01 * torch.randn(4096)      # unstable
+    iou = torch.rand(6, 4, device="cuda")
+    got = ops.multimask_select(masks, iou)
+    m, i = O.dynamic_multimask_via_stability(masks.cpu().view(6, 4, 64, 64), iou.cpu())
+    want = torch.stack([masks.cpu()[b, got[b].item()].view(64, 64) for b in range(6)])[:, None]
+    assert torch.equal(want, m) and got[0].item() == 0 and got[1].item() != 0
+
+
+def test_predictor_surface_matches_run_video(ctx):
+    """init_state_from_tensor / add_new_text / propagate_in_video give the same masks as the fused session."""
+    eng = ctx["eng"]
+    images, text = ctx["images"].cuda(), ctx["text"].cuda()
+    want = eng.run_video(images, text, (60, 100))
+    want = [w.clone() for w in want]
+    st = eng.init_state_from_tensor(images, 60, 100)
+    eng.reset_state(st)
+    for o in range(text.shape[0]):
+        fi, ids, m = eng.add_new_text(st, 0, o, text[o:o + 1])
+    assert ids == [0, 1] and m.shape == (2, 1, 60, 100)
+    got = [m for _, _, m in eng.propagate_in_video(st)]
+    for a, b in zip(got, want):
+        assert torch.allclose(a[:, 0], b, atol=1e-4)
+    with pytest.raises(RuntimeError):
+        eng.add_new_text(st, 0, 7, text[:1])   # no new objects after tracking starts (sam2_video_predictor.py:_obj_id_to_idx)

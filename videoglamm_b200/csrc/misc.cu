@@ -429,6 +429,36 @@ __global__ void rope_kv_append_kernel(__nv_bfloat16* qkv, __nv_bfloat16* cache, 
   }
 }
 
+// one block per object: stability score of mask 0 (|{x > d}| / |{x > -d}|) and best-IoU index among masks 1..3
+__global__ void multimask_select_kernel(const float* masks, const float* iou, int hw, float delta, float thresh, long long* out_idx) {
+  const int b = blockIdx.x;
+  const float* m0 = masks + static_cast<long long>(b) * 4 * hw;
+  int ci = 0, cu = 0;
+  for (int i = threadIdx.x; i < hw; i += blockDim.x) {
+    const float v = m0[i];
+    ci += v > delta;
+    cu += v > -delta;
+  }
+  __shared__ int si[256], su[256];
+  si[threadIdx.x] = ci;
+  su[threadIdx.x] = cu;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      si[threadIdx.x] += si[threadIdx.x + s];
+      su[threadIdx.x] += su[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float stab = su[0] > 0 ? static_cast<float>(si[0]) / static_cast<float>(su[0]) : 1.0f;
+    int best = 1;
+    for (int j = 2; j < 4; ++j)
+      if (iou[b * 4 + j] > iou[b * 4 + best]) best = j;  // first maximal index, like torch.argmax
+    out_idx[b] = stab >= thresh ? 0 : best;
+  }
+}
+
 // one block (256 threads) per row
 __global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
   const int row = blockIdx.x;
@@ -619,4 +649,11 @@ extern "C" int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, con
                                                                 n_heads, head_dim, theta);
   count_launch();
   return check_launch("rope_kv_append_kernel");
+}
+
+extern "C" int vg_multimask_select(const float* masks, const float* iou, int n_obj, int hw, float delta, float thresh, long long* out_idx, void* stream) {
+  if (!masks || !iou || !out_idx || n_obj <= 0) return set_error(VG_EINVAL, "vg_multimask_select: bad argument");
+  multimask_select_kernel<<<n_obj, 256, 0, STREAM>>>(masks, iou, hw, delta, thresh, out_idx);
+  count_launch();
+  return check_launch("multimask_select_kernel");
 }

@@ -95,8 +95,6 @@ class VideoGLaMMForCausalLM:
         chat.py:570); returns (output_ids int64 [1, L_txt+N], video_segments_batch: [ {frame_idx: {obj_id: bool ndarray [H,W]}} ])."""
         if not self.use_sam2 and use_sam2_video_branch:
             raise ValueError("Cannot use SAM2 video branch without SAM2")
-        if not use_sam2_video_branch:
-            raise NotImplementedError("framewise branch (VideoGLaMM.py:598-768) is not built yet; pass use_sam2_video_branch=True")
         assert len(images) == 1 and len(images_for_sam) == 1 and input_ids.shape[0] == 1
         if context_images is None or context_images[0] is None:
             raise NotImplementedError("still-image inputs (context_images=None, arch.py encode_images) are not on the video path")
@@ -106,7 +104,8 @@ class VideoGLaMMForCausalLM:
         if emb.shape[0] == 0:
             return out_ids, [{}]                                                     # VideoGLaMM.py:840-842
         H, W = original_size_list[0]
-        frames = self.sam.run_video(images_for_sam[0].to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
+        run = self.sam.run_video if use_sam2_video_branch else self.sam.run_framewise      # VideoGLaMM.py:576-596 dispatch
+        frames = run(images_for_sam[0].to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
         stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)                 # ONE device->host copy per clip
         segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}
         return out_ids, [segs]

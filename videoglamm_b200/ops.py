@@ -341,3 +341,13 @@ def rope_kv_append_(qkv: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tenso
     assert qkv.dtype == cache.dtype == torch.bfloat16 and pos_dev.dtype == torch.int32 and qkv.is_contiguous() and cache.stride(1) == 1
     L.check(L.lib().vg_rope_kv_append(_ptr(qkv), _ptr(cache), C.c_longlong(cache.stride(0)), _ptr(pos_dev), n_heads, head_dim, C.c_float(theta),
                                       _stream()), "vg_rope_kv_append")
+
+
+def multimask_select(masks: torch.Tensor, iou: torch.Tensor, delta: float = 0.05, thresh: float = 0.98) -> torch.Tensor:
+    """masks fp32 [B,4,hw], iou fp32 [B,4] -> int64 [B] selected mask index (dynamic multimask via stability)."""
+    _require_cuda(masks, iou)
+    assert masks.dtype == iou.dtype == torch.float32 and masks.is_contiguous() and iou.is_contiguous() and masks.shape[1] == 4
+    out = torch.empty((masks.shape[0],), device=masks.device, dtype=torch.int64)
+    L.check(L.lib().vg_multimask_select(_ptr(masks), _ptr(iou), masks.shape[0], masks.shape[2], C.c_float(delta), C.c_float(thresh), _ptr(out),
+                                        _stream()), "vg_multimask_select")
+    return out

@@ -1,0 +1,141 @@
+"""Host-side pre-processing and prompt building with the reference's semantics. These are CPU
+image/string transforms in the reference as well (cv2 / PIL / HF CLIPImageProcessor / tokenizer); the arithmetic-heavy path starts at
+the tensors they produce. Paths cited are relative to /root/reference/VideoGLaMM/."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+IMAGE_TOKEN_INDEX = -200                 # model/videogpt_plus/constants.py:12
+DEFAULT_IMAGE_TOKEN, DEFAULT_VIDEO_TOKEN = "<image>", "<video>"
+CHUNK_SIZE = 4
+
+IMAGENET_MEAN, IMAGENET_STD = np.array([0.485, 0.456, 0.406]).reshape(1, 1, 3), np.array([0.229, 0.224, 0.225]).reshape(1, 1, 3)
+CLIP_MEAN, CLIP_STD = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+SAM_MEAN, SAM_STD = torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1), torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+
+
+def iv2_frames_to_tensors(frames: list, size: int = 224) -> list[torch.Tensor]:
+    """VideoTrainProcessor.preprocess / frames2tensor (model/videogpt_plus/model/internvideo/utils.py:104-143): cv2 bilinear resize,
+    (x/255 - mean)/std in float64, HWC -> CHW."""
+    import cv2
+    out = []
+    for f in frames:
+        x = cv2.resize(np.asarray(f), (size, size))
+        x = (x / 255.0 - IMAGENET_MEAN) / IMAGENET_STD
+        out.append(torch.from_numpy(np.transpose(x, (2, 0, 1))))
+    return out
+
+
+def clip_image_processor(size: int = 336):
+    """HF CLIPImageProcessor with openai/clip-vit-large-patch14-336's preprocessor_config (built locally: no hub access needed)."""
+    from transformers import CLIPImageProcessor
+    return CLIPImageProcessor(do_resize=True, size={"shortest_edge": size}, resample=3, do_center_crop=True, crop_size={"height": size, "width": size},
+                              do_rescale=True, rescale_factor=1 / 255, do_normalize=True, image_mean=CLIP_MEAN, image_std=CLIP_STD, do_convert_rgb=True)
+
+
+class EncPreprocessor_VideoGPTPlus:
+    """utils/enc_preprocessors.py:108-166 (video branch): trim / pad-by-repeat to `num_frames`, IV2 frames + CLIP context images."""
+
+    def __init__(self, num_frames: int = 16, image_processor=None):
+        self.num_frames = num_frames
+        self.image_processor = image_processor or clip_image_processor()
+
+    def preprocess(self, pil_images):
+        if not isinstance(pil_images, list):
+            return {"images": self.image_processor.preprocess(pil_images, return_tensors="pt")["pixel_values"][0], "context_images": None}
+        pil_images = list(pil_images[: self.num_frames])
+        while len(pil_images) < self.num_frames:
+            pil_images.append(pil_images[-1])
+        video_frames = iv2_frames_to_tensors(pil_images)
+        context = [self.image_processor.preprocess(im, return_tensors="pt")["pixel_values"][0] for im in pil_images]
+        return {"images": video_frames, "context_images": context}
+
+
+def get_preprocess_shape(oldh: int, oldw: int, long_side: int) -> tuple[int, int]:
+    """ResizeLongestSide.get_preprocess_shape (model/segment_anything/utils/transforms.py:103-113)"""
+    scale = long_side * 1.0 / max(oldh, oldw)
+    return int(oldh * scale + 0.5), int(oldw * scale + 0.5)
+
+
+def sam_preprocess(x: np.ndarray, img_size: int = 1024):
+    """sam_preprocess(model_type="sam2") utils/sam_transforms.py:26-65: PIL bilinear ResizeLongestSide(1024) on uint8, normalise, then a
+    SECOND bilinear squash to 1024x1024 (F.interpolate, align_corners=False). Returns ([3,1024,1024] fp32, resize_shape)."""
+    from PIL import Image
+    newh, neww = get_preprocess_shape(x.shape[0], x.shape[1], img_size)
+    r = np.array(Image.fromarray(x).resize((neww, newh), Image.BILINEAR))
+    t = torch.from_numpy(r).permute(2, 0, 1).contiguous()
+    t = (t - SAM_MEAN) / SAM_STD
+    t = F.interpolate(t.unsqueeze(0), (img_size, img_size), mode="bilinear").squeeze(0)
+    return t, (newh, neww)
+
+
+class SAM_v2_Preprocess:
+    def preprocess(self, x: np.ndarray):
+        return sam_preprocess(x)
+
+
+def tokenizer_image_token(prompt: str, tokenizer, image_token_index: int = IMAGE_TOKEN_INDEX, return_tensors=None):
+    """model/videogpt_plus/mm_utils.py:17-37: tokenise the text between <image> markers, join with the -200 sentinel, keep one BOS."""
+    chunks = [tokenizer(c).input_ids for c in prompt.split(DEFAULT_IMAGE_TOKEN)]
+    ids, offset = [], 0
+    if len(chunks) > 0 and len(chunks[0]) > 0 and chunks[0][0] == tokenizer.bos_token_id:
+        offset = 1
+        ids.append(chunks[0][0])
+    sep = [image_token_index] * (offset + 1)
+    inter = [e for pair in zip(chunks, [sep] * len(chunks)) for e in pair][:-1]
+    for x in inter:
+        ids.extend(x[offset:])
+    if return_tensors == "pt":
+        return torch.tensor(ids, dtype=torch.long)
+    if return_tensors is not None:
+        raise ValueError(f"Unsupported tensor type: {return_tensors}")
+    return ids
+
+
+PHI3_SYSTEM, PHI3_ROLES, PHI3_SEP = "<|system|>\nYou are a helpful AI assistant.", ("\n<|user|>\n", "\n<|assistant|>\n"), "<|end|>"
+
+
+def phi3_prompt(messages: list[tuple[str, str]]) -> str:
+    """conv_phi3_instruct with SeparatorStyle.MPT (model/videogpt_plus/conversation.py:60-68, 124-132)."""
+    ret = PHI3_SYSTEM + PHI3_SEP
+    for role, message in messages:
+        ret += role + message + PHI3_SEP if message else role
+    return ret
+
+
+class ConvGenerator_VideoGPTPlus:
+    """utils/conv_generator.py:86-131 (chat path, mm_use_im_start_end False)."""
+
+    def __init__(self, num_frames: int = 16):
+        self.NUM_FRAMES = num_frames
+
+    def apply_for_chat(self, prompt_text: str, type: str = "video", tokenizer=None, device="cuda"):
+        if type == "video":
+            prompt = (DEFAULT_VIDEO_TOKEN + "\n" + prompt_text).replace(DEFAULT_VIDEO_TOKEN, DEFAULT_IMAGE_TOKEN * self.NUM_FRAMES)
+        elif type == "image":
+            prompt = DEFAULT_IMAGE_TOKEN + "\n" + prompt_text
+        else:
+            raise ValueError(type)
+        prompt = phi3_prompt([(PHI3_ROLES[0], prompt), (PHI3_ROLES[1], "")])
+        return tokenizer_image_token(prompt, tokenizer, return_tensors="pt").unsqueeze(0).to(device)
+
+
+def preprocess_vision(np_images, type="video", enc_preprocessor=None, sam_preprocessor=None, conv_generator=None, precision="fp32", device="cuda"):
+    """chat.py:402-456 (video): sub-sample encoder frames with np.linspace, encode ALL frames for SAM2.
+    Returns (enc_image, enc_context_image, image_sam, original_size_list, resize_list), each a list of length 1."""
+    from PIL import Image
+    if type != "video":
+        raise NotImplementedError("still-image inputs are not on the video path")
+    assert len(np_images) == 1, "Batch size must be 1"
+    frames = np_images[0]
+    n = conv_generator.NUM_FRAMES
+    enc_frames = [frames[i] for i in np.linspace(0, len(frames) - 1, n, dtype=int)] if len(frames) > n else list(frames)
+    d = enc_preprocessor.preprocess([Image.fromarray(f) for f in enc_frames])
+    dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision, torch.float32)
+    enc_image = [torch.stack(d["images"], 0).to(dt).to(device, non_blocking=True)]
+    enc_ctx = [torch.stack(d["context_images"], 0).to(dt).to(device, non_blocking=True)]
+    pre = [sam_preprocessor.preprocess(f) for f in frames]
+    image_sam = [torch.stack([p[0] for p in pre], 0).to(dt).to(device, non_blocking=True)]
+    return enc_image, enc_ctx, image_sam, [frames[0].shape[:2]], [pre[0][1]]

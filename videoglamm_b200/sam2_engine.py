@@ -467,3 +467,88 @@ class Sam2Engine:
                 collect.setdefault("low_res", {})[t] = pred
             outs.append(ops.bilinear(pred, Hv, Wv, mode=3 if binary else 0))
         return outs
+
+    # ------------------------------------------------------------------------------------------------ framewise branch
+    @torch.no_grad()
+    def run_framewise(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False):
+        """SAM2 part of VideoGLaMM_SAM2.inference_framewise (VideoGLaMM.py:598-768 with get_visual_embs_sam2 :205-241): every frame is
+        decoded independently — image_embed = top-level feature + no_mem_embed, prompt = the text token only (no padding points),
+        multimask_output=False with the stability fallback (mask_decoder.py:247-295), repeat_image over the objects,
+        postprocess_masks bilinear to the original size (:147-153). Returns per frame [n_obj, H, W] logits (or uint8 masks)."""
+        cfg = self.cfg
+        T, B = images.shape[0], text_embeds.shape[0]
+        Hv, Wv = video_hw
+        side = 4 * cfg.feat_size
+        outs = []
+        sparse = text_embeds.to(F32).reshape(B, 1, cfg.d_model)
+        for t0 in range(0, T, self.frames_per_encode):
+            fb = self.forward_image(images[t0:t0 + self.frames_per_encode].float())
+            nb = fb["top"].shape[0] // self.HW
+            for i in range(nb):
+                f = {k: v.view(nb, -1, v.shape[-1])[i] for k, v in fb.items()}
+                pix = ops.add(f["top"], self.no_mem_embed, rows=B * self.HW)
+                masks, iou, _, _ = self.mask_decoder(pix, f["s0"], f["s1"], sparse)
+                sel = ops.multimask_select(masks, iou.contiguous())
+                low = masks[torch.arange(B, device=self.dev), sel].reshape(B, side, side).contiguous()
+                outs.append(ops.bilinear(low, Hv, Wv, mode=3 if binary else 0))
+        return outs
+
+    # ------------------------------------------------------------------------------------------------ predictor surface (SURVEY.md §8b)
+    @torch.no_grad()
+    def init_state_from_tensor(self, images: torch.Tensor, video_height: int, video_width: int) -> dict:
+        """SAM2VideoPredictor.init_state_from_tensor sam2_video_predictor.py:109-180: the frames are encoded up front (no one-frame cache)."""
+        feats = []
+        for t0 in range(0, images.shape[0], self.frames_per_encode):
+            fb = self.forward_image(images[t0:t0 + self.frames_per_encode].to(self.dev).float())
+            nb = fb["top"].shape[0] // self.HW
+            feats += [{k: v.view(nb, -1, v.shape[-1])[i] for k, v in fb.items()} for i in range(nb)]
+        return dict(feats=feats, num_frames=images.shape[0], video_height=video_height, video_width=video_width, obj_ids=[], per_obj={},
+                    tracking_has_started=False)
+
+    def reset_state(self, state: dict) -> None:
+        state.update(obj_ids=[], per_obj={}, tracking_has_started=False)
+
+    @torch.no_grad()
+    def add_new_text(self, inference_state: dict, frame_idx: int, obj_id, text: torch.Tensor):
+        """SAM2VideoPredictor.add_new_text :416-495 (the VideoGLaMM fork's text prompt) on the conditioning frame 0.
+        Returns (frame_idx, obj_ids, video_res_masks fp32 [n_obj,1,H,W]) like the reference."""
+        st = inference_state
+        if frame_idx != 0:
+            raise NotImplementedError("text prompts are supported on frame 0 only (the only call pattern of VideoGLaMM.py:846-863)")
+        if st["tracking_has_started"] and obj_id not in st["per_obj"]:
+            raise RuntimeError(f"Cannot add new object id {obj_id} after tracking starts.")
+        f0 = st["feats"][0]
+        pix0 = ops.add(f0["top"], self.no_mem_embed)
+        r = self.forward_sam_heads(pix0, f0["s0"], f0["s1"], text.to(self.dev, F32).reshape(1, 1, -1), 1)
+        if obj_id not in st["per_obj"]:
+            st["obj_ids"].append(obj_id)
+        st["per_obj"][obj_id] = r
+        low = torch.cat([st["per_obj"][o]["low_res_masks"] for o in st["obj_ids"]], 0)
+        masks = ops.bilinear(low, st["video_height"], st["video_width"])
+        return frame_idx, list(st["obj_ids"]), masks[:, None]
+
+    @torch.no_grad()
+    def propagate_in_video(self, inference_state: dict):
+        """SAM2VideoPredictor.propagate_in_video :745-827 (forward, from frame 0): generator of (frame_idx, obj_ids, masks [n_obj,1,H,W])."""
+        st = inference_state
+        if not st["obj_ids"]:
+            raise RuntimeError("No points are provided; please add points first")
+        st["tracking_has_started"] = True
+        B, T = len(st["obj_ids"]), st["num_frames"]
+        Hv, Wv = st["video_height"], st["video_width"]
+        f0 = st["feats"][0]
+        low = torch.cat([st["per_obj"][o]["low_res_masks"] for o in st["obj_ids"]], 0)
+        ptr = torch.cat([st["per_obj"][o]["obj_ptr"] for o in st["obj_ids"]], 0)
+        cond = {0: FrameMem(low, ptr, self.encode_memory(f0["top"], low, binarize=True))}
+        non_cond: dict[int, FrameMem] = {}
+        for t in range(T):
+            if t in cond:
+                pred = cond[t].pred_masks
+            else:
+                f = st["feats"][t]
+                memory, mem_pos, n_ptr = self._memory_bank(t, cond, non_cond, T, B)
+                pix = self.memory_attention(f["top"], B, memory, mem_pos, n_ptr)
+                r = self.forward_sam_heads(pix, f["s0"], f["s1"], None, B)
+                pred = r["low_res_masks"]
+                non_cond[t] = FrameMem(pred, r["obj_ptr"], self.encode_memory(f["top"], pred, binarize=False))
+            yield t, list(st["obj_ids"]), ops.bilinear(pred, Hv, Wv)[:, None]
