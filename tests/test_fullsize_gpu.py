@@ -1,0 +1,75 @@
+"""Parity at BASELINE.json's FULL widths (Hiera-L 144..1152 / head_dim 72, Phi-3 3072 x 32 heads x 96, CLIP-L 1024 x 16 x 64,
+InternVideo2 1408 x 16 x 88, SAM2 decoder / memory 256) against the CPU fp32 oracle. Depth is reduced where the CPU oracle would take
+minutes (the layers are identical); the SAM2 image encoder runs at its true depth (48 blocks) on one 1024x1024 frame."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import lmm as M, sam2 as O, weights as Wt  # noqa: E402
+from videoglamm_b200.config import Sam2Config, make_lmm_config  # noqa: E402
+from videoglamm_b200.lmm_engine import LmmEngine  # noqa: E402
+from videoglamm_b200.sam2_engine import Sam2Engine  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def tok(x):
+    return x[0].permute(1, 2, 0).reshape(-1, x.shape[1])
+
+
+def test_hiera_l_full_depth_one_frame_and_heads():
+    ocfg = O.Sam2Cfg()
+    sd = Wt.make_sam2_state_dict(ocfg, 4321)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}
+    eng = Sam2Engine(sd, Sam2Config())
+    torch.manual_seed(1)
+    img = torch.randn(1, 3, 1024, 1024)
+    with torch.no_grad():
+        fpn, pos = O.forward_image(sd, ocfg, img)
+    f = eng.forward_image(img.cuda())
+    assert f["top"].shape == (4096, 256) and f["s0"].shape == (65536, 32) and f["s1"].shape == (16384, 64)
+    assert rel(f["top"], tok(fpn[2])) < 2e-2 and rel(f["s1"], tok(fpn[1])) < 2e-2 and rel(f["s0"], tok(fpn[0])) < 2e-2
+    # heads + memory encoder + one memory-attention call on the oracle's features (identical inputs), 2 objects
+    text = torch.randn(2, 1, 256)
+    pix = (fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)).expand(2, -1, -1, -1)
+    hi = [fpn[0].expand(2, -1, -1, -1), fpn[1].expand(2, -1, -1, -1)]
+    with torch.no_grad():
+        oh = O.forward_sam_heads(sd, ocfg, pix, hi, text_inputs=text)
+        mf, _ = O.encode_new_memory(sd, ocfg, fpn[2].expand(2, -1, -1, -1), oh["high_res_masks"], is_mask_from_pts=False)
+    s0, s1 = tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous()
+    eh = eng.forward_sam_heads(pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous(), s0, s1, text.cuda(), 2)
+    assert rel(eh["low_res_masks"], oh["low_res_masks"][:, 0]) < 2e-2
+    emf = eng.encode_memory(tok(fpn[2]).cuda().contiguous(), oh["low_res_masks"][:, 0].cuda().contiguous(), binarize=False)
+    assert rel(emf, mf.permute(0, 2, 3, 1).reshape(2, -1, 64)) < 1.5e-2
+    Nk = 3 * 4096 + 12
+    mem = torch.randn(Nk, 2, 64).bfloat16().float()
+    mpos = torch.randn(Nk, 1, 64).expand(-1, 2, -1)
+    with torch.no_grad():
+        oma = O.memory_attention(sd, ocfg, O._flat(fpn[2]).expand(-1, 2, -1), O._flat(pos[2]).expand(-1, 2, -1), mem, mpos, 12)
+    ema = eng.memory_attention(tok(fpn[2]).cuda().contiguous(), 2, mem.permute(1, 0, 2).contiguous().cuda().bfloat16(), mpos[:, 0].contiguous().cuda(), 12)
+    assert rel(ema.view(2, 4096, 256), oma.permute(1, 0, 2)) < 1e-2
+
+
+def test_full_width_towers_and_phi3_reduced_depth():
+    kw = dict(clip=dict(layers=3), iv2=dict(depth=3), phi=dict(layers=2, sliding_window=2047))
+    ocfg, ecfg = M.make_cfg(**kw, seg_token_idx=32011), make_lmm_config(**kw, seg_token_idx=32011)
+    sd = Wt.make_lmm_state_dict(ocfg, 99)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}
+    eng = LmmEngine(sd, ecfg)
+    torch.manual_seed(2)
+    T = 4
+    images, ctx = torch.randn(T, 3, 224, 224), torch.randn(T, 3, 336, 336)
+    with torch.no_grad():
+        vis = M.visual_tokens(sd, ocfg, images, ctx)
+    evis = eng.visual_tokens(images.cuda(), ctx.cuda())
+    assert evis.shape == vis.shape == (T * 208, 3072) and rel(evis, vis) < 1.5e-2
+    ids = torch.cat([torch.randint(3, 32000, (9,)), torch.full((T,), -200), torch.randint(3, 32000, (14,))])
+    with torch.no_grad():
+        ids_ref, emb_ref, _ = M.generate(sd, ocfg, ids, images, ctx, 4, forced={1: 32011})
+    out_ids, emb = eng.generate(ids[None].cuda(), images.cuda(), ctx.cuda(), 4, forced={1: 32011})
+    assert torch.equal(out_ids[0].cpu(), ids_ref)          # greedy ids bit-exact at full width (855-token sequence, KV-cached vs no-cache)
+    assert rel(emb, emb_ref) < 2e-2

@@ -56,6 +56,52 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
   }
 }
 
+// fp32-in fast path: one warp per row, 128-bit loads (lane owns float4 chunks lane, lane+32, ...), 64/128-bit stores
+template <int MAXC>
+__global__ void norm_vec_kernel(const float* __restrict__ x, long long ldx, void* y, int ydt, long long ldy, const float* __restrict__ w,
+                                const float* __restrict__ b, int rows, int cols, float eps, int rms) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  const int nch = cols >> 2;
+  float4 v[MAXC];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * 32;
+    v[i] = c < nch ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  float mean = 0.f;
+  if (!rms) mean = warp_sum(sum) / cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    if (lane + i * 32 < nch) {
+      const float a = v[i].x - mean, c2 = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+      sq += a * a + c2 * c2 + d * d + e * e;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXC; ++i) {
+    const int c = lane + i * 32;
+    if (c < nch) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+      float4 o = make_float4((v[i].x - mean) * rstd * ww.x, (v[i].y - mean) * rstd * ww.y, (v[i].z - mean) * rstd * ww.z, (v[i].w - mean) * rstd * ww.w);
+      if (b) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + c);
+        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      }
+      if (ydt == VG_F32)
+        *(reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + static_cast<long long>(row) * ldy) + c) = o;
+      else
+        *(reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(y) + static_cast<long long>(row) * ldy) + c) = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+}
+
 // one 256-thread block per row (few, wide rows: LLM decode), values cached in registers, block reduction through smem
 template <int MAXV>
 __global__ void __launch_bounds__(256) norm_block_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, const float* w,
@@ -509,6 +555,21 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
       norm_block_kernel<16><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
     count_launch();
     return check_launch("norm_block_kernel");
+  }
+  const int esz_y = y_dtype == VG_F32 ? 4 : 2;
+  const bool vec_ok = x_dtype == VG_F32 && (cols % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & (esz_y * 4 - 1)) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) && cols <= 128 * 12;
+  if (vec_ok) {
+    const float* xf = static_cast<const float*>(x);
+    if (cols <= 128 * 2)
+      norm_vec_kernel<2><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    else if (cols <= 128 * 5)
+      norm_vec_kernel<5><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    else
+      norm_vec_kernel<12><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    count_launch();
+    return check_launch("norm_vec_kernel");
   }
   if (cols <= 32 * 4)
     norm_kernel<4><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
