@@ -85,6 +85,8 @@ int vg_gemm_naive(const VgGemm* g, void* stream);
  * Replaces F.scaled_dot_product_attention at .../backbones/hieradet.py:72-76, .../sam/transformer.py:249-255,316-322,
  * InternVideo2 _naive_attn (internvideo2.py:190-209), HF CLIP / Phi-3 attention (called from clip_encoder.py:45-72, phi3.py:72-81).
  * Requirements: D % 8 == 0, D <= 256; q/k/v strides multiples of 8 elements, 16-byte aligned bases.
+ * Kernels: dense problems with Nq, Nk >= 128 run on the tcgen05 kernel (attention_tc.cu: TMA -> smem -> tcgen05.mma, S and O in TMEM);
+ * windowed / sliding-window / tiny problems use the mma.sync kernel; Nq == 1 uses the split-K decode kernel.
  */
 typedef struct VgAttention {
   const void *q, *k, *v; void* o;
@@ -99,6 +101,7 @@ typedef struct VgAttention {
                                                    attention) uses up to 8*B*H*Nq*(Dpad+2)*4 bytes */
   int ws_has_counters;                          /* the LAST B*H ints of `workspace` are zero-initialised ticket counters owned by the
                                                    library (kept zero between calls): single-query split-K then merges in-kernel */
+  int force_legacy;                             /* 1: skip the tcgen05 kernel and use the mma.sync kernel (tests / A-B timing) */
   const int* nk_dev;                            /* optional (Nq == 1 only): the number of keys is read from this DEVICE int at run time
                                                    (Nk is then only an upper bound) so a captured decode step can be replayed */
 } VgAttention;

@@ -61,7 +61,7 @@ class VgAttention(C.Structure):
         ("causal", C.c_int), ("window", C.c_int),
         ("q_win", C.c_int), ("q_gridw", C.c_int), ("q_nwx", C.c_int), ("q_nwy", C.c_int),
         ("k_win", C.c_int), ("k_gridw", C.c_int), ("k_nwx", C.c_int), ("k_nwy", C.c_int),
-        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("ws_has_counters", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("ws_has_counters", C.c_int), ("force_legacy", C.c_int),
         ("nk_dev", C.c_void_p),
     ]
 

@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 // HBM/L2-bound: one block per (head, batch); each warp walks 32-key groups: lane-per-key QK^T (no shuffles in the dot product),
 // warp-level online softmax, then lane-per-feature PV with the probabilities staged in shared memory; warps merged at the end.
 template <int DMAX>
-__global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
+__global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
   if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
-  constexpr int NW = 8, EPL = DMAX / 32;  // features per lane in the PV phase
+  constexpr int NW = 4, PPL = DMAX / 64;  // warps per block; bf16x2 feature pairs per lane in the PV phase
   __shared__ float s_q[DMAX];
   __shared__ float s_p[NW][32];
   __shared__ float s_o[NW][DMAX];
@@ -249,24 +249,25 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
   const __nv_bfloat16* qp = p.q + b * p.q_bs + h * p.q_hs;
   const __nv_bfloat16* kb = p.k + b * p.k_bs + h * p.k_hs;
   const __nv_bfloat16* vb = p.v + b * p.v_bs + h * p.v_hs;
-  for (int d = tid; d < DMAX; d += 256) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
+  for (int d = tid; d < DMAX; d += 128) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
   __syncthreads();
   int k_begin = 0;
   if (p.window > 0) k_begin = max(0, p.Nk - 1 - p.window);
   // this block's key range (split-K over blockIdx.z)
-  const int span = (p.Nk - k_begin + p.nsplit - 1) / p.nsplit;
-  const int k_lo = k_begin + blockIdx.z * ((span + 31) / 32 * 32);
-  const int k_hi = min(p.Nk, k_lo + (span + 31) / 32 * 32);
-  float m_run = -INFINITY, l_run = 0.f, o[EPL];
+  const int span = ((p.Nk - k_begin + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
+  const int k_lo = k_begin + blockIdx.z * span;
+  const int k_hi = min(p.Nk, k_lo + span);
+  float m_run = -INFINITY, l_run = 0.f, o[2 * PPL];
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) o[e] = 0.f;
-  const int chunks = p.D >> 3;
+  for (int e = 0; e < 2 * PPL; ++e) o[e] = 0.f;
+  const int chunks = p.D >> 3, npairs = p.D >> 1;
   for (int g0 = k_lo + warp * 32; g0 < k_hi; g0 += NW * 32) {
     const int j = g0 + lane;
     float sc = -INFINITY;
-    if (j < k_hi) {
+    if (j < k_hi) {  // lane-per-key dot product: 16-byte loads of this lane's key row
       const uint4* kr = reinterpret_cast<const uint4*>(kb + static_cast<long long>(j) * p.k_rs);
       float acc = 0.f;
+#pragma unroll 4
       for (int c = 0; c < chunks; ++c) {
         const uint4 kv = __ldg(kr + c);
         const float* qq = s_q + c * 8;
@@ -284,16 +285,30 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
     m_run = m_new;
     s_p[warp][lane] = pj;
     __syncwarp();
-    const int nvalid = min(32, k_hi - g0);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) o[e] *= alpha;
-    for (int jj = 0; jj < nvalid; ++jj) {
-      const float pv = s_p[warp][jj];
-      const __nv_bfloat16* vr = vb + static_cast<long long>(g0 + jj) * p.v_rs;
+    for (int e = 0; e < 2 * PPL; ++e) o[e] *= alpha;
+    // lane-per-feature-pair PV: 4 keys per step, all loads issued before the FMAs (rows past k_hi are clamped; their p is 0)
+    for (int jj = 0; jj < 32; jj += 4) {
+      if (g0 + jj >= k_hi) break;
+      uint32_t vv[4][PPL];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const int d = lane + e * 32;
-        if (d < p.D) o[e] = fmaf(pv, __bfloat162float(vr[d]), o[e]);
+      for (int u = 0; u < 4; ++u) {
+        const int key = min(g0 + jj + u, k_hi - 1);
+        const uint32_t* vr = reinterpret_cast<const uint32_t*>(vb + static_cast<long long>(key) * p.v_rs);
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+          const int pr = lane + e * 32;
+          vv[u][e] = pr < npairs ? __ldg(vr + pr) : 0u;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float pv = s_p[warp][jj + u];
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+          o[2 * e] = fmaf(pv, bf16_lo(vv[u][e]), o[2 * e]);
+          o[2 * e + 1] = fmaf(pv, bf16_hi(vv[u][e]), o[2 * e + 1]);
+        }
       }
     }
     __syncwarp();
@@ -303,7 +318,11 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
     s_l[warp] = l_run;
   }
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) s_o[warp][lane + e * 32] = o[e];
+  for (int e = 0; e < PPL; ++e) {
+    const int pr = lane + e * 32;
+    s_o[warp][2 * pr] = o[2 * e];
+    s_o[warp][2 * pr + 1] = o[2 * e + 1];
+  }
   __syncthreads();
   float m_all = -INFINITY;
 #pragma unroll
@@ -311,13 +330,13 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
   float l_all = 0.f;
 #pragma unroll
   for (int w = 0; w < NW; ++w) l_all += (s_m[w] == -INFINITY) ? 0.f : s_l[w] * __expf(s_m[w] - m_all);
-  if (p.nsplit > 1) {  // un-normalised partial (m, l, o[D]) for the merge kernel
+  if (p.nsplit > 1) {  // un-normalised partial (m, l, o[D]) for the merge
     float* wp = p.ws + ((static_cast<long long>(b) * gridDim.x + h) * p.nsplit + blockIdx.z) * (DMAX + 2);
     if (tid == 0) {
       wp[0] = m_all;
       wp[1] = l_all;
     }
-    for (int d = tid; d < p.D; d += 256) {
+    for (int d = tid; d < p.D; d += 128) {
       float acc = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
       ll += (m == -INFINITY) ? 0.f : __ldcg(base + sidx * (DMAX + 2) + 1) * __expf(m - mm);
     }
     __nv_bfloat16* opm = p.o + b * p.o_bs + h * p.o_hs;
-    for (int d = tid; d < p.D; d += 256) {
+    for (int d = tid; d < p.D; d += 128) {
       float acc = 0.f;
       for (int sidx = 0; sidx < p.nsplit; ++sidx) {
         const float m = __ldcg(base + sidx * (DMAX + 2));
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(256) attn_decode_kernel(AttnParams p) {
     return;
   }
   __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
-  for (int d = tid; d < p.D; d += 256) {
+  for (int d = tid; d < p.D; d += 128) {
     float acc = 0.f;
 #pragma unroll
     for (int w = 0; w < NW; ++w) acc += (s_m[w] == -INFINITY) ? 0.f : s_o[w][d] * __expf(s_m[w] - m_all);
@@ -449,6 +468,10 @@ static int launch_attn(AttnParams p, cudaStream_t s, void* workspace, long long 
 
 }  // namespace vg
 
+namespace vg {
+int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int* dpm_out);  // attention_tc.cu
+}
+
 using namespace vg;
 
 extern "C" int vg_attention(const VgAttention* a, void* stream) {
@@ -477,7 +500,7 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
     const int dmax = a->D <= 128 ? 128 : 256;
     int nsplit = 1;
     if (a->workspace != nullptr) {
-      nsplit = (a->Nk + 383) / 384;
+      nsplit = (a->Nk + 255) / 256;
       if (nsplit > 16) nsplit = 16;
       const long long need = static_cast<long long>(a->B) * a->H * nsplit * (dmax + 2) * 4 + (a->ws_has_counters ? static_cast<long long>(a->B) * a->H * 4 : 0);
       if (need > a->workspace_bytes) nsplit = 1;
@@ -488,9 +511,9 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       p.counters = reinterpret_cast<int*>(static_cast<char*>(a->workspace) + a->workspace_bytes - static_cast<long long>(a->B) * a->H * 4);
     dim3 grid(a->H, a->B, nsplit);
     if (dmax == 128)
-      attn_decode_kernel<128><<<grid, 256, 0, s>>>(p);
+      attn_decode_kernel<128><<<grid, 128, 0, s>>>(p);
     else
-      attn_decode_kernel<256><<<grid, 256, 0, s>>>(p);
+      attn_decode_kernel<256><<<grid, 128, 0, s>>>(p);
     count_launch();
     if (nsplit > 1 && p.counters == nullptr) {
       dim3 mg(a->H, a->B);
@@ -501,6 +524,25 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       count_launch();
     }
     return check_launch("attn_decode_kernel");
+  }
+  if (!a->force_legacy) {  // tcgen05 path (large dense problems); falls through to the mma.sync kernel when not applicable
+    int ns = 1, dpm = 128;
+    const int rc = attention_tc_try(a, s, &ns, &dpm);
+    if (rc == VG_OK) {
+      if (ns > 1) {
+        p.ws = static_cast<float*>(a->workspace);
+        p.nsplit = ns;
+        const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
+        if (dpm == 128)
+          flash_attn_merge_kernel<128><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+        else
+          flash_attn_merge_kernel<256><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+        count_launch();
+        return check_launch("flash_attn_merge_kernel");
+      }
+      return VG_OK;
+    }
+    if (rc != VG_ENOSUP) return rc;
   }
   if (a->D <= 32) return launch_attn<32>(p, s, a->workspace, a->workspace_bytes);
   if (a->D <= 64) return launch_attn<64>(p, s, a->workspace, a->workspace_bytes);

@@ -1,0 +1,373 @@
+// tcgen05 flash attention (sm_100a): S = Q K^T and O += P V on the 5th-gen tensor cores with accumulators in TMEM.
+//   warp 0 (1 lane)  TMA producer: Q tile once, K/V tiles through a 2-stage ring (4D tensor maps over the strided q/k/v views,
+//                    head-dim tail zero-filled by TMA out-of-bounds handling, SWIZZLE_128B)
+//   warp 1 (1 lane)  MMA issuer:   S[128 x BN] = Q K^T (both K-major);  O[128 x Dp] += P V (P K-major from smem, V MN-major)
+//   warp 2           TMEM allocator
+//   warps 4..7       softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S, masks, online max with LAZY rescaling of O
+//                    (O is only rescaled in TMEM when a row max grows by more than 2^8), P -> bf16 -> swizzled smem, final O / l.
+// Optional split-K over keys for problems with few query tiles (SAM2 memory attention: 4096 queries x <= 28.7k keys, 1 head).
+// Version 1 is serial per key tile (QK^T -> softmax -> PV); S/P double-buffering is the next step.
+#include <mutex>
+#include <unordered_map>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace vg {
+
+struct AttnTcParams {
+  int B, H, Nq, Nk, D, Dp, nblk;
+  float scale;
+  int causal, nsplit;
+  __nv_bfloat16* o;
+  long long o_bs, o_hs, o_rs;
+  float* ws;  // split-K partials [split][b][h][row][DPM + 2]
+  int dpm;    // row width of the partials (128 or 256)
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023) != 0) __trap();
+  constexpr int BM = 128;
+  const int kv_blk_bytes = BN * 128;           // one 64-feature block of a K or V tile
+  const int kv_stage_bytes = p.nblk * kv_blk_bytes;
+  uint8_t* sQ = smem;                          // nblk x [128 rows x 128 B]
+  uint8_t* sK = sQ + p.nblk * 16384;           // 2 stages
+  uint8_t* sV = sK + 2 * kv_stage_bytes;       // 2 stages
+  uint8_t* sP = sV + 2 * kv_stage_bytes;       // (BN / 64) x [128 rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (BN / 64) * 16384);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_tiles = (p.Nq + BM - 1) / BM;
+  const int split = blockIdx.x / q_tiles;
+  const int q0 = (blockIdx.x - split * q_tiles) * BM, h = blockIdx.y, b = blockIdx.z;
+  const int off = p.Nk - p.Nq;
+  int k_begin = 0, k_end = p.Nk;
+  if (p.causal) k_end = min(p.Nk, q0 + BM + off);
+  if (p.nsplit > 1) {
+    const int per = ((p.Nk + p.nsplit - 1) / p.nsplit + BN - 1) / BN * BN;
+    k_begin = split * per;
+    k_end = min(k_end, k_begin + per);
+  }
+  const int ntiles = k_end > k_begin ? (k_end - k_begin + BN - 1) / BN : 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tO = tmem_base;         // columns [0, Dp)
+  const uint32_t tS = tmem_base + 256;   // columns [256, 256 + BN)
+
+  if (warp == 0) {
+    if (lane == 0 && ntiles > 0) {
+      // ------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(q_full, p.nblk * 16384);
+      for (int blk = 0; blk < p.nblk; ++blk) tma_load_4d(&tmQ, q_full, sQ + blk * 16384, blk * 64, h, q0, b);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kv_stage_bytes);
+        const int k0 = k_begin + j * BN;
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          tma_load_4d(&tmK, &kv_full[st], sK + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, k0, b);
+          tma_load_4d(&tmV, &kv_full[st], sV + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, k0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && ntiles > 0) {
+      // ------------------------------------------------ MMA issuer
+      const uint32_t idesc_s = umma_idesc_bf16(BM, BN);
+      const uint32_t idesc_o = umma_idesc_bf16_bmn(BM, p.Dp);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        // S = Q K^T over the (zero-padded) head dim, 16 features per MMA
+        for (int blk = 0; blk < p.nblk; ++blk) {
+          const int steps = min(4, (p.Dp - 64 * blk) >> 4);
+          const uint64_t qd = umma_desc_sw128(smem_u32(sQ + blk * 16384));
+          const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * kv_stage_bytes + blk * kv_blk_bytes));
+          for (int k = 0; k < steps; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc_s, (blk | k) != 0);
+        }
+        umma_commit(s_full);  // also implies PV of the previous tile has retired (in-order completion)
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        // O += P V: 16 keys per MMA; V is MN-major (features contiguous): 8-key groups every 1024 B, 64-feature blocks every BN*128 B
+        for (int kk = 0; kk < BN / 16; ++kk) {
+          const uint64_t pd = umma_desc_sw128(smem_u32(sP + (kk >> 2) * 16384)) + 2 * (kk & 3);
+          const uint64_t vd = umma_desc_sw128_mn(smem_u32(sV + st * kv_stage_bytes + kk * 2048), kv_blk_bytes, 1024);
+          umma_bf16(tO, pd, vd, idesc_o, (j | kk) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ softmax / correction / epilogue: one query row per thread
+    const int ew = warp & 3;
+    const int r = ew * 32 + lane;  // row in the tile == TMEM lane
+    const int row = q0 + r;
+    const uint32_t lane_addr = static_cast<uint32_t>(ew * 32) << 16;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    float m_ref = -INFINITY, l = 0.f;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int k0 = k_begin + j * BN;
+      const int col_lim = p.causal ? min(p.Nk, row + off + 1) : p.Nk;  // valid columns are < col_lim
+      float sv[BN];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        tmem_ld32(tS + lane_addr + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = (k0 + c * 32 + i < col_lim) ? __uint_as_float(raw[i]) : -INFINITY;
+          sv[c * 32 + i] = x;
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      // lazy rescale (warp-uniform because tcgen05.ld/st are warp-collective): only when some row's max grew by more than 2^8
+      const bool need = (m_ref != -INFINITY) && ((m_new - m_ref) * sl2 > 8.0f);
+      if (m_ref == -INFINITY) m_ref = m_new;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
+        for (int c = 0; c < p.Dp; c += 32) {
+          uint32_t raw[32];
+          tmem_ld32(tO + lane_addr + c, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__uint_as_float(raw[i]) * alpha);
+          tmem_st32(tO + lane_addr + c, raw);
+        }
+        tmem_st_wait();
+        l *= alpha;
+        if (need) m_ref = m_new;
+      }
+      const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
+      // P = exp2(S*scale*log2e - m) -> bf16 -> shared memory in the K-major SWIZZLE_128B operand layout
+      uint8_t* prow = sP + r * 128;
+      const int sw = r & 7;
+#pragma unroll
+      for (int c8 = 0; c8 < BN / 8; ++c8) {
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          pv[i] = ex2_approx(sv[c8 * 8 + i] * sl2 - msc);
+          l += pv[i];
+        }
+        *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + (((c8 & 7) ^ sw) << 4)) =
+            make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
+      }
+      fence_async_shared();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    if (ntiles > 0) {
+      mbar_wait(o_full, 0);
+      tc_fence_after();
+    }
+    if (p.nsplit > 1) {
+      if (row < p.Nq) {
+        float* wp = p.ws + ((((static_cast<long long>(split) * p.B + b) * p.H + h) * p.Nq) + row) * (p.dpm + 2);
+        wp[0] = (m_ref == -INFINITY) ? -INFINITY : m_ref * p.scale;
+        wp[1] = l;
+      }
+    }
+    const float inv = (p.nsplit > 1) ? 1.0f : (l > 0.f ? 1.0f / l : 0.f);
+    for (int c = 0; c < p.Dp; c += 32) {
+      uint32_t raw[32];
+      if (ntiles > 0) {
+        tmem_ld32(tO + lane_addr + c, raw);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) raw[i] = 0u;
+      }
+      if (row >= p.Nq) continue;
+      if (p.nsplit > 1) {
+        float* wp = p.ws + ((((static_cast<long long>(split) * p.B + b) * p.H + h) * p.Nq) + row) * (p.dpm + 2) + 2 + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (c + i < p.D) wp[i] = __uint_as_float(raw[i]);
+      } else {
+        __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs + static_cast<long long>(row) * p.o_rs + c;
+        if (c + 32 <= p.D && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(op + i) = make_uint4(pack_bf16(__uint_as_float(raw[i]) * inv, __uint_as_float(raw[i + 1]) * inv),
+                                                           pack_bf16(__uint_as_float(raw[i + 2]) * inv, __uint_as_float(raw[i + 3]) * inv),
+                                                           pack_bf16(__uint_as_float(raw[i + 4]) * inv, __uint_as_float(raw[i + 5]) * inv),
+                                                           pack_bf16(__uint_as_float(raw[i + 6]) * inv, __uint_as_float(raw[i + 7]) * inv));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c + i < p.D) op[i] = __float2bfloat16(__uint_as_float(raw[i]) * inv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+struct Key4 {
+  const void* ptr;
+  long long hs, rs, bs;
+  int D, H, N, B, rows;
+  bool operator==(const Key4& o) const {
+    return ptr == o.ptr && hs == o.hs && rs == o.rs && bs == o.bs && D == o.D && H == o.H && N == o.N && B == o.B && rows == o.rows;
+  }
+};
+struct Key4Hash {
+  size_t operator()(const Key4& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    for (size_t v : {static_cast<size_t>(k.hs), static_cast<size_t>(k.rs), static_cast<size_t>(k.bs), static_cast<size_t>(k.D), static_cast<size_t>(k.H),
+                     static_cast<size_t>(k.N), static_cast<size_t>(k.B), static_cast<size_t>(k.rows)})
+      h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// bf16 view x[b][n][h][d] with element strides (bs, rs, hs, 1) -> 4D map {D, H, N, B}, box {64, 1, rows, 1}, SWIZZLE_128B, zero OOB fill
+static int make_map4(CUtensorMap* out, const void* ptr, int D, int H, int N, int B, long long hs, long long rs, long long bs, int rows) {
+  static std::mutex mu;
+  static std::unordered_map<Key4, CUtensorMap, Key4Hash> cache;
+  if (H == 1) hs = D;  // strides of size-1 dimensions are irrelevant but must be valid
+  if (B == 1) bs = static_cast<long long>(N) * rs;
+  Key4 key{ptr, hs, rs, bs, D, H, N, B, rows};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return VG_OK;
+    }
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(hs) * 2, static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
+  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(VG_ENOSUP, "attention tensor map rejected (%d)", (int)r);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, *out);
+  }
+  return VG_OK;
+}
+
+template <int BN>
+static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
+  CUtensorMap tq, tk, tv;
+  int rc = make_map4(&tq, a->q, a->D, a->H, a->Nq, a->B, a->q_hs, a->q_rs, a->q_bs, 128);
+  if (rc) return rc;
+  rc = make_map4(&tk, a->k, a->D, a->H, a->Nk, a->B, a->k_hs, a->k_rs, a->k_bs, BN);
+  if (rc) return rc;
+  rc = make_map4(&tv, a->v, a->D, a->H, a->Nk, a->B, a->v_hs, a->v_rs, a->v_bs, BN);
+  if (rc) return rc;
+  const int smem = p.nblk * 16384 + 4 * p.nblk * BN * 128 + (BN / 64) * 16384 + 256;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return set_error(VG_ECUDA, "attention_tc smem attr: %s", cudaGetErrorString(e));
+    attr_smem = 227 * 1024;
+  }
+  const int q_tiles = (a->Nq + 127) / 128;
+  dim3 grid(q_tiles * p.nsplit, a->H, a->B);
+  flash_attn_tc_kernel<BN><<<grid, 256, smem, s>>>(tq, tk, tv, p);
+  count_launch();
+  return check_launch("flash_attn_tc_kernel");
+}
+
+// Returns VG_OK if the tcgen05 kernel handled the call, VG_ENOSUP if the caller should use the generic kernel.
+int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int* dpm_out) {
+  *nsplit_out = 1;
+  if (a->q_win != 0 || a->k_win != 0 || a->window != 0 || a->nk_dev != nullptr) return VG_ENOSUP;
+  if (a->Nq < 128 || a->Nk < 128 || a->D > 256 || (a->D % 8)) return VG_ENOSUP;
+  if ((reinterpret_cast<uintptr_t>(a->o) & 3) || (a->o_rs % 2) || (a->o_hs % 2) || (a->o_bs % 2)) return VG_ENOSUP;
+  AttnTcParams p;
+  p.B = a->B; p.H = a->H; p.Nq = a->Nq; p.Nk = a->Nk; p.D = a->D;
+  p.Dp = (a->D + 15) / 16 * 16;
+  p.nblk = (p.Dp + 63) / 64;
+  p.scale = a->scale; p.causal = a->causal;
+  p.o = static_cast<__nv_bfloat16*>(a->o);
+  p.o_bs = a->o_bs; p.o_hs = a->o_hs; p.o_rs = a->o_rs;
+  p.ws = nullptr; p.nsplit = 1;
+  p.dpm = a->D <= 128 ? 128 : 256;
+  const int BN = a->D > 128 ? 64 : 128;
+  const long long ctas = static_cast<long long>((a->Nq + 127) / 128) * a->H * a->B;
+  if (a->workspace != nullptr && !a->causal && ctas < 148 && a->Nk >= 2048) {
+    int ns = static_cast<int>((148 + ctas - 1) / ctas);
+    if (ns > 8) ns = 8;
+    if (ns > a->Nk / 1024) ns = a->Nk / 1024;
+    const long long need = static_cast<long long>(ns) * a->B * a->H * a->Nq * (p.dpm + 2) * 4;
+    if (ns > 1 && need <= a->workspace_bytes) {
+      p.nsplit = ns;
+      p.ws = static_cast<float*>(a->workspace);
+    }
+  }
+  *nsplit_out = p.nsplit;
+  *dpm_out = p.dpm;
+  return BN == 64 ? launch_tc<64>(a, p, s) : launch_tc<128>(a, p, s);
+}
+
+}  // namespace vg

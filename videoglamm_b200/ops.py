@@ -122,7 +122,7 @@ def launch_count_reset() -> None:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, causal: bool = False, window: int = 0,
               out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None,
-              nk_dev: torch.Tensor | None = None, decode_ws: torch.Tensor | None = None) -> torch.Tensor:
+              nk_dev: torch.Tensor | None = None, decode_ws: torch.Tensor | None = None, legacy: bool = False) -> torch.Tensor:
     """q [B,Nq,H,D], k/v [B,Nk,H,D] bf16 views (any strides with unit last stride) -> out [B,Nq,H,D] (contiguous unless given).
     q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
     un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
@@ -152,13 +152,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     a.B, a.H, a.Nq, a.Nk, a.D = B, H, Nq, Nk, D
     a.scale = float(scale if scale is not None else D ** -0.5)
     a.causal, a.window = int(causal), int(window)
+    a.force_legacy = int(legacy)
     if nk_dev is not None:
         assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
         a.nk_dev = nk_dev.data_ptr()
     if q_win is None and not causal and Nq > 1 and Nk >= 2048 and B * H * ((Nq + 63) // 64) < 148:
         # few query tiles, many keys (SAM2 memory attention): split-K scratch for up to 8 partials
         dp = 32 if D <= 32 else 64 if D <= 64 else 80 if D <= 80 else 96 if D <= 96 else 128 if D <= 128 else 256
-        ws = torch.empty((8 * B * H * Nq * (dp + 2),), device=q.device, dtype=torch.float32)
+        ws = torch.empty((8 * B * H * Nq * (max(dp, 128 if D <= 128 else 256) + 2),), device=q.device, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if decode_ws is not None:  # persistent ZEROED fp32 scratch (see decode_workspace): split-K partials + in-kernel merge tickets
         assert Nq == 1 and decode_ws.dtype == torch.float32 and decode_ws.is_cuda
