@@ -103,7 +103,61 @@ def towers_golden():
     print("towers_tiny", a.shape, b.shape, lg.shape)
 
 
+E2E_SEG = 300
+E2E_LMM = dict(clip=dict(layers=2), iv2=dict(depth=3), phi=dict(vocab=320, hidden=128, layers=2, heads=4, inter=256, sliding_window=None))
+E2E_FORCED = {1: E2E_SEG, 3: E2E_SEG}
+E2E_NEW, E2E_HW = 5, (48, 64)
+
+
+def e2e_inputs():
+    """Seeded inputs of the end-to-end pin (shared by the generator and the tests)."""
+    torch.manual_seed(21)
+    T, Ts = 4, 3
+    images, ctx, sam = torch.randn(T, 3, 224, 224), torch.randn(T, 3, 336, 336), torch.randn(Ts, 3, 256, 256)
+    ids = torch.cat([torch.tensor([1]), torch.randint(3, 290, (5,)), torch.full((T,), -200), torch.randint(3, 290, (7,))])
+    return images, ctx, sam, ids
+
+
+def ref_videoglamm(workdir=None):
+    """The reference's full VideoGLaMMForCausalLM (video branch) on CPU: true IV2 width/grid and CLIP width/336 px (hard-coded in the
+    reference's composition), reduced depths, tiny Phi-3 and tiny SAM2. Weights = oracle.weights seed 11."""
+    import tempfile
+    ocfg, scfg = M.make_cfg(**E2E_LMM, seg_token_idx=E2E_SEG), O.Sam2Cfg(**O.TINY)
+    c = ocfg.clip
+    os.environ["NUM_FRAMES"] = "4"
+    ref = H.build_videoglamm(workdir or tempfile.mkdtemp(), phi=E2E_LMM["phi"], iv2_depth=E2E_LMM["iv2"]["depth"], sam2_overrides=SAM2_TINY_OVERRIDES,
+                             clip=dict(width=c.width, mlp=c.mlp, layers=c.layers, heads=c.heads, image_size=c.image_size, patch=c.patch), seg_token_idx=E2E_SEG)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=11)
+    r = ref.load_state_dict(sd, strict=False)
+    assert not r.unexpected_keys and all(("clip_" in k or "final_clip" in k or "vision_proj" in k) for k in r.missing_keys), r
+    H.fix_clip_hidden_states(ref)
+    H.force_tokens(ref, E2E_FORCED)
+    return ref, sd, ocfg, scfg
+
+
+def ref_e2e_run(ref):
+    images, ctx, sam, ids = e2e_inputs()
+    with torch.no_grad():
+        out_ids, segs = ref.inference([images], [ctx], [sam], ids[None], None, [E2E_HW], max_new_tokens=E2E_NEW, use_sam2_video_branch=True)
+    masks = np.stack([np.stack([segs[0][t][o] for o in sorted(segs[0][t])]) for t in sorted(segs[0])])  # [T, n_obj, H, W] bool
+    return out_ids[0].numpy(), masks
+
+
+def e2e_golden():
+    """VideoGLaMMForCausalLM.inference(use_sam2_video_branch=True) VideoGLaMM.py:560-597, 770-875 of the UNMODIFIED reference: pins the
+    composition (splice, greedy generate with use_cache=False, [SEG] mask shift, text_hidden_fcs gather, per-object add_new_text, propagate,
+    threshold). Two forced [SEG] tokens -> two objects."""
+    ref, *_ = ref_videoglamm()
+    out_ids, masks = ref_e2e_run(ref)
+    np.savez_compressed(os.path.join(OUT, "e2e_tiny.npz"), output_ids=out_ids, masks=np.packbits(masks, axis=-1), mask_shape=np.array(masks.shape))
+    print("e2e_tiny", out_ids.tolist(), masks.shape, masks.mean())
+
+
 if __name__ == "__main__":
+    if "--e2e-only" in sys.argv:
+        e2e_golden()
+        sys.exit(0)
     sam2_video_golden()
     sam2_framewise_golden()
     towers_golden()
+    e2e_golden()

@@ -53,3 +53,31 @@ def test_framewise_dispatch_through_public_api():
     assert torch.equal(out_ids[0].cpu(), ids_ref)
     for t in range(2):
         assert (torch.from_numpy(segs[0][t][0]) == (ref[t][0, 0] > 0)).float().mean() > 0.98
+
+
+def test_e2e_against_reference_golden():
+    """Engine vs the fixture frozen from the UNMODIFIED reference's VideoGLaMMForCausalLM.inference (tests/golden/make_golden.py:e2e_golden):
+    true IV2 width (1408, 16x16 grid) and CLIP width/resolution (1024, 336 px), reduced depths. Token ids bit-exact; bool masks agree except
+    for pixels whose fp32 logit is within bf16 noise of 0."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as MG
+    from test_oracle_golden import _e2e_oracle, load_e2e_golden
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    want_ids, want_masks = load_e2e_golden()
+    ocfg, scfg = M.make_cfg(**MG.E2E_LMM, seg_token_idx=MG.E2E_SEG), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=11)
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**MG.E2E_LMM, seg_token_idx=MG.E2E_SEG), Sam2Config(**O.TINY))
+    images, ctx, sam, ids = MG.e2e_inputs()
+    out_ids, segs = model.inference([images.cuda()], [ctx.cuda()], [sam.cuda()], ids[None].cuda(), None, [MG.E2E_HW], max_new_tokens=MG.E2E_NEW,
+                                    use_sam2_video_branch=True, forced_tokens=MG.E2E_FORCED)
+    assert torch.equal(out_ids[0].cpu(), want_ids)
+    _, logits = _e2e_oracle()
+    T, n_obj = want_masks.shape[:2]
+    assert sorted(segs[0]) == list(range(T)) and all(sorted(segs[0][t]) == list(range(n_obj)) for t in range(T))
+    got = torch.stack([torch.stack([torch.from_numpy(segs[0][t][o]) for o in range(n_obj)]) for t in range(T)])
+    agree = (got == want_masks).float().mean().item()
+    decided = logits.abs() > 0.05 * logits.abs().max()          # pixels whose sign bf16 noise cannot flip
+    assert agree > 0.98 and torch.equal(got[decided], want_masks[decided]), agree

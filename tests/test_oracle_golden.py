@@ -69,3 +69,33 @@ def test_phi3_sliding_window_rule_is_transformers_4_41():
     assert torch.allclose(M.phi3_forward(sd, cfg.phi, x), full)           # window covers everything: j >= i - 11 for i <= 11
     cfg.phi.sliding_window = 10
     assert not torch.allclose(M.phi3_forward(sd, cfg.phi, x)[-1], full[-1])  # row 11 loses key 0
+
+
+def _e2e_oracle():
+    import sys
+    sys.path.insert(0, G)
+    import make_golden as MG
+    ocfg, scfg = M.make_cfg(**MG.E2E_LMM, seg_token_idx=MG.E2E_SEG), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=11)
+    images, ctx, sam, ids = MG.e2e_inputs()
+    with torch.no_grad():
+        out_ids, emb, _ = M.generate(sd, ocfg, ids, images, ctx, MG.E2E_NEW, forced=MG.E2E_FORCED)
+        ssd = {k[len("model.visual_model."):]: v for k, v in sd.items() if k.startswith("model.visual_model.")}
+        logits = O.run_video(ssd, scfg, sam, emb[:, None, :], MG.E2E_HW)
+    return out_ids, torch.stack([l[:, 0] for l in logits])          # ids [L], logits [T, n_obj, H, W]
+
+
+def load_e2e_golden():
+    g = np.load(os.path.join(G, "e2e_tiny.npz"))
+    shape = tuple(int(x) for x in g["mask_shape"])
+    return torch.from_numpy(g["output_ids"]), torch.from_numpy(np.unpackbits(g["masks"], axis=-1, count=shape[-1]).astype(bool).reshape(shape))
+
+
+def test_e2e_composition_matches_reference_golden():
+    """The whole path as ONE call of the unmodified reference (VideoGLaMMForCausalLM.inference, video branch, 2 forced [SEG] -> 2 objects,
+    3 frames): output ids bit-exact, every bool mask pixel identical."""
+    want_ids, want_masks = load_e2e_golden()
+    ids, logits = _e2e_oracle()
+    assert torch.equal(ids, want_ids)
+    assert tuple(logits.shape) == tuple(want_masks.shape)
+    assert torch.equal(logits > 0, want_masks)

@@ -38,3 +38,17 @@ def test_full_size_sam2_key_contract():
     rsd = ref.state_dict()
     assert set(shapes) == set(rsd)
     assert all(tuple(shapes[k]) == tuple(rsd[k].shape) for k in shapes)
+
+
+def test_e2e_inference_live_reference_equals_golden_and_oracle():
+    """Runs the reference's own VideoGLaMMForCausalLM.inference here and checks (a) the committed fixture is what it produces and
+    (b) the oracle composition reproduces it (ids bit-exact, masks identical)."""
+    import numpy as np
+    import make_golden as MG
+    from test_oracle_golden import _e2e_oracle, load_e2e_golden
+    ref, *_ = MG.ref_videoglamm()
+    out_ids, masks = MG.ref_e2e_run(ref)
+    want_ids, want_masks = load_e2e_golden()
+    assert np.array_equal(out_ids, want_ids.numpy()) and np.array_equal(masks, want_masks.numpy())
+    ids, logits = _e2e_oracle()
+    assert torch.equal(ids, want_ids) and torch.equal(logits > 0, want_masks)
