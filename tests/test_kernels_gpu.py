@@ -27,7 +27,9 @@ def _seed():
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (128, 64, 64, 64), (128, 256, 64, 256), (300, 200, 136, 0), (77, 40, 72, 64),
-                                      (1000, 1000, 1000, 256), (9, 256, 256, 0), (1664, 9216, 3072, 0), (1, 32064, 3072, 0), (4096, 4, 32, 0)])
+                                      (1000, 1000, 1000, 256), (9, 256, 256, 0), (1664, 9216, 3072, 0), (1, 32064, 3072, 0), (4096, 4, 32, 0),
+                                      (1000, 576, 136, 192), (1000, 288, 200, 96), (700, 200, 72, 192), (20000, 576, 2304, 0), (20000, 1728, 576, 0),
+                                      (40000, 288, 288, 0), (40000, 864, 288, 0)])
 def test_gemm_plain(M, N, K, bn):
     a = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
@@ -59,6 +61,19 @@ def test_gemm_glu_scale_resid_batched():
     assert rel(ops.gemm(ab, wb, out_dtype=torch.float32), ab.float() @ wb.float().transpose(1, 2)) < 1e-5
     yb = ops.gemm(a, w, out_dtype=torch.bfloat16)
     assert rel(yb, a.float() @ w.float().T) < 4e-3
+
+
+def test_gemm_n_fastest_tiles_with_epilogues():
+    """M >> N with several N tiles: N-fastest tile order + 192-column tiles (Hiera stage-3 shapes), in-place residual and GELU epilogues."""
+    a = torch.randn(20000, 2304, device=DEV).bfloat16()
+    w = (torch.randn(576, 2304, device=DEV) / 48).bfloat16()
+    bias, res = torch.randn(576, device=DEV), torch.randn(20000, 576, device=DEV)
+    want = a.float() @ w.float().T + bias + res
+    assert rel(ops.gemm(a, w, bias=bias, resid=res, out=res), want) < 1e-5
+    a2 = torch.randn(20000, 576, device=DEV).bfloat16()
+    w2 = (torch.randn(2304, 576, device=DEV) / 24).bfloat16()
+    b2 = torch.randn(2304, device=DEV)
+    assert rel(ops.gemm(a2, w2, bias=b2, act="gelu"), F.gelu(a2.float() @ w2.float().T + b2)) < 4e-3
 
 
 def test_gemm_matches_naive_device_reference():
@@ -93,7 +108,8 @@ def sdpa_ref(q, k, v, scale, causal=False, window=0):
     (2, 4, 64, 64, 64, False, 0), (1, 16, 577, 577, 64, False, 0), (1, 16, 1025, 1025, 88, False, 0), (1, 8, 300, 300, 72, False, 0),
     (1, 32, 333, 333, 96, True, 0), (1, 4, 1, 500, 96, True, 0), (1, 4, 700, 700, 96, True, 128), (2, 1, 256, 1100, 256, False, 0),
     (3, 8, 9, 4096, 16, False, 0), (3, 8, 4096, 9, 16, False, 0), (2, 8, 9, 9, 32, False, 0), (1, 2, 130, 70, 128, False, 0),
-    (1, 1, 4096, 8300, 256, False, 0), (2, 2, 300, 5000, 64, False, 0), (1, 1, 70, 2049, 96, False, 0)])  # last three: split-K over keys
+    (1, 1, 4096, 8300, 256, False, 0), (2, 2, 300, 5000, 64, False, 0), (1, 1, 70, 2049, 96, False, 0),  # these three: split-K over keys
+    (1, 32, 1696, 1696, 96, True, 2047)])  # Phi-3 prefill: the sliding window never cuts -> tcgen05 causal path
 def test_attention(B, H, Nq, Nk, D, causal, window):
     q = torch.randn(B, Nq, H, D, device=DEV).bfloat16()
     k = torch.randn(B, Nk, H, D, device=DEV).bfloat16()

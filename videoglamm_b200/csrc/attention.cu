@@ -383,6 +383,143 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
   }
 }
 
+// Version 2 (head dim <= 128): ncu showed version 1 latency-bound (256 CTAs, 10 % warps active, 25 us for 21 MB: every warp walks its keys
+// through ~20 dependent round trips of small loads). Here each block owns <= 64 keys of one head and issues ALL of its K and V bytes as
+// 16-byte cp.async copies up front (24 KB in flight per block, ~6 blocks per SM), then does QK^T, softmax and PV out of shared memory.
+// Grid (H, B, nsplit) with nsplit ~ keys / 64; partials are merged by the last block of each head (ticket counter) or a merge launch.
+constexpr int DEC2_KEYS = 64;
+__global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
+  constexpr int DMAX = 128, LDS = DMAX + 8;  // padded row (bf16 elements)
+  if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
+  __shared__ __align__(16) __nv_bfloat16 s_k[DEC2_KEYS * LDS];
+  __shared__ __align__(16) __nv_bfloat16 s_v[DEC2_KEYS * LDS];
+  __shared__ __align__(16) float s_q[DMAX];
+  __shared__ float s_p[DEC2_KEYS];
+  __shared__ float s_o[2][DMAX];
+  __shared__ float s_red[4];
+  const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __nv_bfloat16* qp = p.q + b * p.q_bs + h * p.q_hs;
+  const __nv_bfloat16* kb = p.k + b * p.k_bs + h * p.k_hs;
+  const __nv_bfloat16* vb = p.v + b * p.v_bs + h * p.v_hs;
+  int k_begin = 0;
+  if (p.window > 0) k_begin = max(0, p.Nk - 1 - p.window);
+  const int span = ((p.Nk - k_begin + p.nsplit - 1) / p.nsplit + 31) / 32 * 32;
+  const int k_lo = k_begin + blockIdx.z * span;
+  const int k_hi = min(p.Nk, k_lo + span);
+  const int chunks = p.D >> 3;  // 16-byte chunks per row
+  float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;  // thread (kh = tid / 64, pr = tid % 64) accumulates feature pair pr over its key half
+  for (int d = tid; d < DMAX; d += 128) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
+  for (int k0 = k_lo; k0 < k_hi; k0 += DEC2_KEYS) {
+    const int n = min(DEC2_KEYS, k_hi - k0);
+    __syncthreads();  // previous tile fully consumed (and s_q written)
+    const int ops = n * chunks;
+    for (int i = tid; i < 2 * ops; i += 128) {
+      const int which = i >= ops, j = which ? i - ops : i;
+      const int key = j / chunks, c = j - key * chunks;
+      const __nv_bfloat16* src = (which ? vb + static_cast<long long>(k0 + key) * p.v_rs : kb + static_cast<long long>(k0 + key) * p.k_rs) + c * 8;
+      cp_async16((which ? s_v : s_k) + key * LDS + c * 8, src, true);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    // QK^T: two threads per key (feature halves), combined with one shuffle
+    {
+      const int key = tid >> 1, half = tid & 1;
+      float acc = 0.f;
+      if (key < n) {
+        const int c_lo = half ? (chunks + 1) / 2 : 0, c_hi = half ? chunks : (chunks + 1) / 2;
+        for (int c = c_lo; c < c_hi; ++c) {
+          const uint4 kv = *reinterpret_cast<const uint4*>(s_k + key * LDS + c * 8);
+          const float4 qa = *reinterpret_cast<const float4*>(s_q + c * 8), qb = *reinterpret_cast<const float4*>(s_q + c * 8 + 4);
+          acc = fmaf(bf16_lo(kv.x), qa.x, acc); acc = fmaf(bf16_hi(kv.x), qa.y, acc);
+          acc = fmaf(bf16_lo(kv.y), qa.z, acc); acc = fmaf(bf16_hi(kv.y), qa.w, acc);
+          acc = fmaf(bf16_lo(kv.z), qb.x, acc); acc = fmaf(bf16_hi(kv.z), qb.y, acc);
+          acc = fmaf(bf16_lo(kv.w), qb.z, acc); acc = fmaf(bf16_hi(kv.w), qb.w, acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      const float sc = key < n ? acc : -INFINITY;
+      const float wm = warp_max(sc);
+      if (lane == 0) s_red[warp] = wm;
+      __syncthreads();
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3])));
+      const float pj = key < n ? __expf(sc - m_new) : 0.f;
+      if (half == 0) s_p[key] = pj;
+      const float ws = warp_sum(half == 0 ? pj : 0.f);
+      __syncthreads();  // s_red reads done, s_p written
+      if (lane == 0) s_red[warp] = ws;
+      __syncthreads();
+      const float alpha = (m_run == -INFINITY) ? 0.f : __expf(m_run - m_new);
+      l_run = l_run * alpha + (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
+      m_run = m_new;
+      o0 *= alpha;
+      o1 *= alpha;
+    }
+    // PV: thread = (key half, feature pair)
+    {
+      const int kh = tid >> 6, pr = tid & 63;
+      if (2 * pr < p.D) {
+        const int j_lo = kh * (DEC2_KEYS / 2), j_hi = min(n, j_lo + DEC2_KEYS / 2);
+#pragma unroll 8
+        for (int j = j_lo; j < j_hi; ++j) {
+          const uint32_t vv = *reinterpret_cast<const uint32_t*>(s_v + j * LDS + 2 * pr);
+          const float pj = s_p[j];
+          o0 = fmaf(pj, bf16_lo(vv), o0);
+          o1 = fmaf(pj, bf16_hi(vv), o1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int kh = tid >> 6, pr = tid & 63;
+    s_o[kh][2 * pr] = o0;
+    s_o[kh][2 * pr + 1] = o1;
+  }
+  __syncthreads();
+  if (p.nsplit > 1) {  // un-normalised partial (m, l, o[D]) for the merge
+    float* wp = p.ws + ((static_cast<long long>(b) * gridDim.x + h) * p.nsplit + blockIdx.z) * (DMAX + 2);
+    if (tid == 0) {
+      wp[0] = m_run;
+      wp[1] = l_run;
+    }
+    for (int d = tid; d < p.D; d += 128) wp[2 + d] = s_o[0][d] + s_o[1][d];
+    if (p.counters == nullptr) return;  // separate merge kernel follows
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int prev = atomicAdd(p.counters + b * gridDim.x + h, 1);
+      s_last = (prev == p.nsplit - 1);
+      if (s_last) p.counters[b * gridDim.x + h] = 0;  // self-cleaning for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* base = p.ws + (static_cast<long long>(b) * gridDim.x + h) * p.nsplit * (DMAX + 2);
+    // weights of the partials: lane s < nsplit of warp 0 owns partial s (nsplit <= 32), published through shared memory
+    if (warp == 0) {
+      const float m_s = lane < p.nsplit ? __ldcg(base + lane * (DMAX + 2)) : -INFINITY;
+      const float mm = warp_max(m_s);
+      const float w_s = (m_s == -INFINITY) ? 0.f : __expf(m_s - mm);
+      const float ll = warp_sum(lane < p.nsplit ? __ldcg(base + lane * (DMAX + 2) + 1) * w_s : 0.f);
+      s_p[lane] = w_s;
+      if (lane == 0) s_red[0] = ll;
+    }
+    __syncthreads();
+    const float ll = s_red[0];
+    __nv_bfloat16* opm = p.o + b * p.o_bs + h * p.o_hs;
+    for (int d = tid; d < p.D; d += 128) {
+      float acc = 0.f;
+      for (int sidx = 0; sidx < p.nsplit; ++sidx) acc = fmaf(__ldcg(base + sidx * (DMAX + 2) + 2 + d), s_p[sidx], acc);
+      opm[d] = __float2bfloat16(ll > 0.f ? acc / ll : 0.f);
+    }
+    return;
+  }
+  __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs;
+  for (int d = tid; d < p.D; d += 128) op[d] = __float2bfloat16(l_run > 0.f ? (s_o[0][d] + s_o[1][d]) / l_run : 0.f);
+}
+
 template <int DMAX>
 __global__ void attn_decode_merge_kernel(const AttnParams p) {
   const int h = blockIdx.x, b = blockIdx.y;
@@ -500,8 +637,9 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
     const int dmax = a->D <= 128 ? 128 : 256;
     int nsplit = 1;
     if (a->workspace != nullptr) {
-      nsplit = (a->Nk + 255) / 256;
-      if (nsplit > 16) nsplit = 16;
+      nsplit = dmax == 128 ? (a->Nk + DEC2_KEYS - 1) / DEC2_KEYS : (a->Nk + 255) / 256;
+      const int cap = dmax == 128 ? 32 : 16;
+      if (nsplit > cap) nsplit = cap;
       const long long need = static_cast<long long>(a->B) * a->H * nsplit * (dmax + 2) * 4 + (a->ws_has_counters ? static_cast<long long>(a->B) * a->H * 4 : 0);
       if (need > a->workspace_bytes) nsplit = 1;
     }
@@ -511,7 +649,7 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       p.counters = reinterpret_cast<int*>(static_cast<char*>(a->workspace) + a->workspace_bytes - static_cast<long long>(a->B) * a->H * 4);
     dim3 grid(a->H, a->B, nsplit);
     if (dmax == 128)
-      attn_decode_kernel<128><<<grid, 128, 0, s>>>(p);
+      attn_decode2_kernel<<<grid, 128, 0, s>>>(p);
     else
       attn_decode_kernel<256><<<grid, 128, 0, s>>>(p);
     count_launch();
@@ -527,7 +665,9 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   }
   if (!a->force_legacy) {  // tcgen05 path (large dense problems); falls through to the mma.sync kernel when not applicable
     int ns = 1, dpm = 128;
-    const int rc = attention_tc_try(a, s, &ns, &dpm);
+    VgAttention at = *a;
+    if (at.window > 0 && at.causal && at.Nk <= at.window + 1) at.window = 0;  // band j >= i - window never cuts anything: plain causal
+    const int rc = attention_tc_try(&at, s, &ns, &dpm);
     if (rc == VG_OK) {
       if (ns > 1) {
         p.ws = static_cast<float*>(a->workspace);

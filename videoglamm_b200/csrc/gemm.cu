@@ -20,11 +20,12 @@ constexpr int GEMM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spa
 
 template <int BN>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN >= 96 ? 6 : 8));
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulator stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages; 128/256/512 are powers of two
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages; allocations are powers of two (128/256/512)
   static constexpr int STAGING_BYTES = 8 * 4096;             // per epilogue warp: one 32-row TMA-store box (<= 128 B per row)
   static constexpr int VEC_BYTES = 2 /*acc stages*/ * BN * 4;  // bias of the tile being drained
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256 /*barriers*/;  // base is 1024-aligned (checked)
@@ -33,6 +34,7 @@ struct GemmCfg {
 struct GemmParams {
   int M, N, K, batch;
   int tiles_m, tiles_n;
+  int n_fastest;  // tile order: N tiles of one M stripe adjacent (A is the big operand) or M tiles of one N stripe adjacent (W is)
   void* C;
   long long ldc, strideC;
   int out_f32;
@@ -49,17 +51,29 @@ struct GemmParams {
   int tma_reduce;     // residual aliases C: TMA reduce-add instead of load + add + store
 };
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, below fp32 resolution of the GELU output): ~15 instructions, branch-free,
-// instead of libdevice erff (~100 with divergence), which made GELU epilogues the bottleneck of the MLP GEMMs.
-__device__ __forceinline__ float fast_erf(float x) {
+// Activations for the epilogues. ncu (profiles/r01_ncu_targets_d.md) showed the small-K GEMMs issue-bound in the epilogue warps at ~35
+// instructions per output element, ~25 of them the activation (libdevice-style __fdividef/__expf range handling). These forms are branch-free
+// and use the raw MUFU approximations (rcp.approx / ex2.approx, ~1-2 ulp): GELU = 11 ALU + 2 MUFU, SiLU/QuickGELU/sigmoid = 3 ALU + 2 MUFU.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// exact-erf GELU x*Phi(x) with erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): for z = |x|/sqrt(2), t = 1/(1 + p z),
+// Phi(|x|) = 1 - 0.5 t (a1 + t(a2 + t(a3 + t(a4 + t a5)))) exp(-x^2/2) =: 1 - h, and x*Phi(x) = max(x,0) - |x| h for either sign.
+__device__ __forceinline__ float gelu_erf(float x) {
   const float ax = fabsf(x);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float y = 1.0f - poly * t * __expf(-ax * ax);
-  return copysignf(y, x);
+  const float t = rcp_approx(fmaf(ax, 0.2316418882f, 1.0f));
+  float q = fmaf(t, 0.5307027145f, -0.7265760135f);
+  q = fmaf(q, t, 0.7107068705f);
+  q = fmaf(q, t, -0.142248368f);
+  q = fmaf(q, t, 0.127414796f);
+  const float e = ex2_approx((x * -0.7213475204f) * x);
+  const float h = q * (t * e);
+  return fmaf(-ax, h, fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ float sigmoid_scaled(float x, float neg_scale_log2e) {  // 1 / (1 + exp(-scale * x))
+  return rcp_approx(1.0f + ex2_approx(x * neg_scale_log2e));
 }
 
 template <int N>
@@ -68,11 +82,11 @@ __device__ __forceinline__ void apply_act_vec(float (&v)[32], int act) {
   switch (act) {
     case VG_ACT_GELU:
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = 0.5f * v[j] * (1.0f + fast_erf(v[j] * 0.70710678118654752f));
+      for (int j = 0; j < N; ++j) v[j] = gelu_erf(v[j]);
       break;
     case VG_ACT_QUICKGELU:
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-1.702f * v[j]));
+      for (int j = 0; j < N; ++j) v[j] *= sigmoid_scaled(v[j], -2.4554669596f);
       break;
     case VG_ACT_RELU:
 #pragma unroll
@@ -80,11 +94,11 @@ __device__ __forceinline__ void apply_act_vec(float (&v)[32], int act) {
       break;
     case VG_ACT_SILU:
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
+      for (int j = 0; j < N; ++j) v[j] *= sigmoid_scaled(v[j], -1.4426950409f);
       break;
     case VG_ACT_SIGMOID:
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = __fdividef(1.0f, 1.0f + __expf(-v[j]));
+      for (int j = 0; j < N; ++j) v[j] = sigmoid_scaled(v[j], -1.4426950409f);
       break;
     default: break;
   }
@@ -92,11 +106,11 @@ __device__ __forceinline__ void apply_act_vec(float (&v)[32], int act) {
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
-    case VG_ACT_GELU: return 0.5f * x * (1.0f + fast_erf(x * 0.70710678118654752f));
-    case VG_ACT_QUICKGELU: return x / (1.0f + __expf(-1.702f * x));
+    case VG_ACT_GELU: return gelu_erf(x);
+    case VG_ACT_QUICKGELU: return x * sigmoid_scaled(x, -2.4554669596f);
     case VG_ACT_RELU: return fmaxf(x, 0.0f);
-    case VG_ACT_SILU: return x / (1.0f + __expf(-x));
-    case VG_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-x));
+    case VG_ACT_SILU: return x * sigmoid_scaled(x, -1.4426950409f);
+    case VG_ACT_SIGMOID: return sigmoid_scaled(x, -1.4426950409f);
     default: return x;
   }
 }
@@ -162,8 +176,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = t / tiles_per_batch;
         const int r = t - b * tiles_per_batch;
-        const int n_blk = r / p.tiles_m;
-        const int m_blk = r - n_blk * p.tiles_m;
+        const int n_blk = p.n_fastest ? r % p.tiles_n : r / p.tiles_m;
+        const int m_blk = p.n_fastest ? r / p.tiles_n : r - n_blk * p.tiles_m;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -187,7 +201,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -233,8 +247,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
-      const int n_blk = r / p.tiles_m;
-      const int m_blk = r - n_blk * p.tiles_m;
+      const int n_blk = p.n_fastest ? r % p.tiles_n : r / p.tiles_m;
+      const int m_blk = p.n_fastest ? r / p.tiles_n : r - n_blk * p.tiles_m;
       // stage the tile's bias in shared memory BEFORE waiting for the accumulator (latency overlaps the MMA main loop)
       float* s_bias = s_vec + acc * BN;
       if (p.bias != nullptr) {
@@ -249,7 +263,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_after();
       const int row = m_blk * BLOCK_M + ew * 32 + lane;
       const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::ACC_STRIDE;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = n_blk * BN + c * 32;
@@ -750,6 +764,9 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   GemmParams p = to_params(g);
   p.tiles_m = (g->M + BLOCK_M - 1) / BLOCK_M;
   p.tiles_n = (g->N + BN - 1) / BN;
+  // Tile order: the operand that does NOT fit the concurrent working set should be swept once. A (M x K) bigger than W (N x K): the N
+  // tiles of one M stripe are adjacent, so A is read from HBM once and W stays in L2 (ncu: fc2 32768x576x2304 read 501 MB instead of 226).
+  p.n_fastest = (static_cast<long long>(g->M) * g->batch > g->N && p.tiles_n > 1) ? 1 : 0;
   // Output path: bulk tensor stores need a 16-byte aligned base and 16-byte multiple strides. A residual that aliases the output
   // (the in-place residual-stream update every transformer block does) becomes a TMA reduce-add; any other residual is added in registers.
   const int esz = g->out_dtype == VG_F32 ? 4 : 2;
@@ -806,11 +823,28 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
     else
       bn = (g->N > 64 && g->N % 128 == 0 && t128 * 2 > num_sms()) ? 128 : 64;
   }
+  if (bn == 256 && g->force_block_n == 0) {
+    // N not a multiple of 256 (Hiera widths are multiples of 144): 192- or 96-column tiles waste fewer MMA columns. Cost model: waves x
+    // (tile columns + a fixed per-tile overhead of ~32 columns); ties keep the wider tile (fewer A re-reads from shared memory).
+    const long long tm = (g->M + BLOCK_M - 1) / BLOCK_M;
+    double best = 1e30;
+    for (int cand : {256, 192, 96}) {
+      if (cand == 96 && (g->N % 96 != 0 || g->N % 128 == 0)) continue;
+      const long long tiles = tm * ((g->N + cand - 1) / cand) * g->batch;
+      const double cost = static_cast<double>((tiles + num_sms() - 1) / num_sms()) * (cand + 32);
+      if (cost < best * 0.97) {
+        best = cost;
+        bn = cand;
+      }
+    }
+  }
   switch (bn) {
     case 256: return launch_gemm<256>(g, s);
+    case 192: return launch_gemm<192>(g, s);
     case 128: return launch_gemm<128>(g, s);
+    case 96: return launch_gemm<96>(g, s);
     case 64: return launch_gemm<64>(g, s);
-    default: return set_error(VG_EINVAL, "vg_gemm: force_block_n must be 0/64/128/256");
+    default: return set_error(VG_EINVAL, "vg_gemm: force_block_n must be 0/64/96/128/192/256");
   }
 }
 

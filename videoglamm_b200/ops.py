@@ -165,7 +165,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         assert Nq == 1 and decode_ws.dtype == torch.float32 and decode_ws.is_cuda
         a.workspace, a.workspace_bytes, a.ws_has_counters = decode_ws.data_ptr(), decode_ws.numel() * 4, 1
     elif Nq == 1 and q_win is None and Nk >= 768:  # decode: split-K scratch
-        ws = torch.empty((B * H * 16 * (max(D, 128) + 130),), device=q.device, dtype=torch.float32)
+        ws = torch.empty((B * H * 32 * (max(D, 128) + 130),), device=q.device, dtype=torch.float32)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     L.check(L.lib().vg_attention(C.byref(a), _stream()), "vg_attention")
     return out
@@ -333,8 +333,8 @@ def launch_count_add(n: int) -> None:
 
 
 def decode_workspace(B: int, H: int, D: int, device) -> torch.Tensor:
-    """Zero-initialised scratch for single-query attention with in-kernel split-K merge (16 partials per head + B*H ticket counters)."""
-    return torch.zeros((B * H * 16 * (max(D, 128) + 130) + B * H,), device=device, dtype=torch.float32)
+    """Zero-initialised scratch for single-query attention with in-kernel split-K merge (up to 32 partials per head + B*H ticket counters)."""
+    return torch.zeros((B * H * 32 * (max(D, 128) + 130) + B * H,), device=device, dtype=torch.float32)
 
 
 def rope_kv_append_(qkv: torch.Tensor, cache: torch.Tensor, pos_dev: torch.Tensor, n_heads: int, head_dim: int, theta: float) -> None:
