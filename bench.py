@@ -186,11 +186,14 @@ def run_engine(args):
     if rank == 0 and os.environ.get("VG_GEMM_SHAPES"):
         for row in prof["top_shapes"]:
             print("gemm shape", row, file=sys.stderr)
+    dec = time_decode_step(model, L) if rank == 0 else None
+    mdec = time_mask_decoder(model) if rank == 0 else None
     cpu = cpu_baseline_sample(L) if (rank == 0 and not args.no_cpu_baseline) else None
     if rank == 0:
         tf_peak, hbm_peak, src = _peaks()
         n_clips = args.steps * world
-        ach = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof["ms"] > 0 else 0.0
+        tp = prof["tensor"]
+        ach = tp["flops"] / (tp["ms"] * 1e-3) / 1e12 if tp["ms"] > 0 else 0.0
         h2d = sum(t.numel() * t.element_size() for t in host)
         d2h = T_SAM * VIDEO_HW[0] * VIDEO_HW[1] + (host[3].numel() + N_NEW) * 8
         line = {
@@ -205,10 +208,19 @@ def run_engine(args):
                        "latency_ms_single_clip": latency_ms},
             "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (all GEMM launches of one clip)", "achieved": ach, "peak": tf_peak,
-                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": f"{src} bf16_tflops_sustained",
-                         "launches": prof["n"], "gemm_ms_per_clip": prof["ms"], "gemm_share_of_step": prof["ms"] / (ms / args.steps), "note": "per-launch CUDA events on an extra eager (non-graph) step",
+            "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip, M > 8)", "achieved": ach, "peak": tf_peak,
+                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": NCU_TRAFFIC, "peak_source": f"{src} bf16_tflops_sustained",
+                         "launches": tp["n"], "gemm_ms_per_clip": tp["ms"], "gemm_share_of_step": tp["ms"] / (ms / args.steps),
+                         "note": "algorithmic 2MNK per launch / per-launch CUDA events on an extra eager (non-graph) step; traffic = ncu dram bytes of the "
+                                 "largest-share shape (profiles/r01_ncu_targets_*.md)",
                          "whole_clip_tflops": clip_flops(L) / (ms / args.steps * 1e-3) / 1e12},
+            "roofline_decode": {"bound": "hbm", "kernel": "one KV-cached Phi-3 decode step (graph replay: 4 weight-streaming GEMVs + RoPE/append + "
+                                "single-query attention per layer, lm_head, argmax)", "achieved": dec["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                                "frac": dec["gbs"] / hbm_peak, "bytes_per_step": dec["bytes"], "ms_per_step": dec["ms"], "peak_source": f"{src} hbm_gbs"},
+            "mask_decoder": {"kernel_group": "PromptEncoder dense + TwoWayTransformer + upscaling + hypernetwork MLPs + IoU/object heads (graph replay, B=1 object)",
+                             "ms_per_frame": mdec["ms"], "launches": mdec["launches"], "algorithmic_bytes": mdec["bytes"], "achieved_gbs": mdec["gbs"],
+                             "hbm_frac": mdec["gbs"] / hbm_peak, "algorithmic_gflop": mdec["gflop"], "achieved_tflops": mdec["tflops"],
+                             "tensor_frac": mdec["tflops"] / tf_peak},
             "clocks": clocks,
         }
         if cpu:
@@ -216,6 +228,71 @@ def run_engine(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest-share tensor GEMM shape (Hiera stage-3 fc2, 32768 x 576 x 2304,
+# in-place fp32 residual) from the committed `ncu --set full` capture; algorithmic bytes of that launch: 151.0 (A) + 2.7 (W) + 75.5 (C read) +
+# 75.5 (C write) = 304.7 MB. Updated by hand when the capture is retaken (profiles/).
+NCU_TRAFFIC = {"kernel": "gemm_tcgen05_kernel 32768x576x2304 +resid", "dram_bytes": 571.7e6, "algorithmic_bytes": 304.7e6, "source": "profiles/r01_ncu_targets_d.md row 1"}
+
+
+def time_decode_step(model, L: int, reps: int = 8) -> dict:
+    """HBM roofline of the decode phase: replays the captured decode-step graph and divides the bytes one step must stream (every Phi-3
+    layer weight + lm_head once, K/V rows of the L cached positions) by its duration."""
+    lmm = model.lmm
+    ph = lmm.cfg.phi
+    kv_bound = min(lmm.kv[0].shape[0], (L + N_NEW + 511) // 512 * 512)
+    lmm.dec_pos.fill_(L)
+    lmm.dec_nk.fill_(L + 1)
+    lmm.dec_tok.fill_(5)
+    step = lambda: lmm.g_decode((kv_bound,), lambda: lmm._decode_step(kv_bound), mutable_state=(lmm.dec_tok, lmm.dec_pos, lmm.dec_nk))
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    wbytes = ph.layers * 2 * (3 * ph.hidden * ph.hidden + ph.hidden * ph.hidden + 2 * ph.inter * ph.hidden + ph.inter * ph.hidden) + 2 * ph.vocab * ph.hidden
+    kvbytes = ph.layers * 2 * (L + reps // 2) * ph.hidden * 2
+    return {"ms": ms, "bytes": wbytes + kvbytes, "gbs": (wbytes + kvbytes) / (ms * 1e-3) / 1e9}
+
+
+def time_mask_decoder(model, reps: int = 20) -> dict:
+    """BASELINE.json metric (ii): the SAM2 mask-decoder kernel group for one (frame, 1 object), captured in a CUDA graph and replayed.
+    Algorithmic traffic per SURVEY.md section 8(d): image_embed 2.10 + dense PE 2.10 + feat_s0 4.19 + feat_s1 2.10 MB + outputs 0.79 MB
+    (weights 8.43 MB stay L2-resident across frames and are not counted); 3.64 GFLOP per object."""
+    from videoglamm_b200 import ops
+    from videoglamm_b200.graphs import GraphedStage
+    sam = model.sam
+    cfg = sam.cfg
+    dev = sam.dev
+    g = torch.Generator(device="cpu").manual_seed(1)
+    HW, C = sam.HW, cfg.d_model
+    pix = torch.randn(HW, C, generator=g).to(dev)
+    s0 = torch.randn(16 * HW, C // 8, generator=g).to(dev).bfloat16()
+    s1 = torch.randn(4 * HW, C // 4, generator=g).to(dev).bfloat16()
+    sparse = torch.randn(1, 3, C, generator=g).to(dev)
+    stage = GraphedStage("mask_decoder_bench")
+    run = lambda: stage(("md",), lambda pix, s0, s1, sparse: sam.mask_decoder(pix, s0, s1, sparse)[0], pix=pix, s0=s0, s1=s1, sparse=sparse)
+    n0 = ops.launch_count()
+    run()
+    run()
+    torch.cuda.synchronize()
+    n1 = ops.launch_count()
+    run()
+    launches = ops.launch_count() - n1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = (2.10 + 2.10 + 4.19 + 2.10 + 0.79) * 1e6
+    return {"ms": ms, "launches": launches, "bytes": nbytes, "gbs": nbytes / (ms * 1e-3) / 1e9, "gflop": 3.64, "tflops": 3.64e9 / (ms * 1e-3) / 1e12}
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm (oracle port)

@@ -789,6 +789,9 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
 
 }  // namespace vg
 
+namespace vg {
+int gemv_ring_try(const VgGemm* g, cudaStream_t s);  // gemv_ring.cu
+}
 using namespace vg;
 
 extern "C" int vg_gemm(const VgGemm* g, void* stream) {
@@ -804,6 +807,10 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
     GemmParams p = to_params(g);
     const bool af32 = g->a_dtype == VG_F32;
     if (af32 && ((g->lda % 4) || (reinterpret_cast<uintptr_t>(g->A) & 15))) return set_error(VG_EINVAL, "vg_gemm: fp32 A must be 16B aligned");
+    if (g->M == 1) {
+      const int rrc = gemv_ring_try(g, s);  // persistent TMA-ring kernel (decode-sized problems); VG_ENOSUP -> generic skinny kernel
+      if (rrc != VG_ENOSUP) return rrc;
+    }
     if (g->M == 1) { if (af32) launch_gemv<1, true>(g, p, s); else launch_gemv<1, false>(g, p, s); }
     else if (g->M <= 2) { if (af32) launch_gemv<2, true>(g, p, s); else launch_gemv<2, false>(g, p, s); }
     else if (g->M <= 4) { if (af32) launch_gemv<4, true>(g, p, s); else launch_gemv<4, false>(g, p, s); }

@@ -108,7 +108,12 @@ def gemm_profile(enable: bool):
         a[1] += ms
         a[2] += fl
     top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:40]
+    tensor = [(k, v) for k, v in by_shape.items() if k[0] > 8]      # tcgen05 kernel; M <= 8 takes the weight-streaming (HBM-bound) kernel
+    skinny = [(k, v) for k, v in by_shape.items() if k[0] <= 8]
     return {"n": len(rec), "ms": sum(v[1] for v in by_shape.values()), "flops": sum(v[2] for v in by_shape.values()),
+            "tensor": {"n": sum(v[0] for _, v in tensor), "ms": sum(v[1] for _, v in tensor), "flops": sum(v[2] for _, v in tensor)},
+            "skinny": {"n": sum(v[0] for _, v in skinny), "ms": sum(v[1] for _, v in skinny),
+                       "weight_bytes": sum(v[0] * 2.0 * k[1] * k[2] * k[3] for k, v in skinny)},
             "top_shapes": [{"MNKB": list(k), "launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)} for k, v in top]}
 
 
