@@ -5,6 +5,7 @@
 // Hiera windows are addressed by index arithmetic on the un-partitioned [H,W] token grid (no window_partition copy).
 // Bring-up tensor path: mma.sync m16n8k16 bf16 with fp32 accumulate, cp.async double-buffered K/V tiles.
 #include "common.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vg {
@@ -390,6 +391,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
 constexpr int DEC2_KEYS = 64;
 __global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
   constexpr int DMAX = 128, LDS = DMAX + 8;  // padded row (bf16 elements)
+  pdl_launch_dependents();
+  pdl_wait();  // q / the newest cache row come from the preceding kernels; nk_dev is advanced by the previous decode step
   if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
   __shared__ __align__(16) __nv_bfloat16 s_k[DEC2_KEYS * LDS];
   __shared__ __align__(16) __nv_bfloat16 s_v[DEC2_KEYS * LDS];
@@ -649,7 +652,10 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       p.counters = reinterpret_cast<int*>(static_cast<char*>(a->workspace) + a->workspace_bytes - static_cast<long long>(a->B) * a->H * 4);
     dim3 grid(a->H, a->B, nsplit);
     if (dmax == 128)
-      attn_decode2_kernel<<<grid, 128, 0, s>>>(p);
+    {
+      const cudaError_t e = launch_pdl(attn_decode2_kernel, grid, dim3(128), 0, s, p);
+      if (e != cudaSuccess) return set_error(VG_ECUDA, "attn_decode2 launch: %s", cudaGetErrorString(e));
+    }
     else
       attn_decode_kernel<256><<<grid, 128, 0, s>>>(p);
     count_launch();

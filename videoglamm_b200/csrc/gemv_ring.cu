@@ -13,6 +13,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vg {
@@ -35,8 +36,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float act_ring(float x, int act) {
   switch (act) {
@@ -220,7 +219,6 @@ static int env_flag(const char* name, int dflt) {
 // Returns VG_OK when the ring kernel handled the call, VG_ENOSUP when the caller should use the generic skinny kernel.
 int gemv_ring_try(const VgGemm* g, cudaStream_t s) {
   static const int enabled = env_flag("VG_GEMV_RING", 1);
-  static const int use_pdl = env_flag("VG_PDL", 1);
   if (!enabled || g->M != 1 || g->batch != 1 || (g->K % 8) || g->K < 1024) return VG_ENOSUP;
   const int n_out = g->glu ? g->N / 2 : g->N;
   if (n_out < 1024 || (g->glu && (g->N % 32))) return VG_ENOSUP;
@@ -259,17 +257,7 @@ int gemv_ring_try(const VgGemm* g, cudaStream_t s) {
     if (e != cudaSuccess) return set_error(VG_ECUDA, "gemv_ring smem attr: %s", cudaGetErrorString(e));
     attr_done[ki] = true;
   }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(RING_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  cudaError_t e = launch_pdl(kern, dim3(grid), dim3(RING_THREADS), smem, s, p);
   if (e != cudaSuccess) return set_error(VG_ECUDA, "gemv_ring launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("gemv_ring_kernel");

@@ -1,6 +1,7 @@
 // Normalisation, elementwise, pooling, resampling, small convolutions, RoPE, embedding, argmax.
 // All HBM-bound: coalesced channel-contiguous access, fp32 math, dtype (bf16/fp32) chosen at run time.
 #include "common.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vg {
@@ -450,6 +451,8 @@ __global__ void row_scatter_kernel(const __nv_bfloat16* src, __nv_bfloat16* cach
 }
 
 __global__ void rope_kv_append_kernel(__nv_bfloat16* qkv, __nv_bfloat16* cache, long long ld, const int* pos_dev, int H, int hd, float theta) {
+  pdl_launch_dependents();
+  pdl_wait();  // qkv comes from the preceding GEMV; pos_dev is advanced by the previous decode step
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int half = hd / 2, D = H * hd;
   const int pos = *pos_dev;
@@ -706,8 +709,9 @@ extern "C" int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, con
                                  void* stream) {
   if (!qkv || !cache || !pos_dev || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_kv_append: bad argument");
   const int n = n_heads * head_dim * 2;  // q+k pairs (H*hd) + v elements (H*hd)
-  rope_kv_append_kernel<<<blocks_for(n, 256), 256, 0, STREAM>>>(static_cast<__nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(cache), ld_cache, pos_dev,
-                                                                n_heads, head_dim, theta);
+  const cudaError_t e = launch_pdl(rope_kv_append_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, STREAM, static_cast<__nv_bfloat16*>(qkv),
+                                   static_cast<__nv_bfloat16*>(cache), ld_cache, pos_dev, n_heads, head_dim, theta);
+  if (e != cudaSuccess) return set_error(VG_ECUDA, "rope_kv_append launch: %s", cudaGetErrorString(e));
   count_launch();
   return check_launch("rope_kv_append_kernel");
 }
