@@ -37,6 +37,8 @@ __device__ __forceinline__ long long tok_row(int b, int t, int win, int gridw, i
 
 template <int DP>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   constexpr int BM = 64, BN = 64, LD = DP + 8, CH = DP / 8;  // CH: 16-byte chunks per row
   constexpr bool Q_IN_REGS = DP <= 128;
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
 // warp-level online softmax, then lane-per-feature PV with the probabilities staged in shared memory; warps merged at the end.
 template <int DMAX>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
   constexpr int NW = 4, PPL = DMAX / 64;  // warps per block; bf16x2 feature pairs per lane in the PV phase
   __shared__ float s_q[DMAX];
@@ -525,6 +529,8 @@ __global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
 
 template <int DMAX>
 __global__ void attn_decode_merge_kernel(const AttnParams p) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int h = blockIdx.x, b = blockIdx.y;
   const float* wp = p.ws + (static_cast<long long>(b) * gridDim.x + h) * p.nsplit * (DMAX + 2);
   float m_all = -INFINITY;
@@ -548,6 +554,8 @@ __global__ void attn_decode_merge_kernel(const AttnParams p) {
 // one warp per (b, h, row): combine nsplit partials
 template <int DP>
 __global__ void flash_attn_merge_kernel(const AttnParams p) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long gw = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
@@ -596,11 +604,11 @@ static int launch_attn(AttnParams p, cudaStream_t s, void* workspace, long long 
     attr = true;
   }
   dim3 grid(q_tiles * p.nsplit, p.H, p.B);
-  flash_attn_kernel<DP><<<grid, 128, smem, s>>>(p);
+  launch_k(flash_attn_kernel<DP>, dim3(grid), dim3(128), smem, s, p);
   count_launch();
   if (p.nsplit > 1) {
     const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
-    flash_attn_merge_kernel<DP><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+    launch_k(flash_attn_merge_kernel<DP>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, p);
     count_launch();
   }
   return check_launch("flash_attn_kernel");
@@ -657,14 +665,14 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       if (e != cudaSuccess) return set_error(VG_ECUDA, "attn_decode2 launch: %s", cudaGetErrorString(e));
     }
     else
-      attn_decode_kernel<256><<<grid, 128, 0, s>>>(p);
+      launch_k(attn_decode_kernel<256>, dim3(grid), dim3(128), 0, s, p);
     count_launch();
     if (nsplit > 1 && p.counters == nullptr) {
       dim3 mg(a->H, a->B);
       if (dmax == 128)
-        attn_decode_merge_kernel<128><<<mg, 128, 0, s>>>(p);
+        launch_k(attn_decode_merge_kernel<128>, dim3(mg), dim3(128), 0, s, p);
       else
-        attn_decode_merge_kernel<256><<<mg, 128, 0, s>>>(p);
+        launch_k(attn_decode_merge_kernel<256>, dim3(mg), dim3(128), 0, s, p);
       count_launch();
     }
     return check_launch("attn_decode_kernel");
@@ -680,9 +688,9 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
         p.nsplit = ns;
         const long long rows = static_cast<long long>(p.B) * p.H * p.Nq;
         if (dpm == 128)
-          flash_attn_merge_kernel<128><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+          launch_k(flash_attn_merge_kernel<128>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, p);
         else
-          flash_attn_merge_kernel<256><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, s>>>(p);
+          launch_k(flash_attn_merge_kernel<256>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, s, p);
         count_launch();
         return check_launch("flash_attn_merge_kernel");
       }

@@ -11,6 +11,7 @@
 #include <unordered_map>
 
 #include "common.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vg {
@@ -85,6 +86,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // q/k/v are the predecessor's outputs; the prologue above overlapped its tail
   const uint32_t tO = tmem_base;         // columns [0, Dp)
   const uint32_t tS = tmem_base + 256;   // columns [256, 256 + BN)
 
@@ -333,7 +336,7 @@ static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
   }
   const int q_tiles = (a->Nq + 127) / 128;
   dim3 grid(q_tiles * p.nsplit, a->H, a->B);
-  flash_attn_tc_kernel<BN><<<grid, 256, smem, s>>>(tq, tk, tv, p);
+  launch_k(flash_attn_tc_kernel<BN>, dim3(grid), dim3(256), smem, s, tq, tk, tv, p);
   count_launch();
   return check_launch("flash_attn_tc_kernel");
 }

@@ -9,6 +9,7 @@
 #include <unordered_map>
 
 #include "common.h"
+#include "pdl.cuh"
 #include "ptx.cuh"
 
 namespace vg {
@@ -159,6 +160,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the predecessor's tail;
+  // operands, residual and output belong to it from here on.
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int num_k = (p.K + BLOCK_K - 1) / BLOCK_K;
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
@@ -429,6 +434,8 @@ template <int MR, int WPC, int U, bool AF32>
 // time) is fused: the sum of squares is accumulated from the same A loads the dot product needs.
 __global__ void __launch_bounds__(256) gemv_kernel(const void* __restrict__ Av, long long lda, const __nv_bfloat16* __restrict__ B, long long ldb,
                                                    const GemmParams p, float rms_eps) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   __shared__ float s_part[8][3 * MR];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_out = p.glu ? p.N / 2 : p.N;
@@ -557,7 +564,7 @@ static void launch_gemv(const VgGemm* g, const GemmParams& p, cudaStream_t s) {
   const bool split = n_out < 6144 && g->K >= 2048;
   const unsigned blocks = split ? (static_cast<unsigned>(n_out) * 4 + 7) / 8 : (static_cast<unsigned>(n_out) + 7) / 8;
   const int u = MR > 2 ? 2 : gemv_variant();
-#define VG_GEMV_LAUNCH(WPC, UU) gemv_kernel<MR, WPC, UU, AF32><<<blocks, 256, 0, s>>>(g->A, g->lda, B, g->ldb, p, g->a_rms_eps)
+#define VG_GEMV_LAUNCH(WPC, UU) launch_k(gemv_kernel<MR, WPC, UU, AF32>, dim3(blocks), dim3(256), 0, s, g->A, g->lda, B, g->ldb, p, g->a_rms_eps)
   if (split) {
     if (u >= 8) VG_GEMV_LAUNCH(4, 8); else if (u >= 4) VG_GEMV_LAUNCH(4, 4); else VG_GEMV_LAUNCH(4, 2);
   } else {
@@ -569,6 +576,8 @@ static void launch_gemv(const VgGemm* g, const GemmParams& p, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------- naive reference
 __global__ void gemm_naive_kernel(const __nv_bfloat16* A, long long lda, long long sA, const __nv_bfloat16* B, long long ldb,
                                   long long sB, GemmParams p) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int n_out = p.glu ? p.N / 2 : p.N;
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const long long per_batch = static_cast<long long>(p.M) * n_out;
@@ -782,7 +791,7 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   }
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * g->batch;
   const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  gemm_tcgen05_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  launch_k(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tcgen05_kernel");
 }

@@ -24,6 +24,8 @@ static inline unsigned blocks_for(long long n, int threads) { return static_cast
 template <int MAXV>
 __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, const float* w, const float* b,
                             int rows, int cols, float eps, int rms) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -61,6 +63,8 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
 template <int MAXC>
 __global__ void norm_vec_kernel(const float* __restrict__ x, long long ldx, void* y, int ydt, long long ldy, const float* __restrict__ w,
                                 const float* __restrict__ b, int rows, int cols, float eps, int rms) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -107,6 +111,8 @@ __global__ void norm_vec_kernel(const float* __restrict__ x, long long ldx, void
 template <int MAXV>
 __global__ void __launch_bounds__(256) norm_block_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, const float* w,
                                                          const float* b, int cols, float eps, int rms) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   __shared__ float red[8];
   const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const long long xo = static_cast<long long>(row) * ldx, yo = static_cast<long long>(row) * ldy;
@@ -152,6 +158,8 @@ __global__ void __launch_bounds__(256) norm_block_kernel(const void* x, int xdt,
 // ------------------------------------------------------------------------------------------------ add / cast
 __global__ void add_kernel(const void* a, int adt, long long lda, int a_rows, const void* b, int bdt, long long ldb, int b_rows, float alpha, void* out,
                            int odt, long long ldo, long long rows, int cols) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= rows * cols) return;
   const long long r = i / cols;
@@ -162,6 +170,8 @@ __global__ void add_kernel(const void* a, int adt, long long lda, int a_rows, co
 }
 
 __global__ void pool2x2_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, int n, int h, int w, int c, int is_max) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int oh = h / 2, ow = w / 2;
   if (i >= static_cast<long long>(n) * oh * ow * c) return;
@@ -179,6 +189,8 @@ __global__ void pool2x2_kernel(const void* x, int xdt, long long ldx, void* y, i
 }
 
 __global__ void upsample2x_add_kernel(const float* lat, const float* top, float* out, int n, int h, int w, int c) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int H = 2 * h, W = 2 * w;
   if (i >= static_cast<long long>(n) * H * W * c) return;
@@ -194,6 +206,8 @@ __global__ void upsample2x_add_kernel(const float* lat, const float* top, float*
 // one warp per output pixel; cout <= 128 (4 values per lane)
 __global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bias, const void* feat, int fdt, const float* ln_w,
                                          const float* ln_b, float eps, void* out, int odt, int n, int h, int w, int cout, int feat_bcast) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int H = 2 * h, W = 2 * w;
@@ -240,6 +254,8 @@ __global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bi
 
 __global__ void im2col_kernel(const void* x, int xdt, __nv_bfloat16* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow,
                               int kpad) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n) * oh * ow * kpad) return;
   const int col = static_cast<int>(i % kpad);
@@ -259,6 +275,8 @@ __global__ void im2col_kernel(const void* x, int xdt, __nv_bfloat16* out, int n,
 }
 
 __global__ void dwconv_kernel(const void* x, int xdt, const float* wt, const float* bias, void* y, int ydt, int n, int h, int w, int c, int k) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n) * h * w * c) return;
   const int ch = static_cast<int>(i % c);
@@ -284,6 +302,8 @@ __global__ void dwconv_kernel(const void* x, int xdt, const float* wt, const flo
 // one warp per output pixel; lanes stride over cout (<= 256 -> 8 per lane)
 __global__ void conv3x3s2_ln_gelu_kernel(const void* x, int xdt, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
                                          float eps, void* y, int ydt, int n, int h, int w, int cin, int cout) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int oh = h / 2, ow = w / 2;
@@ -339,6 +359,8 @@ template <int CIN, int COUT>
 __global__ void conv3x3s2_ln_gelu_small_kernel(const void* x, int xdt, const float* __restrict__ wt, const float* __restrict__ bias,
                                                const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, void* y, int ydt, int n,
                                                int h, int w) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long pix = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int oh = h / 2, ow = w / 2;
   if (pix >= static_cast<long long>(n) * oh * ow) return;
@@ -378,6 +400,8 @@ __global__ void conv3x3s2_ln_gelu_small_kernel(const void* x, int xdt, const flo
 }
 
 __global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n) * oh * ow) return;
   const int ox = static_cast<int>(i % ow);
@@ -402,6 +426,8 @@ __global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, 
 }
 
 __global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim, int gw, int gh) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int half = dim / 2;  // complex pairs per row
   if (i >= static_cast<long long>(nrows) * half) return;
@@ -421,6 +447,8 @@ __global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim
 }
 
 __global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int half = hd / 2;
   if (i >= static_cast<long long>(rows) * nheads * half) return;
@@ -438,6 +466,8 @@ __global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* po
 
 __global__ void embedding_kernel(const __nv_bfloat16* table, long long ldt, const long long* ids, void* out, int odt, long long ldo, int rows,
                                  int cols) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(rows) * cols) return;
   const int c = static_cast<int>(i % cols);
@@ -446,6 +476,8 @@ __global__ void embedding_kernel(const __nv_bfloat16* table, long long ldt, cons
 }
 
 __global__ void row_scatter_kernel(const __nv_bfloat16* src, __nv_bfloat16* cache, long long ld, const int* pos, int col0, int cols) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < cols) cache[static_cast<long long>(*pos) * ld + col0 + i] = src[col0 + i];
 }
@@ -480,6 +512,8 @@ __global__ void rope_kv_append_kernel(__nv_bfloat16* qkv, __nv_bfloat16* cache, 
 
 // one block per object: stability score of mask 0 (|{x > d}| / |{x > -d}|) and best-IoU index among masks 1..3
 __global__ void multimask_select_kernel(const float* masks, const float* iou, int hw, float delta, float thresh, long long* out_idx) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int b = blockIdx.x;
   const float* m0 = masks + static_cast<long long>(b) * 4 * hw;
   int ci = 0, cu = 0;
@@ -510,6 +544,8 @@ __global__ void multimask_select_kernel(const float* masks, const float* iou, in
 
 // one block (256 threads) per row
 __global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
   const int row = blockIdx.x;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -551,11 +587,11 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
   const unsigned grid = (rows + warps - 1) / warps;
   if (cols > 512 && cols <= 256 * 16 && rows < 2048) {  // wide rows, not enough of them to fill the chip with one warp each
     if (cols <= 256 * 4)
-      norm_block_kernel<4><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+      launch_k(norm_block_kernel<4>, dim3(rows), dim3(256), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
     else if (cols <= 256 * 8)
-      norm_block_kernel<8><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+      launch_k(norm_block_kernel<8>, dim3(rows), dim3(256), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
     else
-      norm_block_kernel<16><<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
+      launch_k(norm_block_kernel<16>, dim3(rows), dim3(256), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, cols, eps, rms);
     count_launch();
     return check_launch("norm_block_kernel");
   }
@@ -566,22 +602,22 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
   if (vec_ok) {
     const float* xf = static_cast<const float*>(x);
     if (cols <= 128 * 2)
-      norm_vec_kernel<2><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+      launch_k(norm_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     else if (cols <= 128 * 5)
-      norm_vec_kernel<5><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+      launch_k(norm_vec_kernel<5>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     else
-      norm_vec_kernel<12><<<grid, warps * 32, 0, STREAM>>>(xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+      launch_k(norm_vec_kernel<12>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     count_launch();
     return check_launch("norm_vec_kernel");
   }
   if (cols <= 32 * 4)
-    norm_kernel<4><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    launch_k(norm_kernel<4>, dim3(grid), dim3(warps * 32), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
   else if (cols <= 32 * 12)
-    norm_kernel<12><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    launch_k(norm_kernel<12>, dim3(grid), dim3(warps * 32), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
   else if (cols <= 32 * 48)
-    norm_kernel<48><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    launch_k(norm_kernel<48>, dim3(grid), dim3(warps * 32), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
   else if (cols <= 32 * 100)
-    norm_kernel<100><<<grid, warps * 32, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    launch_k(norm_kernel<100>, dim3(grid), dim3(warps * 32), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
   else
     return set_error(VG_ENOSUP, "vg_norm: cols %d > 3200", cols);
   count_launch();
@@ -591,7 +627,7 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
 extern "C" int vg_add(const void* a, int a_dtype, long long lda, int a_rows, const void* b, int b_dtype, long long ldb, int b_rows, float alpha, void* out,
                       int out_dtype, long long ldo, int rows, int cols, void* stream) {
   if (!a || !out || rows <= 0 || cols <= 0 || a_rows <= 0 || (b && b_rows <= 0)) return set_error(VG_EINVAL, "vg_add: bad argument");
-  add_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(a, a_dtype, lda, a_rows, b, b_dtype, ldb, b_rows, alpha, out,
+  launch_k(add_kernel, dim3(blocks_for(static_cast<long long>(rows) * cols, 256)), dim3(256), 0, STREAM, a, a_dtype, lda, a_rows, b, b_dtype, ldb, b_rows, alpha, out,
                                                                                         out_dtype, ldo, rows, cols);
   count_launch();
   return check_launch("add_kernel");
@@ -600,7 +636,7 @@ extern "C" int vg_add(const void* a, int a_dtype, long long lda, int a_rows, con
 extern "C" int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int n, int h, int w, int c, int is_max,
                           void* stream) {
   if (!x || !y || (h & 1) || (w & 1)) return set_error(VG_EINVAL, "vg_pool2x2: bad argument (h, w must be even)");
-  pool2x2_kernel<<<blocks_for(static_cast<long long>(n) * (h / 2) * (w / 2) * c, 256), 256, 0, STREAM>>>(x, x_dtype, ldx, y, y_dtype, ldy, n, h,
+  launch_k(pool2x2_kernel, dim3(blocks_for(static_cast<long long>(n) * (h / 2) * (w / 2) * c, 256)), dim3(256), 0, STREAM, x, x_dtype, ldx, y, y_dtype, ldy, n, h,
                                                                                                           w, c, is_max);
   count_launch();
   return check_launch("pool2x2_kernel");
@@ -608,7 +644,7 @@ extern "C" int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, in
 
 extern "C" int vg_upsample2x_add(const float* lat, const float* top, float* out, int n, int h, int w, int c, void* stream) {
   if (!lat || !top || !out) return set_error(VG_EINVAL, "vg_upsample2x_add: null");
-  upsample2x_add_kernel<<<blocks_for(static_cast<long long>(n) * 4 * h * w * c, 256), 256, 0, STREAM>>>(lat, top, out, n, h, w, c);
+  launch_k(upsample2x_add_kernel, dim3(blocks_for(static_cast<long long>(n) * 4 * h * w * c, 256)), dim3(256), 0, STREAM, lat, top, out, n, h, w, c);
   count_launch();
   return check_launch("upsample2x_add_kernel");
 }
@@ -617,7 +653,7 @@ extern "C" int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bia
                                     const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, int feat_bcast, void* stream) {
   if (!g || !bias || !out || cout > 128) return set_error(VG_EINVAL, "vg_convt2x2_epilogue: bad argument (cout <= 128)");
   const long long pix = static_cast<long long>(n) * 4 * h * w;
-  convt2x2_epilogue_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(g, g_dtype, bias, feat, feat_dtype, ln_w, ln_b, eps, out, out_dtype, n, h, w,
+  launch_k(convt2x2_epilogue_kernel, dim3(blocks_for(pix, 8)), dim3(256), 0, STREAM, g, g_dtype, bias, feat, feat_dtype, ln_w, ln_b, eps, out, out_dtype, n, h, w,
                                                                     cout, feat_bcast);
   count_launch();
   return check_launch("convt2x2_epilogue_kernel");
@@ -626,7 +662,7 @@ extern "C" int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bia
 extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
                          void* stream) {
   if (!x || !out || kpad < cin * k * k) return set_error(VG_EINVAL, "vg_im2col: bad argument");
-  im2col_kernel<<<blocks_for(static_cast<long long>(n) * oh * ow * kpad, 256), 256, 0, STREAM>>>(x, x_dtype, static_cast<__nv_bfloat16*>(out), n,
+  launch_k(im2col_kernel, dim3(blocks_for(static_cast<long long>(n) * oh * ow * kpad, 256)), dim3(256), 0, STREAM, x, x_dtype, static_cast<__nv_bfloat16*>(out), n,
                                                                                                   cin, h, w, k, s, p, oh, ow, kpad);
   count_launch();
   return check_launch("im2col_kernel");
@@ -635,7 +671,7 @@ extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, 
 extern "C" int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, void* y, int y_dtype, int n, int h, int wd, int c, int k,
                          void* stream) {
   if (!x || !w || !y) return set_error(VG_EINVAL, "vg_dwconv: null");
-  dwconv_kernel<<<blocks_for(static_cast<long long>(n) * h * wd * c, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, y, y_dtype, n, h, wd, c, k);
+  launch_k(dwconv_kernel, dim3(blocks_for(static_cast<long long>(n) * h * wd * c, 256)), dim3(256), 0, STREAM, x, x_dtype, w, bias, y, y_dtype, n, h, wd, c, k);
   count_launch();
   return check_launch("dwconv_kernel");
 }
@@ -645,37 +681,37 @@ extern "C" int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, 
   if (!x || !w || !bias || !ln_w || !ln_b || !y || cout > 256 || (h & 1) || (wd & 1)) return set_error(VG_EINVAL, "vg_conv3x3s2_ln_gelu: bad argument");
   const long long pix = static_cast<long long>(n) * (h / 2) * (wd / 2);
   if (cin == 1 && cout == 4) {
-    conv3x3s2_ln_gelu_small_kernel<1, 4><<<blocks_for(pix, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
+    launch_k(conv3x3s2_ln_gelu_small_kernel<1, 4>, dim3(blocks_for(pix, 256)), dim3(256), 0, STREAM, x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
     count_launch();
     return check_launch("conv3x3s2_ln_gelu_small_kernel");
   }
   if (cin == 4 && cout == 16) {
-    conv3x3s2_ln_gelu_small_kernel<4, 16><<<blocks_for(pix, 256), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
+    launch_k(conv3x3s2_ln_gelu_small_kernel<4, 16>, dim3(blocks_for(pix, 256)), dim3(256), 0, STREAM, x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd);
     count_launch();
     return check_launch("conv3x3s2_ln_gelu_small_kernel");
   }
-  conv3x3s2_ln_gelu_kernel<<<blocks_for(pix, 8), 256, 0, STREAM>>>(x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin, cout);
+  launch_k(conv3x3s2_ln_gelu_kernel, dim3(blocks_for(pix, 8)), dim3(256), 0, STREAM, x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin, cout);
   count_launch();
   return check_launch("conv3x3s2_ln_gelu_kernel");
 }
 
 extern "C" int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream) {
   if (!x || !y) return set_error(VG_EINVAL, "vg_bilinear: null");
-  bilinear_kernel<<<blocks_for(static_cast<long long>(n) * oh * ow, 256), 256, 0, STREAM>>>(x, y, n, ih, iw, oh, ow, mode, scale, bias);
+  launch_k(bilinear_kernel, dim3(blocks_for(static_cast<long long>(n) * oh * ow, 256)), dim3(256), 0, STREAM, x, y, n, ih, iw, oh, ow, mode, scale, bias);
   count_launch();
   return check_launch("bilinear_kernel");
 }
 
 extern "C" int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* stream) {
   if (!x || dim % 4) return set_error(VG_EINVAL, "vg_rope2d: dim must be a multiple of 4");
-  rope2d_kernel<<<blocks_for(static_cast<long long>(nrows) * dim / 2, 256), 256, 0, STREAM>>>(static_cast<__nv_bfloat16*>(x), ld, nrows, dim, gw, gh);
+  launch_k(rope2d_kernel, dim3(blocks_for(static_cast<long long>(nrows) * dim / 2, 256)), dim3(256), 0, STREAM, static_cast<__nv_bfloat16*>(x), ld, nrows, dim, gw, gh);
   count_launch();
   return check_launch("rope2d_kernel");
 }
 
 extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
   if (!qkv || !pos || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_neox: bad argument");
-  rope_neox_kernel<<<blocks_for(static_cast<long long>(rows) * n_heads_total * head_dim / 2, 256), 256, 0, STREAM>>>(
+  launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * n_heads_total * head_dim / 2, 256)), dim3(256), 0, STREAM, 
       static_cast<__nv_bfloat16*>(qkv), ld, pos, rows, n_heads_total, head_dim, theta);
   count_launch();
   return check_launch("rope_neox_kernel");
@@ -684,7 +720,7 @@ extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, i
 extern "C" int vg_embedding(const void* table, long long ldt, const long long* ids, void* out, int out_dtype, long long ldo, int rows, int cols,
                             void* stream) {
   if (!table || !ids || !out) return set_error(VG_EINVAL, "vg_embedding: null");
-  embedding_kernel<<<blocks_for(static_cast<long long>(rows) * cols, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(table), ldt, ids,
+  launch_k(embedding_kernel, dim3(blocks_for(static_cast<long long>(rows) * cols, 256)), dim3(256), 0, STREAM, static_cast<const __nv_bfloat16*>(table), ldt, ids,
                                                                                               out, out_dtype, ldo, rows, cols);
   count_launch();
   return check_launch("embedding_kernel");
@@ -692,14 +728,14 @@ extern "C" int vg_embedding(const void* table, long long ldt, const long long* i
 
 extern "C" int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream) {
   if (!x || !out) return set_error(VG_EINVAL, "vg_argmax: null");
-  argmax_kernel<<<rows, 256, 0, STREAM>>>(x, x_dtype, ldx, out, cols);
+  launch_k(argmax_kernel, dim3(rows), dim3(256), 0, STREAM, x, x_dtype, ldx, out, cols);
   count_launch();
   return check_launch("argmax_kernel");
 }
 
 extern "C" int vg_row_scatter(const void* src, void* cache, long long ld_cache, const int* pos_dev, int col0, int cols, void* stream) {
   if (!src || !cache || !pos_dev || cols <= 0) return set_error(VG_EINVAL, "vg_row_scatter: bad argument");
-  row_scatter_kernel<<<blocks_for(cols, 256), 256, 0, STREAM>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(cache), ld_cache,
+  launch_k(row_scatter_kernel, dim3(blocks_for(cols, 256)), dim3(256), 0, STREAM, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(cache), ld_cache,
                                                                 pos_dev, col0, cols);
   count_launch();
   return check_launch("row_scatter_kernel");
@@ -718,7 +754,7 @@ extern "C" int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, con
 
 extern "C" int vg_multimask_select(const float* masks, const float* iou, int n_obj, int hw, float delta, float thresh, long long* out_idx, void* stream) {
   if (!masks || !iou || !out_idx || n_obj <= 0) return set_error(VG_EINVAL, "vg_multimask_select: bad argument");
-  multimask_select_kernel<<<n_obj, 256, 0, STREAM>>>(masks, iou, hw, delta, thresh, out_idx);
+  launch_k(multimask_select_kernel, dim3(n_obj), dim3(256), 0, STREAM, masks, iou, hw, delta, thresh, out_idx);
   count_launch();
   return check_launch("multimask_select_kernel");
 }

@@ -19,7 +19,15 @@ inline bool pdl_enabled() {
   return v != 0;
 }
 
-template <typename... KArgs, typename... Args>
+inline bool pdl_all_enabled() {  // measured on B200 (profiles/r01_pdl.md): PDL on every launch gains nothing outside the decode chain -> opt-in
+  static const int v = [] {
+    const char* e = getenv("VG_PDL_ALL");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0 && pdl_enabled();
+}
+
+template <bool kAlways = true, typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -30,8 +38,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (kAlways ? pdl_enabled() : pdl_all_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Ordinary launch site (attribute only with VG_PDL_ALL=1); the kernels still execute pdl_wait(), which is a no-op without the attribute.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  return launch_pdl<false>(kernel, grid, block, smem, stream, args...);
+}
+
 }  // namespace vg
+
