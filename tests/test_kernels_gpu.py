@@ -125,6 +125,23 @@ def test_attention_packed_qkv_strides():
     assert rel(ops.attention(q, k, v), sdpa_ref(q, k, v, D ** -0.5)) < 6e-3
 
 
+@pytest.mark.parametrize("legacy", [False, True])
+def test_attention_hiera_windows_16(legacy):
+    """Hiera stage-3 geometry: 16x16-token windows (256 tokens), 8 heads x 72 on the packed qkv rows -> tcgen05 kernel with windowed TMA
+    boxes (legacy=True: the mma.sync kernel on the same call)."""
+    n_img, gh, gw, win, H, D = 3, 32, 48, 16, 8, 72
+    qkv = torch.randn(n_img * gh * gw, 3 * H * D, device=DEV).bfloat16()
+    q, k, v = (qkv[:, j * H * D:(j + 1) * H * D].unflatten(1, (H, D)) for j in range(3))
+    nwy, nwx = gh // win, gw // win
+
+    def part(t):
+        t = t.reshape(n_img, nwy, win, nwx, win, H, D).permute(0, 1, 3, 2, 4, 5, 6)
+        return t.reshape(-1, win * win, H, D)
+
+    o = ops.attention(q[None], k[None], v[None], q_win=(win, gw, nwx, nwy), k_win=(win, gw, nwx, nwy), legacy=legacy)
+    assert rel(part(o[0]), sdpa_ref(part(q), part(k), part(v), D ** -0.5)) < 6e-3
+
+
 @pytest.mark.parametrize("pooled", [False, True])
 def test_attention_hiera_windows(pooled):
     n_img, gh, gw, win, H, D = 2, 16, 24, 8, 2, 72

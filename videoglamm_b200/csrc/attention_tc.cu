@@ -24,10 +24,13 @@ struct AttnTcParams {
   long long o_bs, o_hs, o_rs;
   float* ws;  // split-K partials [split][b][h][row][DPM + 2]
   int dpm;    // row width of the partials (128 or 256)
+  int win, gridw, nwx;  // Hiera 2D windows (win > 0): batch entry b is window (b / nwx, b % nwx) of a [rows_y, gridw] token grid; tile rows are
+                        // (ty, tx) = (r / win, r % win) and the tensor maps are {D, H, x, y} with boxes of win x (rows / win) tokens
+  int s_col, tmem_cols; // TMEM column of S and the allocation size: 128/256 when O needs <= 128 columns (two blocks per SM), else 256/512
 };
 
-template <int BN>
-__global__ void __launch_bounds__(256, 1)
+template <int BN, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -79,7 +82,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_fence_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
+    tmem_alloc(tmem_slot, p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -89,21 +92,25 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   pdl_launch_dependents();
   pdl_wait();  // q/k/v are the predecessor's outputs; the prologue above overlapped its tail
   const uint32_t tO = tmem_base;         // columns [0, Dp)
-  const uint32_t tS = tmem_base + 256;   // columns [256, 256 + BN)
+  const uint32_t tS = tmem_base + p.s_col;   // columns [s_col, s_col + BN)
+  // tensor-map coordinates of a tile whose first row is r0: linear (row, batch) or windowed (x, y)
+  const int wx0 = p.win ? (b % p.nwx) * p.win : 0, wy0 = p.win ? (b / p.nwx) * p.win : 0;
+  auto c2 = [&](int r0) { return p.win ? wx0 : r0; };
+  auto c3 = [&](int r0) { return p.win ? wy0 + r0 / p.win : b; };
 
   if (warp == 0) {
     if (lane == 0 && ntiles > 0) {
       // ------------------------------------------------ TMA producer
       mbar_arrive_expect_tx(q_full, p.nblk * 16384);
-      for (int blk = 0; blk < p.nblk; ++blk) tma_load_4d(&tmQ, q_full, sQ + blk * 16384, blk * 64, h, q0, b);
+      for (int blk = 0; blk < p.nblk; ++blk) tma_load_4d(&tmQ, q_full, sQ + blk * 16384, blk * 64, h, c2(q0), c3(q0));
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
         mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&kv_full[st], 2 * kv_stage_bytes);
         const int k0 = k_begin + j * BN;
         for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(&tmK, &kv_full[st], sK + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, k0, b);
-          tma_load_4d(&tmV, &kv_full[st], sV + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, k0, b);
+          tma_load_4d(&tmK, &kv_full[st], sK + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
+          tma_load_4d(&tmV, &kv_full[st], sV + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
         }
       }
     }
@@ -229,7 +236,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < 32; ++i)
           if (c + i < p.D) wp[i] = __uint_as_float(raw[i]);
       } else {
-        __nv_bfloat16* op = p.o + b * p.o_bs + h * p.o_hs + static_cast<long long>(row) * p.o_rs + c;
+        const long long orow = p.win ? static_cast<long long>(wy0 + row / p.win) * p.gridw + wx0 + row % p.win : row;
+        __nv_bfloat16* op = p.o + (p.win ? 0 : b * p.o_bs) + h * p.o_hs + orow * p.o_rs + c;
         if (c + 32 <= p.D && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8)
@@ -249,7 +257,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -271,28 +279,29 @@ static EncodeTiledFn encode_fn() {
 struct Key4 {
   const void* ptr;
   long long hs, rs, bs;
-  int D, H, N, B, rows;
+  int D, H, N, B, rows, rows3;
   bool operator==(const Key4& o) const {
-    return ptr == o.ptr && hs == o.hs && rs == o.rs && bs == o.bs && D == o.D && H == o.H && N == o.N && B == o.B && rows == o.rows;
+    return ptr == o.ptr && hs == o.hs && rs == o.rs && bs == o.bs && D == o.D && H == o.H && N == o.N && B == o.B && rows == o.rows && rows3 == o.rows3;
   }
 };
 struct Key4Hash {
   size_t operator()(const Key4& k) const {
     size_t h = reinterpret_cast<size_t>(k.ptr);
     for (size_t v : {static_cast<size_t>(k.hs), static_cast<size_t>(k.rs), static_cast<size_t>(k.bs), static_cast<size_t>(k.D), static_cast<size_t>(k.H),
-                     static_cast<size_t>(k.N), static_cast<size_t>(k.B), static_cast<size_t>(k.rows)})
+                     static_cast<size_t>(k.N), static_cast<size_t>(k.B), static_cast<size_t>(k.rows), static_cast<size_t>(k.rows3)})
       h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
     return h;
   }
 };
 
 // bf16 view x[b][n][h][d] with element strides (bs, rs, hs, 1) -> 4D map {D, H, N, B}, box {64, 1, rows, 1}, SWIZZLE_128B, zero OOB fill
-static int make_map4(CUtensorMap* out, const void* ptr, int D, int H, int N, int B, long long hs, long long rs, long long bs, int rows) {
+// (windowed use: N = grid width, B = stacked grid rows, box {64, 1, win, rows3})
+static int make_map4(CUtensorMap* out, const void* ptr, int D, int H, int N, int B, long long hs, long long rs, long long bs, int rows, int rows3 = 1) {
   static std::mutex mu;
   static std::unordered_map<Key4, CUtensorMap, Key4Hash> cache;
   if (H == 1) hs = D;  // strides of size-1 dimensions are irrelevant but must be valid
   if (B == 1) bs = static_cast<long long>(N) * rs;
-  Key4 key{ptr, hs, rs, bs, D, H, N, B, rows};
+  Key4 key{ptr, hs, rs, bs, D, H, N, B, rows, rows3};
   {
     std::lock_guard<std::mutex> g(mu);
     auto it = cache.find(key);
@@ -305,7 +314,7 @@ static int make_map4(CUtensorMap* out, const void* ptr, int D, int H, int N, int
   if (!enc) return set_error(VG_ECUDA, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(hs) * 2, static_cast<cuuint64_t>(rs) * 2, static_cast<cuuint64_t>(bs) * 2};
-  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(rows), 1};
+  cuuint32_t box[4] = {64, 1, static_cast<cuuint32_t>(rows), static_cast<cuuint32_t>(rows3)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -318,25 +327,37 @@ static int make_map4(CUtensorMap* out, const void* ptr, int D, int H, int N, int
   return VG_OK;
 }
 
-template <int BN>
+template <int BN, int MINB>
 static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
   CUtensorMap tq, tk, tv;
-  int rc = make_map4(&tq, a->q, a->D, a->H, a->Nq, a->B, a->q_hs, a->q_rs, a->q_bs, 128);
-  if (rc) return rc;
-  rc = make_map4(&tk, a->k, a->D, a->H, a->Nk, a->B, a->k_hs, a->k_rs, a->k_bs, BN);
-  if (rc) return rc;
-  rc = make_map4(&tv, a->v, a->D, a->H, a->Nk, a->B, a->v_hs, a->v_rs, a->v_bs, BN);
-  if (rc) return rc;
+  int rc;
+  if (p.win) {
+    // token grid [rows_y = windows_y * win (all images stacked), gridw] -> map {D, H, x, y}, box {64, 1, win, rows / win}
+    const int rows_y = a->B / p.nwx * p.win;
+    rc = make_map4(&tq, a->q, a->D, a->H, p.gridw, rows_y, a->q_hs, a->q_rs, a->q_rs * p.gridw, p.win, 128 / p.win);
+    if (rc) return rc;
+    rc = make_map4(&tk, a->k, a->D, a->H, p.gridw, rows_y, a->k_hs, a->k_rs, a->k_rs * p.gridw, p.win, BN / p.win);
+    if (rc) return rc;
+    rc = make_map4(&tv, a->v, a->D, a->H, p.gridw, rows_y, a->v_hs, a->v_rs, a->v_rs * p.gridw, p.win, BN / p.win);
+    if (rc) return rc;
+  } else {
+    rc = make_map4(&tq, a->q, a->D, a->H, a->Nq, a->B, a->q_hs, a->q_rs, a->q_bs, 128);
+    if (rc) return rc;
+    rc = make_map4(&tk, a->k, a->D, a->H, a->Nk, a->B, a->k_hs, a->k_rs, a->k_bs, BN);
+    if (rc) return rc;
+    rc = make_map4(&tv, a->v, a->D, a->H, a->Nk, a->B, a->v_hs, a->v_rs, a->v_bs, BN);
+    if (rc) return rc;
+  }
   const int smem = p.nblk * 16384 + 4 * p.nblk * BN * 128 + (BN / 64) * 16384 + 256;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(flash_attn_tc_kernel<BN, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return set_error(VG_ECUDA, "attention_tc smem attr: %s", cudaGetErrorString(e));
     attr_smem = 227 * 1024;
   }
   const int q_tiles = (a->Nq + 127) / 128;
   dim3 grid(q_tiles * p.nsplit, a->H, a->B);
-  launch_k(flash_attn_tc_kernel<BN>, dim3(grid), dim3(256), smem, s, tq, tk, tv, p);
+  launch_k(flash_attn_tc_kernel<BN, MINB>, dim3(grid), dim3(256), smem, s, tq, tk, tv, p);
   count_launch();
   return check_launch("flash_attn_tc_kernel");
 }
@@ -344,7 +365,11 @@ static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
 // Returns VG_OK if the tcgen05 kernel handled the call, VG_ENOSUP if the caller should use the generic kernel.
 int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int* dpm_out) {
   *nsplit_out = 1;
-  if (a->q_win != 0 || a->k_win != 0 || a->window != 0 || a->nk_dev != nullptr) return VG_ENOSUP;
+  if (a->window != 0 || a->nk_dev != nullptr) return VG_ENOSUP;
+  const bool windowed = a->q_win != 0 || a->k_win != 0;
+  if (windowed && !(a->q_win == a->k_win && a->q_gridw == a->k_gridw && a->q_nwx == a->k_nwx && a->q_nwy == a->k_nwy && a->q_win > 0 &&
+                    128 % a->q_win == 0 && 64 % a->q_win == 0 && a->Nq == a->q_win * a->q_win && a->Nq % 128 == 0 && !a->causal && a->D <= 128))
+    return VG_ENOSUP;  // pooled-query windows and windows smaller than one tile stay on the generic kernel
   if (a->Nq < 128 || a->Nk < 128 || a->D > 256 || (a->D % 8)) return VG_ENOSUP;
   if ((reinterpret_cast<uintptr_t>(a->o) & 3) || (a->o_rs % 2) || (a->o_hs % 2) || (a->o_bs % 2)) return VG_ENOSUP;
   AttnTcParams p;
@@ -356,7 +381,16 @@ int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int*
   p.o_bs = a->o_bs; p.o_hs = a->o_hs; p.o_rs = a->o_rs;
   p.ws = nullptr; p.nsplit = 1;
   p.dpm = a->D <= 128 ? 128 : 256;
-  const int BN = a->D > 128 ? 64 : 128;
+  p.win = windowed ? a->q_win : 0;
+  p.gridw = a->q_gridw;
+  p.nwx = a->q_nwx;
+  // 64-key tiles: O (<= 128 columns) + S (64) fit a 256-column TMEM allocation and ~112 KB of shared memory, so TWO blocks share an SM and one
+  // block's softmax overlaps the other's MMAs (ncu: tensor pipe 16-26 % with one serial block per SM). VG_ATTN_BN=128 restores the wide tile.
+  static const int bn_env = [] { const char* e = getenv("VG_ATTN_BN"); return e ? atoi(e) : 64; }();
+  const int BN = a->D > 128 ? 64 : (bn_env == 128 ? 128 : 64);
+  const bool small_tmem = p.Dp <= 128 && BN == 64;
+  p.s_col = small_tmem ? 128 : 256;
+  p.tmem_cols = small_tmem ? 256 : 512;
   const long long ctas = static_cast<long long>((a->Nq + 127) / 128) * a->H * a->B;
   if (a->workspace != nullptr && !a->causal && ctas < 148 && a->Nk >= 2048) {
     int ns = static_cast<int>((148 + ctas - 1) / ctas);
@@ -370,7 +404,8 @@ int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int*
   }
   *nsplit_out = p.nsplit;
   *dpm_out = p.dpm;
-  return BN == 64 ? launch_tc<64>(a, p, s) : launch_tc<128>(a, p, s);
+  if (BN == 128) return launch_tc<128, 1>(a, p, s);
+  return small_tmem ? launch_tc<64, 2>(a, p, s) : launch_tc<64, 1>(a, p, s);
 }
 
 }  // namespace vg
