@@ -44,12 +44,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint8_t* sP = sV + 2 * kv_stage_bytes;       // (BN / 64) x [128 rows x 128 B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (BN / 64) * 16384);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* o_full = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]  S = Q K^T of tile j landed in TMEM buffer j & 1
+  uint64_t* s_empty = bars + 11;  // [2]  the softmax threads have read that buffer
+  uint64_t* p_full = bars + 13;   //      P of tile j is in shared memory
+  uint64_t* p_empty = bars + 14;  //      PV of tile j retired: P may be overwritten, O may be rescaled
+  uint64_t* o_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + BM - 1) / BM;
@@ -73,11 +77,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 128);
     }
-    mbar_init(s_full, 1);
     mbar_init(p_full, 128);
+    mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
     mbar_fence_init();
   }
@@ -91,8 +99,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();  // q/k/v are the predecessor's outputs; the prologue above overlapped its tail
-  const uint32_t tO = tmem_base;         // columns [0, Dp)
-  const uint32_t tS = tmem_base + p.s_col;   // columns [s_col, s_col + BN)
+  const uint32_t tO = tmem_base;             // columns [0, Dp)
+  const uint32_t tS = tmem_base + p.s_col;   // two S buffers: columns [s_col + st * BN, s_col + (st + 1) * BN)
   // tensor-map coordinates of a tile whose first row is r0: linear (row, batch) or windowed (x, y)
   const int wx0 = p.win ? (b % p.nwx) * p.win : 0, wy0 = p.win ? (b / p.nwx) * p.win : 0;
   auto c2 = [&](int r0) { return p.win ? wx0 : r0; };
@@ -100,38 +108,57 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   if (warp == 0) {
     if (lane == 0 && ntiles > 0) {
-      // ------------------------------------------------ TMA producer
+      // ------------------------------------------------ TMA producer: Q once, then the K ring (slot free as soon as its QK^T retired)
       mbar_arrive_expect_tx(q_full, p.nblk * 16384);
       for (int blk = 0; blk < p.nblk; ++blk) tma_load_4d(&tmQ, q_full, sQ + blk * 16384, blk * 64, h, c2(q0), c3(q0));
       for (int j = 0; j < ntiles; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kv_stage_bytes);
+        mbar_wait(&k_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], kv_stage_bytes);
         const int k0 = k_begin + j * BN;
-        for (int blk = 0; blk < p.nblk; ++blk) {
-          tma_load_4d(&tmK, &kv_full[st], sK + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
-          tma_load_4d(&tmV, &kv_full[st], sV + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
-        }
+        for (int blk = 0; blk < p.nblk; ++blk)
+          tma_load_4d(&tmK, &k_full[st], sK + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0 && ntiles > 0) {
+      // ------------------------------------------------ TMA producer for V (slot free when its PV retired)
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], kv_stage_bytes);
+        const int k0 = k_begin + j * BN;
+        for (int blk = 0; blk < p.nblk; ++blk)
+          tma_load_4d(&tmV, &v_full[st], sV + st * kv_stage_bytes + blk * kv_blk_bytes, blk * 64, h, c2(k0), c3(k0));
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && ntiles > 0) {
-      // ------------------------------------------------ MMA issuer
+      // ------------------------------------------------ MMA issuer. Issue order QK(0), QK(1), PV(0), QK(2), PV(1), ...: S is double-buffered
+      // in TMEM so that the softmax of tile j never waits for a QK^T, and PV(j) runs under the softmax of tile j + 1.
       const uint32_t idesc_s = umma_idesc_bf16(BM, BN);
       const uint32_t idesc_o = umma_idesc_bf16_bmn(BM, p.Dp);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < ntiles; ++j) {
+      auto issue_qk = [&](int j) {
         const int st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        if (j >= 2) mbar_wait(&s_empty[st], ((j >> 1) - 1) & 1);
         tc_fence_after();
         // S = Q K^T over the (zero-padded) head dim, 16 features per MMA
         for (int blk = 0; blk < p.nblk; ++blk) {
           const int steps = min(4, (p.Dp - 64 * blk) >> 4);
           const uint64_t qd = umma_desc_sw128(smem_u32(sQ + blk * 16384));
           const uint64_t kd = umma_desc_sw128(smem_u32(sK + st * kv_stage_bytes + blk * kv_blk_bytes));
-          for (int k = 0; k < steps; ++k) umma_bf16(tS, qd + 2 * k, kd + 2 * k, idesc_s, (blk | k) != 0);
+          for (int k = 0; k < steps; ++k) umma_bf16(tS + st * BN, qd + 2 * k, kd + 2 * k, idesc_s, (blk | k) != 0);
         }
-        umma_commit(s_full);  // also implies PV of the previous tile has retired (in-order completion)
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[st]);
+      };
+      issue_qk(0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j & 1;
+        if (j + 1 < ntiles) issue_qk(j + 1);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
         // O += P V: 16 keys per MMA; V is MN-major (features contiguous): 8-key groups every 1024 B, 64-feature blocks every BN*128 B
@@ -140,7 +167,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint64_t vd = umma_desc_sw128_mn(smem_u32(sV + st * kv_stage_bytes + kk * 2048), kv_blk_bytes, 1024);
           umma_bf16(tO, pd, vd, idesc_o, (j | kk) != 0);
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
+        umma_commit(p_empty);
       }
       umma_commit(o_full);
     }
@@ -153,28 +181,47 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const float sl2 = p.scale * 1.4426950408889634f;
     float m_ref = -INFINITY, l = 0.f;
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int st = j & 1;
+      mbar_wait(&s_full[st], (j >> 1) & 1);
       tc_fence_after();
       const int k0 = k_begin + j * BN;
       const int col_lim = p.causal ? min(p.Nk, row + off + 1) : p.Nk;  // valid columns are < col_lim
+      // masking is only needed on tiles that cross the key limit of some row of this warp (the last tile / the causal diagonal)
+      const bool need_mask = __any_sync(0xffffffffu, k0 + BN > col_lim);
       float sv[BN];
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t raw[32];
-        tmem_ld32(tS + lane_addr + c * 32, raw);
+        tmem_ld32(tS + st * BN + lane_addr + c * 32, raw);
         tmem_ld_wait();
+        if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = (k0 + c * 32 + i < col_lim) ? __uint_as_float(raw[i]) : -INFINITY;
-          sv[c * 32 + i] = x;
-          mx = fmaxf(mx, x);
+          for (int i = 0; i < 32; ++i) {
+            const float x = (k0 + c * 32 + i < col_lim) ? __uint_as_float(raw[i]) : -INFINITY;
+            sv[c * 32 + i] = x;
+            mx = fmaxf(mx, x);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            sv[c * 32 + i] = __uint_as_float(raw[i]);
+            mx = fmaxf(mx, sv[c * 32 + i]);
+          }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&s_empty[st]);  // this S buffer may be overwritten by QK^T of tile j + 2
       const float m_new = fmaxf(m_ref, mx);
       // lazy rescale (warp-uniform because tcgen05.ld/st are warp-collective): only when some row's max grew by more than 2^8
       const bool need = (m_ref != -INFINITY) && ((m_new - m_ref) * sl2 > 8.0f);
       if (m_ref == -INFINITY) m_ref = m_new;
+      // PV of the previous tile must have retired before O is rescaled or P is overwritten (it was issued when that tile's P arrived,
+      // one whole softmax ago, so this wait is normally already satisfied)
+      if (j > 0) {
+        mbar_wait(p_empty, (j - 1) & 1);
+        tc_fence_after();
+      }
       if (__any_sync(0xffffffffu, need)) {
         const float alpha = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
         for (int c = 0; c < p.Dp; c += 32) {
@@ -198,7 +245,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          pv[i] = ex2_approx(sv[c8 * 8 + i] * sl2 - msc);
+          pv[i] = ex2_approx(fmaf(sv[c8 * 8 + i], sl2, -msc));
           l += pv[i];
         }
         *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + (((c8 & 7) ^ sw) << 4)) =
