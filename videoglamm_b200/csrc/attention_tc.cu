@@ -216,13 +216,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       // lazy rescale (warp-uniform because tcgen05.ld/st are warp-collective): only when some row's max grew by more than 2^8
       const bool need = (m_ref != -INFINITY) && ((m_new - m_ref) * sl2 > 8.0f);
       if (m_ref == -INFINITY) m_ref = m_new;
-      // PV of the previous tile must have retired before O is rescaled or P is overwritten (it was issued when that tile's P arrived,
-      // one whole softmax ago, so this wait is normally already satisfied)
-      if (j > 0) {
-        mbar_wait(p_empty, (j - 1) & 1);
-        tc_fence_after();
-      }
+      // PV of the previous tile must have retired before O is rescaled or P is overwritten. It was issued when that tile's P arrived, and the
+      // issue -> execute -> commit -> mbarrier chain takes ~0.5 us, so the wait is deferred until the exponentials of THIS tile are done
+      // (they only need registers); the rare rescale path waits first.
+      bool pv_done = (j == 0);
       if (__any_sync(0xffffffffu, need)) {
+        if (!pv_done) {
+          mbar_wait(p_empty, (j - 1) & 1);
+          tc_fence_after();
+          pv_done = true;
+        }
         const float alpha = need ? ex2_approx((m_ref - m_new) * sl2) : 1.0f;
         for (int c = 0; c < p.Dp; c += 32) {
           uint32_t raw[32];
@@ -237,20 +240,23 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (need) m_ref = m_new;
       }
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      // P = exp2(S*scale*log2e - m) -> bf16 -> shared memory in the K-major SWIZZLE_128B operand layout
+      // P = exp2(S*scale*log2e - m) -> bf16 (registers) -> shared memory in the K-major SWIZZLE_128B operand layout
+      uint32_t pk[BN / 2];
+#pragma unroll
+      for (int i = 0; i < BN / 2; ++i) {
+        const float p0 = ex2_approx(fmaf(sv[2 * i], sl2, -msc)), p1 = ex2_approx(fmaf(sv[2 * i + 1], sl2, -msc));
+        l += p0 + p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+      if (!pv_done) {
+        mbar_wait(p_empty, (j - 1) & 1);
+        tc_fence_after();
+      }
       uint8_t* prow = sP + r * 128;
       const int sw = r & 7;
 #pragma unroll
-      for (int c8 = 0; c8 < BN / 8; ++c8) {
-        float pv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pv[i] = ex2_approx(fmaf(sv[c8 * 8 + i], sl2, -msc));
-          l += pv[i];
-        }
-        *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + (((c8 & 7) ^ sw) << 4)) =
-            make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]), pack_bf16(pv[6], pv[7]));
-      }
+      for (int c8 = 0; c8 < BN / 8; ++c8)
+        *reinterpret_cast<uint4*>(prow + (c8 >> 3) * 16384 + (((c8 & 7) ^ sw) << 4)) = make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
       fence_async_shared();
       tc_fence_before();
       mbar_arrive(p_full);
