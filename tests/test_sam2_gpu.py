@@ -158,3 +158,44 @@ def test_predictor_surface_matches_run_video(ctx):
         assert torch.allclose(a[:, 0], b, atol=1e-4)
     with pytest.raises(RuntimeError):
         eng.add_new_text(st, 0, 7, text[:1])   # no new objects after tracking starts (sam2_video_predictor.py:_obj_id_to_idx)
+
+
+def test_video_session_against_reference_golden():
+    """Engine vs the fixture frozen from the UNMODIFIED reference SAM2VideoPredictor (tests/golden/make_golden.py:sam2_video_golden):
+    9 frames, 2 objects (memory bank full from frame 7 on) and the object-absent branch (NO_OBJ_SCORE fill)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "sam2_tiny_video.npz"))
+    ocfg, ecfg = O.Sam2Cfg(**O.TINY), Sam2Config(**O.TINY)
+    for name, bias, T, nobj in (("present", 4.0, 9, 2), ("absent", -100.0, 2, 1)):
+        sd = Wt.make_sam2_state_dict(ocfg, 1234, obj_score_bias=bias)
+        eng = Sam2Engine(sd, ecfg)
+        torch.manual_seed(5678)
+        images, text = torch.randn(T, 3, ocfg.image_size, ocfg.image_size), torch.randn(nobj, 1, 256)
+        got = torch.stack([m.cpu() for m in eng.run_video(images.cuda(), text.cuda(), (60, 100))])
+        ref = torch.from_numpy(g[name])[:, :, 0]
+        assert got.shape == ref.shape
+        if name == "absent":
+            assert torch.all(got == O.NO_OBJ_SCORE)
+            continue
+        for t in range(T):   # bf16 operands against the reference's fp32: error grows along the 9-frame recurrence
+            assert rel(got[t], ref[t]) < 4e-2, (t, rel(got[t], ref[t]))
+        decided = ref.abs() > 0.05 * ref.abs().max()
+        assert torch.equal(got[decided] > 0, ref[decided] > 0)
+        assert ((got > 0) == (ref > 0)).float().mean() > 0.99
+
+
+def test_long_session_four_objects(ctx):
+    """MeViS-like stress (BASELINE.json configs[4] structure at the shrunken size): 20 frames, 4 objects -> memory bank eviction (7 slots)
+    and the 16-pointer cap are both exercised (sam2_base.py:535-636)."""
+    ocfg, sd, eng = ctx["ocfg"], ctx["sd"], ctx["eng"]
+    torch.manual_seed(99)
+    images, text = torch.randn(20, 3, ocfg.image_size, ocfg.image_size), torch.randn(4, 1, 256)
+    ref = O.run_video(sd, ocfg, images, text, (36, 52))
+    got = eng.run_video(images.cuda(), text.cuda(), (36, 52))
+    agree = []
+    for t in range(20):
+        a, b = got[t].cpu(), ref[t][:, 0]
+        agree.append(((a > 0) == (b > 0)).float().mean().item())
+        assert rel(a, b) < 6e-2, (t, rel(a, b))
+    assert min(agree) > 0.98, agree
