@@ -103,7 +103,17 @@ def run_engine(args):
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON line on stdout -> point fd 1 at stderr meanwhile
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     dev = f"cuda:{local}"
     lmm_cfg, sam_cfg = make_lmm_config(), Sam2Config()
     sd = random_state_dict(videoglamm_param_shapes(lmm_cfg, sam_cfg), dev, seed=1234)

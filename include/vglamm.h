@@ -170,6 +170,14 @@ int vg_rope_kv_append(void* qkv, void* cache, long long ld_cache, const int* pos
 int vg_multimask_select(const float* masks, const float* iou, int n_obj, int hw, float delta, float thresh, long long* out_idx, void* stream);
 /* adds n to the launch counter (replayed CUDA-graph nodes are launches too) */
 void vg_launch_count_add(long long n);
+/* 8-connected components of binary masks: the reference's only native extension, sam2._C.get_connected_componnets
+ * (.../sam2/csrc/connected_components.cu:213-289, bound in .../sam2/utils/misc.py:47-63). mask uint8 [n][h][w] (nonzero = foreground; the
+ * reference's [N,1,H,W] contiguous tensor), h and w even (the reference asserts the same) -> labels int32 [n][h][w]: 0 on the background, else
+ * 1 + min over the component of the linear index of the top-left pixel of each member's 2x2 block (exactly the reference's label values);
+ * counts int32 [n][h][w]: component area on foreground pixels, 0 elsewhere. Caller-owned outputs and workspace (>= 2*n*h*w*4 bytes), runs on
+ * `stream`, errors are return codes (the reference raises through AT_ASSERTM). */
+int vg_connected_components(const unsigned char* mask, int* labels, int* counts, int n, int h, int w, void* workspace, long long workspace_bytes,
+                            void* stream);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

@@ -166,7 +166,8 @@ def test_attention_hiera_windows(pooled):
 
 
 @pytest.mark.parametrize("rows,cols,rms,xdt", [(100, 256, False, torch.float32), (77, 1408, True, torch.float32), (5, 3072, True, torch.bfloat16),
-                                               (1000, 144, False, torch.float32), (64, 64, False, torch.bfloat16), (10, 32, False, torch.float32)])
+                                               (1000, 144, False, torch.float32), (64, 64, False, torch.bfloat16), (10, 32, False, torch.float32),
+                                               (300, 1408, True, torch.bfloat16), (50, 576, False, torch.bfloat16)])
 def test_norm(rows, cols, rms, xdt):
     x = (torch.randn(rows, cols, device=DEV) * 3 + 1).to(xdt)
     w, b = torch.randn(cols, device=DEV), torch.randn(cols, device=DEV)
@@ -307,6 +308,19 @@ def test_attention_single_query_decode(H, Nk, D, window):
     v = torch.randn(1, Nk, H, D, device=DEV).bfloat16()
     o = ops.attention(q, k, v, causal=True, window=window)
     assert rel(o, sdpa_ref(q, k, v, D ** -0.5, True, window)) < 4e-3
+
+
+def test_norm_bf16_in_place_on_packed_rows():
+    """IV2 q/k RMSNorm: bf16 rows that are column slices of the packed qkv matrix, normalised in place (vectorised bf16 path)."""
+    qkv = (torch.randn(257, 3 * 1408, device=DEV) * 2).bfloat16()
+    w = torch.randn(1408, device=DEV)
+    x = qkv[:, 1408:2816]
+    xf = x.float()
+    ref = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    before = qkv.clone()
+    ops.norm(x, w, eps=1e-6, rms=True, out=x)
+    assert rel(qkv[:, 1408:2816], ref) < 4e-3
+    assert torch.equal(qkv[:, :1408], before[:, :1408]) and torch.equal(qkv[:, 2816:], before[:, 2816:])
 
 
 @pytest.mark.parametrize("rows,cols", [(1, 3072), (3, 1408), (100, 1024), (2047, 600)])

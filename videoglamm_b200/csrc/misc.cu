@@ -60,22 +60,28 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
 }
 
 // fp32-in fast path: one warp per row, 128-bit loads (lane owns float4 chunks lane, lane+32, ...), 64/128-bit stores
-template <int MAXC>
-__global__ void norm_vec_kernel(const float* __restrict__ x, long long ldx, void* y, int ydt, long long ldy, const float* __restrict__ w,
+template <int MAXC, bool XBF16 = false>
+__global__ void norm_vec_kernel(const void* __restrict__ xv, long long ldx, void* y, int ydt, long long ldy, const float* __restrict__ w,
                                 const float* __restrict__ b, int rows, int cols, float eps, int rms) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
+  const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(xv) + static_cast<long long>(row) * ldx);
+  const uint2* xh = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(xv) + static_cast<long long>(row) * ldx);  // 4 bf16 per chunk
   const int nch = cols >> 2;
   float4 v[MAXC];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXC; ++i) {
     const int c = lane + i * 32;
-    v[i] = c < nch ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (XBF16) {
+      const uint2 u = c < nch ? xh[c] : make_uint2(0u, 0u);
+      v[i] = make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+    } else {
+      v[i] = c < nch ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     sum += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   float mean = 0.f;
@@ -353,6 +359,76 @@ __global__ void conv3x3s2_ln_gelu_kernel(const void* x, int xdt, const float* wt
   }
 }
 
+// PX consecutive output pixels of one row per warp: every weight value a lane loads is reused for PX pixels (the one-pixel kernel re-read the
+// whole [9*cin, cout] fp32 weight block per pixel: 590 KB x 4096 pixels = 2.4 GB of L2 traffic for the 64 -> 256 stage, 215 us per launch)
+template <int PX>
+__global__ void __launch_bounds__(256) conv3x3s2_ln_gelu_px_kernel(const void* x, int xdt, const float* __restrict__ wt, const float* __restrict__ bias,
+                                                                   const float* __restrict__ ln_w, const float* __restrict__ ln_b, float eps, void* y,
+                                                                   int ydt, int n, int h, int w, int cin, int cout) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
+  const int oh = h / 2, ow = w / 2, gpr = ow / PX;  // pixel groups per output row
+  const long long grp = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (grp >= static_cast<long long>(n) * oh * gpr) return;
+  const int ox0 = static_cast<int>(grp % gpr) * PX;
+  const int oy = static_cast<int>((grp / gpr) % oh);
+  const int img = static_cast<int>(grp / (static_cast<long long>(gpr) * oh));
+  float acc[PX][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int co = lane + i * 32;
+    const float bv = co < cout ? bias[co] : 0.f;
+#pragma unroll
+    for (int q = 0; q < PX; ++q) acc[q][i] = bv;
+  }
+  const int nco = (cout + 31) / 32;  // live accumulator slots per lane (warp-uniform)
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = 2 * oy - 1 + ky;
+    if (iy < 0 || iy >= h) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const float* wk = wt + static_cast<long long>((ky * 3 + kx) * cin) * cout;
+      const long long rowb = (static_cast<long long>(img) * h + iy) * w;
+      for (int ci = 0; ci < cin; ++ci) {
+        float wv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int co = lane + i * 32;
+          wv[i] = (i < nco && co < cout) ? wk[static_cast<long long>(ci) * cout + co] : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < PX; ++q) {
+          const int ix = 2 * (ox0 + q) - 1 + kx;
+          const float xv = (ix >= 0 && ix < w) ? ld(x, xdt, (rowb + ix) * cin + ci) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nco) acc[q][i] = fmaf(xv, wv[i], acc[q][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < PX; ++q) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += (lane + i * 32 < cout) ? acc[q][i] : 0.f;
+    const float mean = warp_sum(sum) / cout;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = (lane + i * 32 < cout) ? acc[q][i] - mean : 0.f;
+      sq += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / cout + eps);
+    const long long pix = (static_cast<long long>(img) * oh + oy) * ow + ox0 + q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int co = lane + i * 32;
+      if (co < cout) st(y, ydt, pix * cout + co, gelu_erf((acc[q][i] - mean) * rstd * ln_w[co] + ln_b[co]));
+    }
+  }
+}
+
 // small-channel variant: one THREAD per output pixel, all COUT channels + LayerNorm + GELU in registers (the warp-per-pixel kernel
 // leaves 28 of 32 lanes idle when cout = 4)
 template <int CIN, int COUT>
@@ -449,19 +525,21 @@ __global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim
 __global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
+  // one thread per (row, rotation pair): the angle (powf + sincosf, ~100 instructions) is computed once and reused for every head
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   const int half = hd / 2;
-  if (i >= static_cast<long long>(rows) * nheads * half) return;
+  if (i >= static_cast<long long>(rows) * half) return;
   const int j = static_cast<int>(i % half);
-  const int hh = static_cast<int>((i / half) % nheads);
-  const long long r = i / (static_cast<long long>(half) * nheads);
+  const long long r = i / half;
   const float inv = powf(theta, -2.0f * j / hd);
   float sn, cs;
   sincosf(pos[r] * inv, &sn, &cs);
-  __nv_bfloat16* p = qkv + r * ld + hh * hd;
-  const float a = __bfloat162float(p[j]), b = __bfloat162float(p[j + half]);
-  p[j] = __float2bfloat16(a * cs - b * sn);
-  p[j + half] = __float2bfloat16(b * cs + a * sn);
+  __nv_bfloat16* p = qkv + r * ld + j;
+  for (int hh = 0; hh < nheads; ++hh, p += hd) {
+    const float a = __bfloat162float(p[0]), b = __bfloat162float(p[half]);
+    p[0] = __float2bfloat16(a * cs - b * sn);
+    p[half] = __float2bfloat16(b * cs + a * sn);
+  }
 }
 
 __global__ void embedding_kernel(const __nv_bfloat16* table, long long ldt, const long long* ids, void* out, int odt, long long ldo, int rows,
@@ -543,36 +621,56 @@ __global__ void multimask_select_kernel(const float* masks, const float* iou, in
 }
 
 // one block (256 threads) per row
-__global__ void argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
+__global__ void __launch_bounds__(1024) argmax_kernel(const void* x, int xdt, long long ldx, long long* out, int cols) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
+  // one block per row (first-index tie break, like torch.argmax). fp32 rows take 128-bit loads: the 32k-column lm_head row is ~8 independent
+  // loads per thread instead of 125 dependent scalar ones (62 us -> a few us per decoded token).
   const int row = blockIdx.x;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    const float v = ld(x, xdt, static_cast<long long>(row) * ldx + c);
+  auto upd = [&](float v, int c) {
     if (v > best || (v == best && c < bi)) {
       best = v;
       bi = c;
     }
-  }
-  __shared__ float sv[256];
-  __shared__ int si[256];
-  sv[threadIdx.x] = best;
-  si[threadIdx.x] = bi;
-  __syncthreads();
-  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-    if (threadIdx.x < s) {
-      const float ov = sv[threadIdx.x + s];
-      const int oi = si[threadIdx.x + s];
-      if (ov > sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) {
-        sv[threadIdx.x] = ov;
-        si[threadIdx.x] = oi;
-      }
+  };
+  const long long base = static_cast<long long>(row) * ldx;
+  if (xdt == VG_F32 && (cols & 3) == 0 && (ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const float4* xr = reinterpret_cast<const float4*>(static_cast<const float*>(x) + base);
+    for (int c = threadIdx.x; c < (cols >> 2); c += blockDim.x) {
+      const float4 v = xr[c];
+      upd(v.x, 4 * c); upd(v.y, 4 * c + 1); upd(v.z, 4 * c + 2); upd(v.w, 4 * c + 3);
     }
-    __syncthreads();
+  } else {
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) upd(ld(x, xdt, base + c), c);
   }
-  if (threadIdx.x == 0) out[row] = si[0];
+  // warp reduction, then one value per warp through shared memory
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    upd(ov, oi);
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) {
+    sv[warp] = best;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    best = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      upd(ov, oi);
+    }
+    if (lane == 0) out[row] = bi;
+  }
 }
 
 }  // namespace vg
@@ -600,13 +698,26 @@ extern "C" int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y
                       (reinterpret_cast<uintptr_t>(y) & (esz_y * 4 - 1)) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
                       (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) && cols <= 128 * 12;
   if (vec_ok) {
-    const float* xf = static_cast<const float*>(x);
+    const void* xf = x;
     if (cols <= 128 * 2)
       launch_k(norm_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     else if (cols <= 128 * 5)
       launch_k(norm_vec_kernel<5>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     else
       launch_k(norm_vec_kernel<12>, dim3(grid), dim3(warps * 32), 0, STREAM, xf, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    count_launch();
+    return check_launch("norm_vec_kernel");
+  }
+  const bool vec_bf = x_dtype == VG_BF16 && (cols % 4) == 0 && (ldx % 4) == 0 && (ldy % 4) == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0 &&
+                      (reinterpret_cast<uintptr_t>(y) & (esz_y * 4 - 1)) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                      (b == nullptr || (reinterpret_cast<uintptr_t>(b) & 15) == 0) && cols <= 128 * 12;
+  if (vec_bf) {  // bf16 rows (IV2 q/k RMSNorm on the packed qkv): 64-bit loads instead of 2-byte ones (30 us -> HBM-bound)
+    if (cols <= 128 * 2)
+      launch_k(norm_vec_kernel<2, true>, dim3(grid), dim3(warps * 32), 0, STREAM, x, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    else if (cols <= 128 * 5)
+      launch_k(norm_vec_kernel<5, true>, dim3(grid), dim3(warps * 32), 0, STREAM, x, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
+    else
+      launch_k(norm_vec_kernel<12, true>, dim3(grid), dim3(warps * 32), 0, STREAM, x, ldx, y, y_dtype, ldy, w, b, rows, cols, eps, rms);
     count_launch();
     return check_launch("norm_vec_kernel");
   }
@@ -690,6 +801,12 @@ extern "C" int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, 
     count_launch();
     return check_launch("conv3x3s2_ln_gelu_small_kernel");
   }
+  if ((wd / 2) % 8 == 0 && cout <= 256) {
+    launch_k(conv3x3s2_ln_gelu_px_kernel<8>, dim3(blocks_for(pix / 8, 8)), dim3(256), 0, STREAM, x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin,
+             cout);
+    count_launch();
+    return check_launch("conv3x3s2_ln_gelu_px_kernel");
+  }
   launch_k(conv3x3s2_ln_gelu_kernel, dim3(blocks_for(pix, 8)), dim3(256), 0, STREAM, x, x_dtype, w, bias, ln_w, ln_b, eps, y, y_dtype, n, h, wd, cin, cout);
   count_launch();
   return check_launch("conv3x3s2_ln_gelu_kernel");
@@ -711,7 +828,7 @@ extern "C" int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int 
 
 extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
   if (!qkv || !pos || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_neox: bad argument");
-  launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * n_heads_total * head_dim / 2, 256)), dim3(256), 0, STREAM, 
+  launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * head_dim / 2, 128)), dim3(128), 0, STREAM, 
       static_cast<__nv_bfloat16*>(qkv), ld, pos, rows, n_heads_total, head_dim, theta);
   count_launch();
   return check_launch("rope_neox_kernel");
@@ -728,7 +845,7 @@ extern "C" int vg_embedding(const void* table, long long ldt, const long long* i
 
 extern "C" int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream) {
   if (!x || !out) return set_error(VG_EINVAL, "vg_argmax: null");
-  launch_k(argmax_kernel, dim3(rows), dim3(256), 0, STREAM, x, x_dtype, ldx, out, cols);
+  launch_k(argmax_kernel, dim3(rows), dim3(cols >= 8192 ? 1024 : 256), 0, STREAM, x, x_dtype, ldx, out, cols);
   count_launch();
   return check_launch("argmax_kernel");
 }

@@ -357,3 +357,22 @@ def multimask_select(masks: torch.Tensor, iou: torch.Tensor, delta: float = 0.05
     L.check(L.lib().vg_multimask_select(_ptr(masks), _ptr(iou), masks.shape[0], masks.shape[2], C.c_float(delta), C.c_float(thresh), _ptr(out),
                                         _stream()), "vg_multimask_select")
     return out
+
+
+def connected_components(mask: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """sam2._C.get_connected_componnets (sam2/csrc/connected_components.cu:213-289): mask uint8 [N,1,H,W] CUDA contiguous -> (labels int32
+    [N,1,H,W], counts int32 [N,1,H,W]); raises RuntimeError on bad input like the reference's AT_ASSERTM."""
+    if not mask.is_cuda:
+        raise RuntimeError("inputs must be a CUDA tensor")
+    if mask.dim() != 4 or mask.shape[1] != 1:
+        raise RuntimeError("inputs must be [N, 1, H, W] shape")
+    if mask.dtype != torch.uint8:
+        raise RuntimeError("inputs must be a uint8 type")
+    mask = mask.contiguous()
+    n, _, h, w = mask.shape
+    labels = torch.empty((n, 1, h, w), device=mask.device, dtype=torch.int32)
+    counts = torch.empty_like(labels)
+    ws = torch.empty((2 * n * h * w,), device=mask.device, dtype=torch.int32)
+    L.check(L.lib().vg_connected_components(_ptr(mask), _ptr(labels), _ptr(counts), n, h, w, _ptr(ws), C.c_longlong(ws.numel() * 4), _stream()),
+            "vg_connected_components")
+    return labels, counts
