@@ -145,6 +145,13 @@ int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, voi
  * (MaskDownSampler stage, memory_encoder.py:17-58). x: [n][h][w][cin] -> y: [n][h/2][w/2][cout]. */
 int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, const float* bias, const float* ln_w, const float* ln_b, float eps,
                          void* y, int y_dtype, int n, int h, int wd, int cin, int cout, void* stream);
+/* The same convolution as a tensor-core GEMM, for cin >= 16: (1) im2col of the channels-last [n][h][w][cin] input (cin % 8 == 0) to bf16
+ * [n*(h/2)*(w/2)][9*cin], column order (ky,kx,ci); (2) vg_gemm with the weights as [cout][(ky,kx,ci)] + bias, fp32 out;
+ * (3) LayerNorm2d + GELU on the fp32 rows (cols % 4 == 0, cols <= 640), bf16 or fp32 out. (MaskDownSampler stages 16->64 and 64->256,
+ * memory_encoder.py:17-58) */
+int vg_im2col3x3s2_cl(const void* x, int x_dtype, void* out, int n, int h, int w, int cin, void* stream);
+int vg_layernorm_gelu(const float* x, long long ldx, void* y, int y_dtype, long long ldy, const float* w, const float* b, int rows, int cols,
+                      float eps, void* stream);
 /* Bilinear resize (align_corners=False, no antialias) of fp32 planes [n][ih][iw] -> [n][oh][ow] with a fused output map:
  * mode 0: identity; 1: sigmoid(x)*scale+bias; 2: (x>0)*scale+bias (sam2_base.py:366-374, 687-697; sam2_video_predictor.py:498-518);
  * mode 3: write uint8 (x > 0) instead of fp32 (VideoGLaMM.py:870-875). */

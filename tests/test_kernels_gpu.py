@@ -142,6 +142,25 @@ def test_attention_hiera_windows_16(legacy):
     assert rel(part(o[0]), sdpa_ref(part(q), part(k), part(v), D ** -0.5)) < 6e-3
 
 
+@pytest.mark.parametrize("win,H", [(4, 4), (8, 2), (4, 8), (8, 4)])
+def test_attention_hiera_small_windows(win, H):
+    """Hiera stage-1/2 geometry: 8x8 / 4x4-token windows, 72-wide heads, q/k/v = column blocks of the packed qkv rows -> one block per window
+    (window_attn_small_kernel). Checked against SDPA on the partitioned windows and against the generic kernel (legacy=True)."""
+    n_img, gh, gw, D = 2, 16, 24, 72
+    qkv = torch.randn(n_img * gh * gw, 3 * H * D, device=DEV).bfloat16()
+    q, k, v = (qkv[:, j * H * D:(j + 1) * H * D].unflatten(1, (H, D)) for j in range(3))
+    nwy, nwx = gh // win, gw // win
+
+    def part(t):
+        t = t.reshape(n_img, nwy, win, nwx, win, H, D).permute(0, 1, 3, 2, 4, 5, 6)
+        return t.reshape(-1, win * win, H, D)
+
+    o = ops.attention(q[None], k[None], v[None], q_win=(win, gw, nwx, nwy), k_win=(win, gw, nwx, nwy))
+    assert rel(part(o[0]), sdpa_ref(part(q), part(k), part(v), D ** -0.5)) < 6e-3
+    o2 = ops.attention(q[None], k[None], v[None], q_win=(win, gw, nwx, nwy), k_win=(win, gw, nwx, nwy), legacy=True)
+    assert rel(o, o2) < 6e-3
+
+
 @pytest.mark.parametrize("pooled", [False, True])
 def test_attention_hiera_windows(pooled):
     n_img, gh, gw, win, H, D = 2, 16, 24, 8, 2, 72
@@ -364,3 +383,22 @@ def test_rope_kv_append_and_fused_merge_decode_attention():
         o = ops.attention(q, k, v, causal=True, nk_dev=nk, decode_ws=ws)
         assert rel(o, sdpa_ref(q, k[:, :1501], v[:, :1501], hd ** -0.5, True, 0)) < 4e-3
     assert int(ws[-H:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(16, 64, 32), (64, 256, 16), (8, 24, 8)])
+def test_conv3x3s2_ln_gelu_gemm_path(cin, cout, hw):
+    """MaskDownSampler wide stages through im2col (channels-last) + tcgen05 GEMM + LayerNorm/GELU kernel vs torch conv2d (bf16 operands)."""
+    n = 2
+    x = torch.randn(n, cin, hw, hw, device=DEV)
+    W, b = torch.randn(cout, cin, 3, 3, device=DEV) / (3 * cin ** 0.5), torch.randn(cout, device=DEV)
+    lw, lb = torch.randn(cout, device=DEV), torch.randn(cout, device=DEV)
+    r = F.conv2d(x.bfloat16().float(), W.bfloat16().float(), b, stride=2, padding=1)
+    u = r.mean(1, keepdim=True)
+    s = (r - u).pow(2).mean(1, keepdim=True)
+    ref = F.gelu(lw[:, None, None] * ((r - u) / torch.sqrt(s + 1e-6)) + lb[:, None, None]).permute(0, 2, 3, 1).reshape(-1, cout)
+    xcl = x.permute(0, 2, 3, 1).reshape(-1, cin).contiguous()
+    y = ops.conv3x3s2_ln_gelu_gemm(xcl, W.permute(0, 2, 3, 1).reshape(cout, 9 * cin).bfloat16().contiguous(), b, lw, lb, 1e-6, n, hw, hw, cin, cout)
+    assert rel(y, ref) < 1e-4
+    yb = ops.conv3x3s2_ln_gelu_gemm(xcl, W.permute(0, 2, 3, 1).reshape(cout, 9 * cin).bfloat16().contiguous(), b, lw, lb, 1e-6, n, hw, hw, cin, cout,
+                                    out_dtype=torch.bfloat16)
+    assert rel(yb, ref) < 4e-3

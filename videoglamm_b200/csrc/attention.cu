@@ -4,6 +4,8 @@
 // Q/K/V/O are addressed through (batch, head, row) element strides so packed qkv GEMM outputs are read in place;
 // Hiera windows are addressed by index arithmetic on the un-partitioned [H,W] token grid (no window_partition copy).
 // Bring-up tensor path: mma.sync m16n8k16 bf16 with fp32 accumulate, cp.async double-buffered K/V tiles.
+#include <cstdlib>
+
 #include "common.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -236,6 +238,167 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- small Hiera windows (16 / 64 tokens)
+// Hiera stages 1-2 attend inside 8x8 / 4x4-token windows with 72-wide heads. The generic 64x64-tile kernel spends a block per (window, head)
+// on a tile that is 75-94 % padding (ncu: 385 us per stage-2 launch for 300 MB of traffic). Here ONE block owns one window and ALL its heads:
+// the packed qkv rows of the window's tokens (contiguous 3*C bf16 each) are copied to shared memory once with 16-byte cp.async, warp
+// (head, 16-row group) computes S = Q K^T, the softmax over the whole window and O = P V entirely in registers with mma.sync m16n8k16
+// (+ an m16n8k8 step for the 8-feature tail of D = 72), writes O back over its own Q slice, and the block stores whole output rows.
+template <int T>
+__global__ void __launch_bounds__(512) window_attn_small_kernel(const __nv_bfloat16* __restrict__ qkv, long long ld, __nv_bfloat16* __restrict__ out,
+                                                                long long ldo, int H, int win, int gridw, int nwx, float scale) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
+  constexpr int D = 72, RG = T / 16;
+  extern __shared__ __align__(16) uint8_t smem_win[];
+  __nv_bfloat16* s = reinterpret_cast<__nv_bfloat16*>(smem_win);
+  const int C = H * D, LDS = 3 * C + 8;  // padded row: consecutive rows start 16 B apart modulo 128 B -> conflict-free ldmatrix
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x;
+  const long long wy0 = static_cast<long long>(b / nwx) * win;
+  const int wx0 = (b % nwx) * win;
+  auto grow = [&](int t) { return (wy0 + t / win) * gridw + wx0 + t % win; };
+  const int cpr = (3 * C) >> 3;  // 16-byte chunks per token row
+  for (int i = tid; i < T * cpr; i += blockDim.x) {
+    const int t = i / cpr, c = i - t * cpr;
+    cp_async16(s + t * LDS + c * 8, qkv + grow(t) * ld + c * 8, true);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int hh = warp / RG, rg = warp - hh * RG;
+  if (hh < H) {
+    const __nv_bfloat16* sQ = s + hh * D;
+    const __nv_bfloat16* sK = s + C + hh * D;
+    const __nv_bfloat16* sV = s + 2 * C + hh * D;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int a_row = rg * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;  // A operand (x4): rows 0-7 / 8-15, cols 0-7 / 8-15
+    const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;            // K tile (x4, non-trans)
+    const int v_row = (lane & 7) + ((lane >> 3) & 1) * 8, v_col = (lane >> 4) * 8;            // V tile (x4, trans)
+    const int x2_row = (lane & 7) + ((lane >> 3) & 1) * 8;                                    // x2 loads: matrices = rows 0-7, 8-15
+    float sc[T / 8][4];
+#pragma unroll
+    for (int i = 0; i < T / 8; ++i) sc[i][0] = sc[i][1] = sc[i][2] = sc[i][3] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      uint32_t a[4];
+      ldmatrix_x4(a, sQ + a_row * LDS + kt * 16 + a_col);
+#pragma unroll
+      for (int n2 = 0; n2 < T / 16; ++n2) {
+        uint32_t bb[4];
+        ldmatrix_x4(bb, sK + (n2 * 16 + b_row) * LDS + kt * 16 + b_col);
+        mma_bf16_16816(sc[2 * n2], a, bb[0], bb[1]);
+        mma_bf16_16816(sc[2 * n2 + 1], a, bb[2], bb[3]);
+      }
+    }
+    {  // features 64..71
+      uint32_t a2[2];
+      ldmatrix_x2(a2, sQ + (rg * 16 + x2_row) * LDS + 64);
+#pragma unroll
+      for (int n2 = 0; n2 < T / 16; ++n2) {
+        uint32_t b2[2];
+        ldmatrix_x2(b2, sK + (n2 * 16 + x2_row) * LDS + 64);
+        mma_bf16_1688(sc[2 * n2], a2, b2[0]);
+        mma_bf16_1688(sc[2 * n2 + 1], a2, b2[1]);
+      }
+    }
+    // softmax over the whole window (rows g and g + 8 of this warp's 16)
+    const float sl2 = scale * 1.4426950408889634f;
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < T / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], sc[nt][e]);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      mx[r] *= sl2;
+    }
+#pragma unroll
+    for (int nt = 0; nt < T / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sc[nt][e] = ex2_approx(fmaf(sc[nt][e], sl2, -mx[e >> 1]));
+        l[e >> 1] += sc[nt][e];
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+      l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+    }
+    // O = P V
+    float o[9][4];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int k2 = 0; k2 < T / 16; ++k2) {
+      uint32_t a[4];
+      a[0] = pack_bf16(sc[2 * k2][0], sc[2 * k2][1]);
+      a[1] = pack_bf16(sc[2 * k2][2], sc[2 * k2][3]);
+      a[2] = pack_bf16(sc[2 * k2 + 1][0], sc[2 * k2 + 1][1]);
+      a[3] = pack_bf16(sc[2 * k2 + 1][2], sc[2 * k2 + 1][3]);
+#pragma unroll
+      for (int d2 = 0; d2 < 4; ++d2) {
+        uint32_t bb[4];
+        ldmatrix_x4_trans(bb, sV + (k2 * 16 + v_row) * LDS + d2 * 16 + v_col);
+        mma_bf16_16816(o[2 * d2], a, bb[0], bb[1]);
+        mma_bf16_16816(o[2 * d2 + 1], a, bb[2], bb[3]);
+      }
+      uint32_t b2[2];
+      ldmatrix_x2_trans(b2, sV + (k2 * 16 + x2_row) * LDS + 64);
+      mma_bf16_16816(o[8], a, b2[0], b2[1]);
+    }
+    // normalised O over this warp's own Q slice (nobody else reads these rows x columns)
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float inv = 1.0f / l[r];
+      __nv_bfloat16* orow = s + (rg * 16 + g + r * 8) * LDS + hh * D;
+#pragma unroll
+      for (int nt = 0; nt < 9; ++nt) *reinterpret_cast<uint32_t*>(orow + nt * 8 + 2 * t4) = pack_bf16(o[nt][2 * r] * inv, o[nt][2 * r + 1] * inv);
+    }
+  }
+  __syncthreads();
+  const int cpo = C >> 3;
+  for (int i = tid; i < T * cpo; i += blockDim.x) {
+    const int t = i / cpo, c = i - t * cpo;
+    *reinterpret_cast<uint4*>(out + grow(t) * ldo + c * 8) = *reinterpret_cast<const uint4*>(s + t * LDS + c * 8);
+  }
+}
+
+// Returns VG_OK when the small-window kernel handled the call, VG_ENOSUP otherwise.
+static int window_attn_small_try(const VgAttention* a, cudaStream_t s) {
+  static const int enabled = [] { const char* e = getenv("VG_WIN_SMALL"); return e ? atoi(e) : 1; }();
+  if (!enabled || a->q_win == 0 || a->q_win != a->k_win || a->q_gridw != a->k_gridw || a->q_nwx != a->k_nwx || a->q_nwy != a->k_nwy) return VG_ENOSUP;
+  const int T = a->q_win * a->q_win;
+  if ((T != 16 && T != 64) || a->Nq != T || a->Nk != T || a->D != 72 || a->causal || a->window) return VG_ENOSUP;
+  const int warps = a->H * T / 16;
+  if (warps > 16) return VG_ENOSUP;
+  const long long C = static_cast<long long>(a->H) * a->D;
+  const __nv_bfloat16* q = static_cast<const __nv_bfloat16*>(a->q);
+  // q, k, v must be the three column blocks of one packed [rows, 3C] matrix; o rows must hold whole [H, D] outputs
+  if (static_cast<const __nv_bfloat16*>(a->k) != q + C || static_cast<const __nv_bfloat16*>(a->v) != q + 2 * C || a->q_hs != a->D || a->k_hs != a->D ||
+      a->v_hs != a->D || a->o_hs != a->D || a->q_rs != a->k_rs || a->q_rs != a->v_rs || (a->q_rs % 8) || (a->o_rs % 8) ||
+      (reinterpret_cast<uintptr_t>(a->o) & 15))
+    return VG_ENOSUP;
+  const int smem = T * (3 * static_cast<int>(C) + 8) * 2;
+  if (smem > 200 * 1024) return VG_ENOSUP;
+  auto kern = T == 16 ? window_attn_small_kernel<16> : window_attn_small_kernel<64>;
+  static bool attr[2] = {false, false};
+  if (!attr[T == 64]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return set_error(VG_ECUDA, "window attention smem attr: %s", cudaGetErrorString(e));
+    attr[T == 64] = true;
+  }
+  launch_k(kern, dim3(a->B), dim3(warps * 32), smem, s, q, a->q_rs, static_cast<__nv_bfloat16*>(a->o), a->o_rs, a->H, a->q_win, a->q_gridw, a->q_nwx,
+           a->scale);
+  count_launch();
+  return check_launch("window_attn_small_kernel");
+}
 
 // ---------------------------------------------------------------------------------------------- single-query attention (LLM decode)
 // HBM/L2-bound: one block per (head, batch); each warp walks 32-key groups: lane-per-key QK^T (no shuffles in the dot product),
@@ -676,6 +839,10 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
       count_launch();
     }
     return check_launch("attn_decode_kernel");
+  }
+  if (!a->force_legacy) {
+    const int wrc = window_attn_small_try(a, s);
+    if (wrc != VG_ENOSUP) return wrc;
   }
   if (!a->force_legacy) {  // tcgen05 path (large dense problems); falls through to the mma.sync kernel when not applicable
     int ns = 1, dpm = 128;

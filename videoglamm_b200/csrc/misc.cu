@@ -60,7 +60,7 @@ __global__ void norm_kernel(const void* x, int xdt, long long ldx, void* y, int 
 }
 
 // fp32-in fast path: one warp per row, 128-bit loads (lane owns float4 chunks lane, lane+32, ...), 64/128-bit stores
-template <int MAXC, bool XBF16 = false>
+template <int MAXC, bool XBF16 = false, bool GELU = false>
 __global__ void norm_vec_kernel(const void* __restrict__ xv, long long ldx, void* y, int ydt, long long ldy, const float* __restrict__ w,
                                 const float* __restrict__ b, int rows, int cols, float eps, int rms) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
@@ -104,6 +104,9 @@ __global__ void norm_vec_kernel(const void* __restrict__ xv, long long ldx, void
       if (b) {
         const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + c);
         o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      }
+      if (GELU) {
+        o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
       }
       if (ydt == VG_F32)
         *(reinterpret_cast<float4*>(reinterpret_cast<float*>(y) + static_cast<long long>(row) * ldy) + c) = o;
@@ -525,20 +528,35 @@ __global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim
 __global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
-  // one thread per (row, rotation pair): the angle (powf + sincosf, ~100 instructions) is computed once and reused for every head
+  // one thread per (row, group of 8 heads, rotation pair): the angle (powf + sincosf, ~100 instructions) is computed once per 8 heads, and the
+  // 16 loads of the group are issued before any arithmetic (a thread per element was compute-bound on the transcendental functions, a serial
+  // loop over all heads latency-bound)
+  constexpr int HG = 8;
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const int half = hd / 2;
-  if (i >= static_cast<long long>(rows) * half) return;
+  const int half = hd / 2, groups = (nheads + HG - 1) / HG;
+  if (i >= static_cast<long long>(rows) * groups * half) return;
   const int j = static_cast<int>(i % half);
-  const long long r = i / half;
+  const int hg = static_cast<int>((i / half) % groups);
+  const long long r = i / (static_cast<long long>(half) * groups);
   const float inv = powf(theta, -2.0f * j / hd);
   float sn, cs;
   sincosf(pos[r] * inv, &sn, &cs);
-  __nv_bfloat16* p = qkv + r * ld + j;
-  for (int hh = 0; hh < nheads; ++hh, p += hd) {
-    const float a = __bfloat162float(p[0]), b = __bfloat162float(p[half]);
-    p[0] = __float2bfloat16(a * cs - b * sn);
-    p[half] = __float2bfloat16(b * cs + a * sn);
+  __nv_bfloat16* p = qkv + r * ld + static_cast<long long>(hg) * HG * hd + j;
+  const int nh = min(HG, nheads - hg * HG);
+  float a[HG], b[HG];
+#pragma unroll
+  for (int u = 0; u < HG; ++u) {
+    if (u < nh) {
+      a[u] = __bfloat162float(p[u * hd]);
+      b[u] = __bfloat162float(p[u * hd + half]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < HG; ++u) {
+    if (u < nh) {
+      p[u * hd] = __float2bfloat16(a[u] * cs - b[u] * sn);
+      p[u * hd + half] = __float2bfloat16(b[u] * cs + a[u] * sn);
+    }
   }
 }
 
@@ -671,6 +689,35 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const void* x, int xdt, lo
     }
     if (lane == 0) out[row] = bi;
   }
+}
+
+// im2col for Conv2d(3x3, stride 2, pad 1) on a channels-last [n][h][w][cin] tensor -> bf16 [n*oh*ow][9*cin], column order (ky, kx, ci):
+// one thread per 8 consecutive channels of one tap (16-byte store). Feeds the tensor-core GEMM (the direct conv kernels are
+// parallelism-bound at 64 -> 256 channels: 238 us per launch for 1.2 GFLOP).
+__global__ void im2col3x3s2_cl_kernel(const void* x, int xdt, __nv_bfloat16* out, int n, int h, int w, int cin) {
+  pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
+  pdl_launch_dependents();
+  const int oh = h / 2, ow = w / 2, c8 = cin >> 3;
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(n) * oh * ow * 9 * c8;
+  if (i >= total) return;
+  const int cc = static_cast<int>(i % c8);
+  long long t = i / c8;
+  const int tap = static_cast<int>(t % 9);
+  const long long pix = t / 9;
+  const int ox = static_cast<int>(pix % ow), oy = static_cast<int>((pix / ow) % oh), img = static_cast<int>(pix / (static_cast<long long>(ow) * oh));
+  const int iy = 2 * oy - 1 + tap / 3, ix = 2 * ox - 1 + tap % 3;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (iy >= 0 && iy < h && ix >= 0 && ix < w) {
+    const long long src = ((static_cast<long long>(img) * h + iy) * w + ix) * cin + cc * 8;
+    if (xdt == VG_F32) {
+      const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + src), b = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + src + 4);
+      v = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    } else {
+      v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(x) + src);
+    }
+  }
+  *reinterpret_cast<uint4*>(out + pix * (9LL * cin) + tap * cin + cc * 8) = v;
 }
 
 }  // namespace vg
@@ -828,7 +875,7 @@ extern "C" int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int 
 
 extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
   if (!qkv || !pos || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_neox: bad argument");
-  launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * head_dim / 2, 128)), dim3(128), 0, STREAM, 
+  launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * ((n_heads_total + 7) / 8) * (head_dim / 2), 128)), dim3(128), 0, STREAM, 
       static_cast<__nv_bfloat16*>(qkv), ld, pos, rows, n_heads_total, head_dim, theta);
   count_launch();
   return check_launch("rope_neox_kernel");
@@ -874,4 +921,30 @@ extern "C" int vg_multimask_select(const float* masks, const float* iou, int n_o
   launch_k(multimask_select_kernel, dim3(n_obj), dim3(256), 0, STREAM, masks, iou, hw, delta, thresh, out_idx);
   count_launch();
   return check_launch("multimask_select_kernel");
+}
+
+extern "C" int vg_im2col3x3s2_cl(const void* x, int x_dtype, void* out, int n, int h, int w, int cin, void* stream) {
+  if (!x || !out || n <= 0 || (cin % 8) || (h % 2) || (w % 2)) return set_error(VG_EINVAL, "vg_im2col3x3s2_cl: cin must be a multiple of 8, h and w even");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return set_error(VG_EINVAL, "vg_im2col3x3s2_cl: 16-byte alignment");
+  const long long total = static_cast<long long>(n) * (h / 2) * (w / 2) * 9 * (cin / 8);
+  launch_k(im2col3x3s2_cl_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, STREAM, x, x_dtype, static_cast<__nv_bfloat16*>(out), n, h, w, cin);
+  count_launch();
+  return check_launch("im2col3x3s2_cl_kernel");
+}
+
+extern "C" int vg_layernorm_gelu(const float* x, long long ldx, void* y, int y_dtype, long long ldy, const float* w, const float* b, int rows, int cols,
+                                 float eps, void* stream) {
+  if (!x || !y || !w || !b || rows <= 0 || cols <= 0) return set_error(VG_EINVAL, "vg_layernorm_gelu: bad argument");
+  const int esz_y = y_dtype == VG_F32 ? 4 : 2;
+  if ((cols % 4) || (ldx % 4) || (ldy % 4) || cols > 128 * 5 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & (esz_y * 4 - 1)) ||
+      (reinterpret_cast<uintptr_t>(w) & 15) || (reinterpret_cast<uintptr_t>(b) & 15))
+    return set_error(VG_ENOSUP, "vg_layernorm_gelu: needs cols %% 4 == 0, cols <= 640 and 16-byte aligned rows");
+  const int warps = 8;
+  const unsigned grid = (rows + warps - 1) / warps;
+  if (cols <= 128 * 2)
+    launch_k(norm_vec_kernel<2, false, true>, dim3(grid), dim3(warps * 32), 0, STREAM, static_cast<const void*>(x), ldx, y, y_dtype, ldy, w, b, rows, cols, eps, 0);
+  else
+    launch_k(norm_vec_kernel<5, false, true>, dim3(grid), dim3(warps * 32), 0, STREAM, static_cast<const void*>(x), ldx, y, y_dtype, ldy, w, b, rows, cols, eps, 0);
+  count_launch();
+  return check_launch("norm_vec_kernel");
 }

@@ -376,3 +376,19 @@ def connected_components(mask: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor
     L.check(L.lib().vg_connected_components(_ptr(mask), _ptr(labels), _ptr(counts), n, h, w, _ptr(ws), C.c_longlong(ws.numel() * 4), _stream()),
             "vg_connected_components")
     return labels, counts
+
+
+def conv3x3s2_ln_gelu_gemm(x: torch.Tensor, w_gemm: torch.Tensor, bias, ln_w, ln_b, eps: float, n: int, h: int, wd: int, cin: int, cout: int,
+                           out_dtype=torch.float32) -> torch.Tensor:
+    """Conv2d(3x3, s2, p1) + LayerNorm2d + GELU on the tensor cores: channels-last im2col (bf16) -> GEMM (+bias, fp32) -> LayerNorm+GELU.
+    x [n*h*wd, cin] channels-last (cin % 8 == 0); w_gemm bf16 [cout, (ky,kx,ci)]."""
+    _require_cuda(x, w_gemm)
+    assert x.is_contiguous() and tuple(w_gemm.shape) == (cout, 9 * cin) and w_gemm.dtype == torch.bfloat16 and cin % 8 == 0
+    rows = n * (h // 2) * (wd // 2)
+    cols = torch.empty((rows, 9 * cin), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().vg_im2col3x3s2_cl(_ptr(x), _dt(x.dtype), _ptr(cols), n, h, wd, cin, _stream()), "vg_im2col3x3s2_cl")
+    g = gemm(cols, w_gemm, bias=bias, out_dtype=torch.float32)
+    y = torch.empty((rows, cout), device=x.device, dtype=out_dtype)
+    L.check(L.lib().vg_layernorm_gelu(_ptr(g), C.c_longlong(g.stride(0)), _ptr(y), _dt(y.dtype), C.c_longlong(y.stride(0)), _ptr(ln_w), _ptr(ln_b), rows, cout,
+                                      C.c_float(eps), _stream()), "vg_layernorm_gelu")
+    return y

@@ -148,6 +148,7 @@ class Sam2Engine:
         for j in range(4):
             wt = self._t(f"{me}.mask_downsampler.encoder.{3 * j}.weight")  # [cout, cin, 3, 3]
             self.ds.append(dict(w=wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]).contiguous(), b=self._t(f"{me}.mask_downsampler.encoder.{3 * j}.bias"),
+                                wg=wt.permute(0, 2, 3, 1).reshape(wt.shape[0], -1).to(BF).contiguous(),   # [cout, (ky,kx,ci)] for the GEMM path
                                 ln=self._ln(f"{me}.mask_downsampler.encoder.{3 * j + 1}"), cin=wt.shape[1], cout=wt.shape[0]))
         self.ds_out = self._lin(f"{me}.mask_downsampler.encoder.12")
         self.pix_proj = self._lin(me + ".pix_feat_proj")
@@ -338,8 +339,9 @@ class Sam2Engine:
         m = m.view(B * S * S, 1)
         side = S
         for j, d in enumerate(self.ds):
-            m = ops.conv3x3s2_ln_gelu(m, d["w"], d["b"], d["ln"][0], d["ln"][1], 1e-6, B, side, side, d["cin"], d["cout"],
-                                      out_dtype=BF if j == 3 else F32)
+            conv = ops.conv3x3s2_ln_gelu_gemm if d["cin"] >= 16 else ops.conv3x3s2_ln_gelu     # wide stages: im2col + tcgen05 GEMM
+            m = conv(m, d["wg"] if d["cin"] >= 16 else d["w"], d["b"], d["ln"][0], d["ln"][1], 1e-6, B, side, side, d["cin"], d["cout"],
+                     out_dtype=BF if j == 3 else F32)
             side //= 2
         m = ops.gemm(m, self.ds_out.w, bias=self.ds_out.b, out_dtype=F32)                                # [B*HW, C]
         px = ops.gemm(ops.cast(top, BF), self.pix_proj.w, bias=self.pix_proj.b, out_dtype=F32)           # [HW, C] shared by objects
