@@ -385,6 +385,33 @@ def test_rope_kv_append_and_fused_merge_decode_attention():
     assert int(ws[-H:].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("pos_val", [1500, 1535, 1536, 70])
+def test_decode_attention_with_fused_rope_and_append(pos_val):
+    """fused_rope_theta: RoPE(q), RoPE(k_new) + KV-cache append inside the decode attention kernel must be BIT-identical to
+    vg_rope_kv_append followed by the plain decode attention (outputs and the appended cache row)."""
+    H, hd, max_len = 8, 96, 2100
+    D = H * hd
+    cache0 = torch.randn(max_len, 3 * D, device=DEV).bfloat16()
+    row = torch.randn(1, 3 * D, device=DEV).bfloat16()
+    pos = torch.tensor([pos_val], device=DEV, dtype=torch.int32)
+    nk = torch.tensor([pos_val + 1], device=DEV, dtype=torch.int32)
+    ws = ops.decode_workspace(1, H, hd, DEV)
+    views = lambda c: (c[:2048, D:2 * D].unflatten(1, (H, hd))[None], c[:2048, 2 * D:].unflatten(1, (H, hd))[None])
+    # un-fused reference pipeline
+    c1, r1 = cache0.clone(), row.clone()
+    ops.rope_kv_append_(r1, c1, pos, H, hd, 10000.0)
+    k1, v1 = views(c1)
+    want = ops.attention(r1[:, :D].unflatten(1, (H, hd))[None], k1, v1, causal=True, nk_dev=nk, decode_ws=ws).clone()
+    # fused
+    c2, r2 = cache0.clone(), row.clone()
+    k2, v2 = views(c2)
+    for _ in range(2):
+        got = ops.attention(r2[:, :D].unflatten(1, (H, hd))[None], k2, v2, causal=True, nk_dev=nk, decode_ws=ws, fused_rope_theta=10000.0)
+        assert torch.equal(got, want)
+    assert torch.equal(c2, c1) and torch.equal(r2, row)          # cache row appended identically; the packed row itself is left un-rotated
+    assert int(ws[-H:].abs().sum()) == 0
+
+
 @pytest.mark.parametrize("cin,cout,hw", [(16, 64, 32), (64, 256, 16), (8, 24, 8)])
 def test_conv3x3s2_ln_gelu_gemm_path(cin, cout, hw):
     """MaskDownSampler wide stages through im2col (channels-last) + tcgen05 GEMM + LayerNorm/GELU kernel vs torch conv2d (bf16 operands)."""

@@ -25,6 +25,7 @@ struct AttnParams {
   int nsplit;
   const int* nk_dev;                 // optional: number of keys read from device memory (graph-replayable decode)
   int* counters;                     // optional [B*H] zeroed ints: the last split block of a (b,h) merges in-kernel (no merge launch)
+  float rope_theta;                  // > 0: decode step with fused RoPE + KV append (q = packed un-rotated [q|k|v] row of position Nk-1)
 };
 
 // row index inside the (batch-strided) tensor for token t of batch entry b
@@ -578,7 +579,24 @@ __global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
   const int k_hi = min(p.Nk, k_lo + span);
   const int chunks = p.D >> 3;  // 16-byte chunks per row
   float m_run = -INFINITY, l_run = 0.f, o0 = 0.f, o1 = 0.f;  // thread (kh = tid / 64, pr = tid % 64) accumulates feature pair pr over its key half
-  for (int d = tid; d < DMAX; d += 128) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
+  const int half = p.D >> 1;
+  if (p.rope_theta > 0.f) {
+    // fused RoPE: rotate-half at position Nk-1, same arithmetic as rope_kv_append_kernel / rope_neox_kernel
+    for (int d = tid; d < DMAX; d += 128) {
+      float v = 0.f;
+      if (d < p.D) {
+        const int j = d < half ? d : d - half;
+        float sn, cs;
+        sincosf((p.Nk - 1) * powf(p.rope_theta, -2.0f * j / p.D), &sn, &cs);
+        const float a = __bfloat162float(qp[j]), bq = __bfloat162float(qp[j + half]);
+        // the un-fused path rounds the rotated q to bf16 before the dot product: keep that rounding so both paths give identical logits
+        v = __bfloat162float(__float2bfloat16(d < half ? a * cs - bq * sn : bq * cs + a * sn)) * p.scale;
+      }
+      s_q[d] = v;
+    }
+  } else {
+    for (int d = tid; d < DMAX; d += 128) s_q[d] = d < p.D ? __bfloat162float(qp[d]) * p.scale : 0.f;
+  }
   for (int k0 = k_lo; k0 < k_hi; k0 += DEC2_KEYS) {
     const int n = min(DEC2_KEYS, k_hi - k0);
     __syncthreads();  // previous tile fully consumed (and s_q written)
@@ -592,6 +610,28 @@ __global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
+    if (p.rope_theta > 0.f && p.Nk - 1 >= k0 && p.Nk - 1 < k0 + n) {
+      // this block owns the newest position: its K/V row is not in the cache yet. Rotate k_new, take v_new from the packed row, use them
+      // from shared memory and append them to the cache for the following steps (exactly one block per head gets here).
+      const int rowi = p.Nk - 1 - k0;
+      const __nv_bfloat16* kn = qp + static_cast<long long>(p.H) * p.D;       // k_new of this head
+      const __nv_bfloat16* vn = qp + 2LL * p.H * p.D;                          // v_new of this head
+      __nv_bfloat16* kc = const_cast<__nv_bfloat16*>(kb) + static_cast<long long>(p.Nk - 1) * p.k_rs;
+      __nv_bfloat16* vc = const_cast<__nv_bfloat16*>(vb) + static_cast<long long>(p.Nk - 1) * p.v_rs;
+      for (int d = tid; d < p.D; d += 128) {
+        const int j = d < half ? d : d - half;
+        float sn, cs;
+        sincosf((p.Nk - 1) * powf(p.rope_theta, -2.0f * j / p.D), &sn, &cs);
+        const float a = __bfloat162float(kn[j]), bk = __bfloat162float(kn[j + half]);
+        const __nv_bfloat16 kr = __float2bfloat16(d < half ? a * cs - bk * sn : bk * cs + a * sn);
+        const __nv_bfloat16 vr = vn[d];
+        s_k[rowi * LDS + d] = kr;
+        s_v[rowi * LDS + d] = vr;
+        kc[d] = kr;
+        vc[d] = vr;
+      }
+      __syncthreads();
+    }
     // QK^T: two threads per key (feature halves), combined with one shuffle
     {
       const int key = tid >> 1, half = tid & 1;
@@ -804,11 +844,15 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   p.scale = a->scale; p.causal = a->causal; p.window = a->window;
   p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
   p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
-  p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev); p.counters = nullptr;
+  p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev); p.counters = nullptr; p.rope_theta = 0.f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->nk_dev != nullptr && a->Nq != 1) return set_error(VG_EINVAL, "vg_attention: nk_dev is only supported for single-query attention");
   if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && (a->Nk >= 256 || a->nk_dev != nullptr)) {  // decode: causal is a no-op for the newest query
     const int dmax = a->D <= 128 ? 128 : 256;
+    if (a->fused_rope_theta > 0.f) {
+      if (dmax != 128 || a->B != 1 || a->q_hs != a->D || (a->D % 2)) return set_error(VG_EINVAL, "vg_attention: fused RoPE/append needs B == 1, D <= 128, packed q row");
+      p.rope_theta = a->fused_rope_theta;
+    }
     int nsplit = 1;
     if (a->workspace != nullptr) {
       nsplit = dmax == 128 ? (a->Nk + DEC2_KEYS - 1) / DEC2_KEYS : (a->Nk + 255) / 256;

@@ -232,11 +232,12 @@ class LmmEngine:
         for l, L in enumerate(self.layers):
             cache = self.kv[l]
             ops.gemm(x, L["qkv"].w, out=self.dec_qkv, a_rms_eps=ph.eps)                       # input RMSNorm fused
-            ops.rope_kv_append_(self.dec_qkv, cache, self.dec_pos, H, hd, ph.rope_theta)       # RoPE(q,k) + cache append, one launch
             q = self.dec_qkv[:, :D].unflatten(1, (H, hd))[None]
             k = cache[:kv_bound, D:2 * D].unflatten(1, (H, hd))[None]
             v = cache[:kv_bound, 2 * D:].unflatten(1, (H, hd))[None]
-            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk, decode_ws=self.dec_ws)
+            # RoPE(q, k_new) and the KV-cache append happen inside the attention kernel (position = dec_nk - 1 = dec_pos)
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk, decode_ws=self.dec_ws,
+                              fused_rope_theta=ph.rope_theta)
             x = ops.gemm(o.view(1, D), L["o"].w, resid=x, out=x)
             h = ops.gemm(x, L["gu"], glu=True, act="silu", a_rms_eps=ph.eps)                   # post-attention RMSNorm fused
             x = ops.gemm(h, L["down"].w, resid=x, out=x)

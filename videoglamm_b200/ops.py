@@ -109,9 +109,11 @@ def gemm_profile(enable: bool):
         a[2] += fl
     top = sorted(by_shape.items(), key=lambda kv: -kv[1][1])[:40]
     tensor = [(k, v) for k, v in by_shape.items() if k[0] > 8]      # tcgen05 kernel; M <= 8 takes the weight-streaming (HBM-bound) kernel
+    big = [(k, v) for k, v in tensor if 2.0 * k[0] * k[1] * k[2] * k[3] >= 1e9]   # launches large enough for the tensor pipe to be the limiter
     skinny = [(k, v) for k, v in by_shape.items() if k[0] <= 8]
     return {"n": len(rec), "ms": sum(v[1] for v in by_shape.values()), "flops": sum(v[2] for v in by_shape.values()),
             "tensor": {"n": sum(v[0] for _, v in tensor), "ms": sum(v[1] for _, v in tensor), "flops": sum(v[2] for _, v in tensor)},
+            "tensor_big": {"n": sum(v[0] for _, v in big), "ms": sum(v[1] for _, v in big), "flops": sum(v[2] for _, v in big)},
             "skinny": {"n": sum(v[0] for _, v in skinny), "ms": sum(v[1] for _, v in skinny),
                        "weight_bytes": sum(v[0] * 2.0 * k[1] * k[2] * k[3] for k, v in skinny)},
             "top_shapes": [{"MNKB": list(k), "launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / max(v[1], 1e-9) / 1e9, 1)} for k, v in top]}
@@ -127,7 +129,8 @@ def launch_count_reset() -> None:
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float | None = None, causal: bool = False, window: int = 0,
               out: torch.Tensor | None = None, q_win: tuple | None = None, k_win: tuple | None = None,
-              nk_dev: torch.Tensor | None = None, decode_ws: torch.Tensor | None = None, legacy: bool = False) -> torch.Tensor:
+              nk_dev: torch.Tensor | None = None, decode_ws: torch.Tensor | None = None, legacy: bool = False,
+              fused_rope_theta: float = 0.0) -> torch.Tensor:
     """q [B,Nq,H,D], k/v [B,Nk,H,D] bf16 views (any strides with unit last stride) -> out [B,Nq,H,D] (contiguous unless given).
     q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
     un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
@@ -161,6 +164,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     if nk_dev is not None:
         assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
         a.nk_dev = nk_dev.data_ptr()
+    if fused_rope_theta:
+        assert Nq == 1 and B == 1 and q.stride(2) == D, "fused RoPE/append: q must be the packed [q|k|v] row of the newest token"
+        a.fused_rope_theta = float(fused_rope_theta)
     if q_win is None and not causal and Nq > 1 and Nk >= 2048 and B * H * ((Nq + 63) // 64) < 148:
         # few query tiles, many keys (SAM2 memory attention): split-K scratch for up to 8 partials
         dp = 32 if D <= 32 else 64 if D <= 64 else 80 if D <= 80 else 96 if D <= 96 else 128 if D <= 128 else 256
