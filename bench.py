@@ -247,7 +247,8 @@ def run_engine(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest-share tensor GEMM shape (Hiera stage-3 fc2, 32768 x 576 x 2304,
 # in-place fp32 residual) from the committed `ncu --set full` capture; algorithmic bytes of that launch: 151.0 (A) + 2.7 (W) + 75.5 (C read) +
 # 75.5 (C write) = 304.7 MB. Updated by hand when the capture is retaken (profiles/).
-NCU_TRAFFIC = {"kernel": "gemm_tcgen05_kernel 32768x576x2304 +resid", "dram_bytes": 571.7e6, "algorithmic_bytes": 304.7e6, "source": "profiles/r01_ncu_targets_d.md row 1"}
+NCU_TRAFFIC = {"kernel": "gemm_tcgen05_kernel<192> 32768x576x2304 +resid", "dram_bytes": 272.6e6, "algorithmic_bytes": 304.7e6,
+               "source": "profiles/r01_ncu_targets_final.md row 1 (229.2 MB read + 43.4 MB written; part of the in-place C update stays in L2)"}
 
 
 def time_decode_step(model, L: int, reps: int = 8) -> dict:

@@ -10,7 +10,8 @@ is taken from this run). Order (= ncu launch ids):
   7 attn  SAM2 memory attn     4096 q x 28700 keys, 1 head x 256 (split-K + merge = 2 launches)
   9 attn  Hiera global         8 imgs x 4096 tokens x 8 heads x 72
  10 attn  Hiera stage-3 window 128 windows x 256 tokens x 8 heads x 72
- 11 attn  Phi-3 decode         1 query x 1709 keys, 32 heads x 96
+ 11 attn  Hiera stage-2 window 8192 windows x 16 tokens x 4 heads x 72 (window_attn_small_kernel)
+ 12 attn  Phi-3 decode         1 query x 1709 keys, 32 heads x 96
 """
 import sys, torch
 sys.path.insert(0, ".")
@@ -50,6 +51,11 @@ q, k, v = (qkv[:, j * 576:(j + 1) * 576].unflatten(1, (8, 72)) for j in range(3)
 ops.attention(q.unflatten(0, (8, 4096)), k.unflatten(0, (8, 4096)), v.unflatten(0, (8, 4096)), scale=72 ** -0.5)
 torch.cuda.synchronize()
 ops.attention(q[None], k[None], v[None], scale=72 ** -0.5, q_win=(16, 64, 4, 4), k_win=(16, 64, 4, 4))
+torch.cuda.synchronize()
+# Hiera stage-2 windows: 8 imgs x 128x128 tokens, 4x4 windows, 4 heads x 72 (one block per window, all heads)
+qkv2 = torch.randn(8 * 128 * 128, 3 * 288, device=dev).bfloat16()
+q2, k2, v2 = (qkv2[:, j * 288:(j + 1) * 288].unflatten(1, (4, 72)) for j in range(3))
+ops.attention(q2[None], k2[None], v2[None], scale=72 ** -0.5, q_win=(4, 128, 32, 32), k_win=(4, 128, 32, 32))
 torch.cuda.synchronize()
 nk = torch.tensor([1709], device=dev, dtype=torch.int32)
 ws = ops.decode_workspace(1, H, hd, dev)
