@@ -99,13 +99,26 @@ class VideoGLaMMForCausalLM:
         if context_images is None or context_images[0] is None:
             raise NotImplementedError("still-image inputs (context_images=None, arch.py encode_images) are not on the video path")
         dev = self.device
+        # host-resident SAM2 frames (100 MB per 8-frame clip at 1024 px): start the transfer now on a side stream, it completes under the LMM stage
+        sam_in, copy_done = images_for_sam[0], None
+        if not sam_in.is_cuda:
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(self._copy_stream):
+                sam_in = sam_in.to(dev, non_blocking=True)
+                copy_done = torch.cuda.Event()
+                copy_done.record(self._copy_stream)
         out_ids, emb = self.lmm.generate(input_ids.to(dev), images[0].to(dev, torch.float32), context_images[0].to(dev, torch.float32),
                                          max_new_tokens, eos_ids=tuple(self.config.eos_token_id), forced=forced_tokens)
         if emb.shape[0] == 0:
             return out_ids, [{}]                                                     # VideoGLaMM.py:840-842
         H, W = original_size_list[0]
         run = self.sam.run_video if use_sam2_video_branch else self.sam.run_framewise      # VideoGLaMM.py:576-596 dispatch
-        frames = run(images_for_sam[0].to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
+        if copy_done is not None:
+            torch.cuda.current_stream(dev).wait_event(copy_done)
+            sam_in.record_stream(torch.cuda.current_stream(dev))
+        frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
         stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)                 # ONE device->host copy per clip
         segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}
         return out_ids, [segs]

@@ -17,6 +17,7 @@ class ClipPipeline:
         self.depth = depth
         self.s_lmm = torch.cuda.Stream(device=model.device)
         self.s_sam = torch.cuda.Stream(device=model.device)
+        self.s_copy = torch.cuda.Stream(device=model.device)   # host -> device prefetch of the SAM2 frames (100 MB per clip at 1024 px)
 
     @torch.no_grad()
     def run(self, clips: list[dict], max_new_tokens: int, forced_tokens: dict | None = None) -> list[tuple]:
@@ -33,6 +34,14 @@ class ClipPipeline:
                 torch.cuda.set_device(dev)
                 with torch.cuda.stream(self.s_lmm):
                     for i, c in enumerate(clips):
+                        # the SAM2 frames of this clip are not needed before its LMM stage is over: copy them on their own stream now, so
+                        # the transfer runs under this clip's LMM kernels instead of in front of its SAM2 stage
+                        sam_dev, ev_copy = c["images_for_sam"], None
+                        if not sam_dev.is_cuda:
+                            with torch.cuda.stream(self.s_copy):
+                                sam_dev = sam_dev.to(dev, non_blocking=True)
+                                ev_copy = torch.cuda.Event()
+                                ev_copy.record(self.s_copy)
                         ids = c["input_ids"].to(dev, non_blocking=True)
                         out_ids, emb = m.lmm.generate(ids, c["images"].to(dev, torch.float32, non_blocking=True),
                                                       c["context_images"].to(dev, torch.float32, non_blocking=True), max_new_tokens,
@@ -41,7 +50,7 @@ class ClipPipeline:
                         emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
                         ev = torch.cuda.Event()
                         ev.record(self.s_lmm)
-                        q.put((i, out_ids, emb, ev))
+                        q.put((i, out_ids, emb, ev, sam_dev, ev_copy))
             except Exception as e:  # surface, don't swallow (the reference's eval loops silently skip failures)
                 errors.append(e)
             finally:
@@ -55,13 +64,16 @@ class ClipPipeline:
                         item = q.get()
                         if item is None:
                             return
-                        i, out_ids, emb, ev = item
+                        i, out_ids, emb, ev, sam_dev, ev_copy = item
                         self.s_sam.wait_event(ev)
+                        if ev_copy is not None:
+                            self.s_sam.wait_event(ev_copy)
+                            sam_dev.record_stream(self.s_sam)
                         if emb.shape[0] == 0:
                             results[i] = (out_ids, {})
                             continue
                         H, W = clips[i]["original_size"]
-                        frames = m.sam.run_video(clips[i]["images_for_sam"].to(dev, non_blocking=True), emb[:, None, :], (int(H), int(W)), binary=True)
+                        frames = m.sam.run_video(sam_dev, emb[:, None, :], (int(H), int(W)), binary=True)
                         stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)
                         results[i] = (out_ids, {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])})
             except Exception as e:
@@ -72,11 +84,13 @@ class ClipPipeline:
         cur = torch.cuda.current_stream(dev)
         self.s_lmm.wait_stream(cur)
         self.s_sam.wait_stream(cur)
+        self.s_copy.wait_stream(cur)
         ta, tb = threading.Thread(target=lmm_stage), threading.Thread(target=sam_stage)
         ta.start(); tb.start()
         ta.join(); tb.join()
         cur.wait_stream(self.s_lmm)
         cur.wait_stream(self.s_sam)
+        cur.wait_stream(self.s_copy)
         if errors:
             raise errors[0]
         return results
