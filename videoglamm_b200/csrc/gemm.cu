@@ -19,17 +19,24 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
-template <int BN>
+// EPI2: two staging boxes per epilogue warp (the bulk store of chunk i is still reading its box while chunk i+1 is computed), paid for with
+// one pipeline stage where shared memory is short. Used for the small-K GEMMs, which are bound by the epilogue: with ONE box every chunk waited
+// for the previous store to finish reading (measured: ~2.5-3 output elements/clk/SM whatever the activation, 2-3x the MMA time at K = 576).
+template <int BN, bool EPI2 = false>
 struct GemmCfg {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 192 ? 4 : (BN >= 96 ? 6 : 8));
-  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulator stages
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages; allocations are powers of two (128/256/512)
-  static constexpr int STAGING_BYTES = 8 * 4096;             // per epilogue warp: one 32-row TMA-store box (<= 128 B per row)
+  static constexpr int STG_PER_WARP = EPI2 ? 2 * 4096 : 4096;  // per epilogue warp: 32-row TMA-store boxes (<= 128 B per row)
+  static constexpr int STAGING_BYTES = 8 * STG_PER_WARP;
   static constexpr int VEC_BYTES = 2 /*acc stages*/ * BN * 4;  // bias of the tile being drained
+  static constexpr int STAGES_WANT = BN == 256 ? 4 : (BN == 192 ? 4 : (BN >= 96 ? 6 : 8));
+  static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - VEC_BYTES - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_WANT < STAGES_FIT ? STAGES_WANT : STAGES_FIT;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 256 /*barriers*/;  // base is 1024-aligned (checked)
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
 struct GemmParams {
@@ -50,6 +57,7 @@ struct GemmParams {
   int b_shared;  // B (weights) shared by every batch entry
   int use_tma_store;  // C leaves through per-warp smem boxes + bulk tensor stores
   int tma_reduce;     // residual aliases C: TMA reduce-add instead of load + add + store
+  int backoff_ns;     // > 0: the single-lane control warps sleep between mbarrier polls (their spin loops compete with the epilogue warps for issue slots)
 };
 
 // Activations for the epilogues. ncu (profiles/r01_ncu_targets_d.md) showed the small-K GEMMs issue-bound in the epilogue warps at ~35
@@ -116,11 +124,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
-template <int BN>
+template <int BN, bool EPI2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EPI2>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023) != 0) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base
   uint8_t* sA = smem;
@@ -184,7 +192,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int n_blk = p.n_fastest ? r % p.tiles_n : r / p.tiles_m;
         const int m_blk = p.n_fastest ? r / p.tiles_n : r - n_blk * p.tiles_m;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          while (!mbar_try_wait(&empty_bar[stage], phase ^ 1)) {
+            if (p.backoff_ns) __nanosleep(p.backoff_ns);
+          }
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_3d(&tmA, &full_bar[stage], sA + stage * Cfg::A_BYTES, kb * BLOCK_K, m_blk * BLOCK_M, b);
           tma_load_3d(&tmB, &full_bar[stage], sB + stage * Cfg::B_BYTES, kb * BLOCK_K, n_blk * BN, p.b_shared ? 0 : b);
@@ -204,7 +214,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        while (!mbar_try_wait(&tempty_bar[acc], acc_phase ^ 1)) {
+          if (p.backoff_ns) __nanosleep(p.backoff_ns);
+        }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
         for (int kb = 0; kb < num_k; ++kb) {
@@ -243,7 +255,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     const int n_out = p.glu ? p.N / 2 : p.N;
     const bool unit_alpha = p.alpha == 1.0f;
-    uint8_t* stg = staging + (warp - 4) * 4096;
+    uint8_t* stg_base = staging + (warp - 4) * Cfg::STG_PER_WARP;
+    int box = 0;  // which of this warp's staging boxes the next chunk uses (EPI2)
     const int esz = p.out_f32 ? 4 : 2;
     const int nvals_c = p.glu ? 16 : 32;
     const int row_bytes = nvals_c * esz;                         // 128 / 64 / 32: equals the TMA swizzle span
@@ -336,7 +349,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.use_tma_store) {
           // the previous bulk store of this warp must have finished READING the staging box before it is overwritten
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          uint8_t* stg = stg_base + (EPI2 ? box * 4096 : 0);
+          if (EPI2) {
+            box ^= 1;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued two chunks ago has read this box
+          } else {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
           __syncwarp();
           uint8_t* srow = stg + lane * row_bytes;
           if (p.out_f32) {
@@ -744,7 +763,7 @@ static int check_gemm(const VgGemm* g) {
 static GemmParams to_params(const VgGemm* g) {
   GemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.batch = g->batch;
-  p.tiles_m = 0; p.tiles_n = 0;
+  p.tiles_m = 0; p.tiles_n = 0; p.n_fastest = 0; p.backoff_ns = 0;
   p.C = g->C; p.ldc = g->ldc; p.strideC = g->strideC;
   p.out_f32 = g->out_dtype == VG_F32;
   p.bias = g->bias; p.strideBias = g->strideBias; p.act = g->act; p.glu = g->glu; p.col_scale = g->col_scale;
@@ -756,12 +775,12 @@ static GemmParams to_params(const VgGemm* g) {
   return p;
 }
 
-template <int BN>
-static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+template <int BN, bool EPI2>
+static int launch_gemm_cfg(const VgGemm* g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, EPI2>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(VG_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -776,6 +795,8 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   // Tile order: the operand that does NOT fit the concurrent working set should be swept once. A (M x K) bigger than W (N x K): the N
   // tiles of one M stripe are adjacent, so A is read from HBM once and W stays in L2 (ncu: fc2 32768x576x2304 read 501 MB instead of 226).
   p.n_fastest = (static_cast<long long>(g->M) * g->batch > g->N && p.tiles_n > 1) ? 1 : 0;
+  static const int backoff = [] { const char* e = getenv("VG_GEMM_BACKOFF"); return e ? atoi(e) : 0; }();
+  p.backoff_ns = backoff;
   // Output path: bulk tensor stores need a 16-byte aligned base and 16-byte multiple strides. A residual that aliases the output
   // (the in-place residual-stream update every transformer block does) becomes a TMA reduce-add; any other residual is added in registers.
   const int esz = g->out_dtype == VG_F32 ? 4 : 2;
@@ -791,9 +812,18 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
   }
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * g->batch;
   const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  launch_k(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p);
+  launch_k(gemm_tcgen05_kernel<BN, EPI2>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tcgen05_kernel");
+}
+
+// Small-K problems are bound by the epilogue (store latency per 32-column chunk), large-K ones by the main loop: pick the staging / pipeline
+// split accordingly. VG_GEMM_EPI2=1 enables the two-box configuration (A/B timing; off by default, see profiles/r01_gemm_epilogue.md).
+template <int BN>
+static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
+  static const int epi2 = [] { const char* e = getenv("VG_GEMM_EPI2"); return e ? atoi(e) : 0; }();  // measured: no gain (profiles/r01_gemm_epilogue.md)
+  if (epi2 && g->K <= 1024) return launch_gemm_cfg<BN, true>(g, stream);
+  return launch_gemm_cfg<BN, false>(g, stream);
 }
 
 }  // namespace vg
