@@ -87,6 +87,16 @@ class VideoGLaMMForCausalLM:
     def get_model(self):
         return self
 
+    def resize_token_embeddings(self, n: int):
+        """chat.py:300 calls this after adding `[SEG]`; exported checkpoints already carry the resized matrices, so only the size is checked."""
+        if n > self.lmm_cfg.phi.vocab:
+            raise ValueError(f"tokenizer has {n} tokens, the packed lm_head/embeddings have {self.lmm_cfg.phi.vocab}")
+        return self
+
+    def _eos_ids(self) -> tuple:
+        e = getattr(self.config, "eos_token_id", ())
+        return tuple(e) if isinstance(e, (list, tuple)) else (() if e is None else (int(e),))
+
     # ---- inference -------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def inference(self, images, context_images, images_for_sam, input_ids, resize_list, original_size_list, max_new_tokens: int = 32,
@@ -110,7 +120,7 @@ class VideoGLaMMForCausalLM:
                 copy_done = torch.cuda.Event()
                 copy_done.record(self._copy_stream)
         out_ids, emb = self.lmm.generate(input_ids.to(dev), images[0].to(dev, torch.float32), context_images[0].to(dev, torch.float32),
-                                         max_new_tokens, eos_ids=tuple(self.config.eos_token_id), forced=forced_tokens)
+                                         max_new_tokens, eos_ids=self._eos_ids(), forced=forced_tokens)
         if emb.shape[0] == 0:
             return out_ids, [{}]                                                     # VideoGLaMM.py:840-842
         H, W = original_size_list[0]

@@ -45,7 +45,7 @@ class ClipPipeline:
                         ids = c["input_ids"].to(dev, non_blocking=True)
                         out_ids, emb = m.lmm.generate(ids, c["images"].to(dev, torch.float32, non_blocking=True),
                                                       c["context_images"].to(dev, torch.float32, non_blocking=True), max_new_tokens,
-                                                      eos_ids=tuple(m.config.eos_token_id), forced=forced_tokens)
+                                                      eos_ids=m._eos_ids(), forced=forced_tokens)
                         emb = emb.clone()
                         emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
                         ev = torch.cuda.Event()
