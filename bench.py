@@ -221,7 +221,7 @@ def run_engine(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip with >= 1 GFLOP: "
                          f"{tp['n']} launches carrying {tp['flops'] / max(tall['flops'], 1):.1%} of the GEMM FLOPs)", "achieved": ach, "peak": tf_peak,
-                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": NCU_TRAFFIC, "peak_source": f"{src} bf16_tflops_sustained",
+                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": NCU_TRAFFIC["dram_bytes"], "traffic_detail": NCU_TRAFFIC, "peak_source": f"{src} bf16_tflops_sustained",
                          "launches": tp["n"], "gemm_ms_per_clip": tp["ms"], "gemm_share_of_step": tp["ms"] / (ms / args.steps),
                          "all_tensor_gemm_launches": {"launches": tall["n"], "ms_per_clip": tall["ms"], "achieved": ach_all, "frac": ach_all / tf_peak,
                                                       "note": "includes ~700 sub-GFLOP launches whose event-timed duration is launch latency"},
