@@ -1,12 +1,15 @@
 // tcgen05 flash attention (sm_100a): S = Q K^T and O += P V on the 5th-gen tensor cores with accumulators in TMEM.
-//   warp 0 (1 lane)  TMA producer: Q tile once, K/V tiles through a 2-stage ring (4D tensor maps over the strided q/k/v views,
-//                    head-dim tail zero-filled by TMA out-of-bounds handling, SWIZZLE_128B)
-//   warp 1 (1 lane)  MMA issuer:   S[128 x BN] = Q K^T (both K-major);  O[128 x Dp] += P V (P K-major from smem, V MN-major)
+//   warp 0 (1 lane)  TMA producer: Q tile once, then the K ring     warp 3 (1 lane)  TMA producer: V ring   (4D tensor maps over the strided
+//                    q/k/v views — linear rows or Hiera 16x16 windows as {D, H, x, y} boxes —, head-dim tail zero-filled by TMA, SWIZZLE_128B)
+//   warp 1 (1 lane)  MMA issuer, order QK(0), QK(1), PV(0), QK(2), PV(1), ...: S is double-buffered in TMEM, so the softmax of tile j never waits
+//                    for a QK^T and PV(j) runs under the softmax of tile j+1. S[128 x BN] = Q K^T (both K-major); O[128 x Dp] += P V (P K-major
+//                    from smem, V MN-major)
 //   warp 2           TMEM allocator
-//   warps 4..7       softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S, masks, online max with LAZY rescaling of O
-//                    (O is only rescaled in TMEM when a row max grows by more than 2^8), P -> bf16 -> swizzled smem, final O / l.
+//   warps 4..7       softmax: thread r owns query row r (TMEM lane r): tcgen05.ld S, masks (boundary tiles only), online max with LAZY rescaling
+//                    of O (O is only rescaled in TMEM when a row max grows by more than 2^8), P -> bf16 -> swizzled smem, final O / l.
+// 64-key tiles; when O needs <= 128 TMEM columns the block allocates 256 columns and ~112 KB of shared memory so that TWO blocks share an SM.
 // Optional split-K over keys for problems with few query tiles (SAM2 memory attention: 4096 queries x <= 28.7k keys, 1 head).
-// Version 1 is serial per key tile (QK^T -> softmax -> PV); S/P double-buffering is the next step.
+// History and measurements of the variants: profiles/r01_attention.md.
 #include <mutex>
 #include <unordered_map>
 
