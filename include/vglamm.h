@@ -139,9 +139,9 @@ int vg_upsample2x_add(const float* lat, const float* top, float* out, int n, int
  * then GELU. (mask_decoder.py:221-225) */
 int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bias, const void* feat, int feat_dtype, const float* ln_w,
                          const float* ln_b, float eps, void* out, int out_dtype, int n, int h, int w, int cout, int feat_bcast, void* stream);
-/* im2col for Conv2d(kernel k, stride s, pad p) on NCHW fp32/bf16 input -> bf16 [n*oh*ow][kpad], column order (ci,ky,kx),
+/* im2col for Conv2d(kernel k, stride s, pad p) on NCHW fp32/bf16 input -> bf16 (or fp32) [n*oh*ow][kpad], column order (ci,ky,kx),
  * zero-filled to kpad (multiple of 8). Patch embeddings: Hiera 7x7/4 (backbones/utils.py:65-95), CLIP 14x14/14, IV2 1x14x14. */
-int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
+int vg_im2col(const void* x, int x_dtype, void* out, int out_dtype, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
               void* stream);
 /* Depthwise KxK conv, stride 1, pad K/2, channels-last [n][h][w][c]; weight [c][K][K] fp32 (CXBlock.dwconv, memory_encoder.py:62-118). */
 int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, void* y, int y_dtype, int n, int h, int wd, int c, int k,
@@ -161,13 +161,13 @@ int vg_layernorm_gelu(const float* x, long long ldx, void* y, int y_dtype, long 
  * mode 0: identity; 1: sigmoid(x)*scale+bias; 2: (x>0)*scale+bias (sam2_base.py:366-374, 687-697; sam2_video_predictor.py:498-518);
  * mode 3: write uint8 (x > 0) instead of fp32 (VideoGLaMM.py:870-875). */
 int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream);
-/* 2D axial RoPE on rows of a [rows][ld] bf16 tensor, in place: row r has grid position (r % gw, (r / gw) % gh); the first
+/* 2D axial RoPE on rows of a [rows][ld] bf16 / fp32 tensor, in place: row r has grid position (r % gw, (r / gw) % gh); the first
  * dim/2 features rotate with x, the rest with y, consecutive (even,odd) pairs are one complex number
  * (position_encoding.py:174-216). Rows [0, nrows). theta 10000. */
-int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* stream);
-/* Phi-3 / Llama rotate-half RoPE in place on q and k slices of a packed qkv tensor [rows][ld] (bf16): for each head, pairs (i, i+hd/2).
+int vg_rope2d(void* x, int x_dtype, long long ld, int nrows, int dim, int gw, int gh, void* stream);
+/* Phi-3 / Llama rotate-half RoPE in place on q and k slices of a packed qkv tensor [rows][ld] (bf16 / fp32): for each head, pairs (i, i+hd/2).
  * pos[r] is the position of row r. */
-int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream);
+int vg_rope_neox(void* qkv, int x_dtype, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream);
 /* out[r][:] = table[ids[r]][:] (nn.Embedding), bf16 table -> out dtype */
 int vg_embedding(const void* table, long long ldt, const long long* ids, void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
 /* cache[*pos_dev][col0 : col0+cols] = src[0][col0 : col0+cols] for a bf16 row (KV-cache append at a device-side position, so that
@@ -190,6 +190,20 @@ void vg_launch_count_add(long long n);
  * `stream`, errors are return codes (the reference raises through AT_ASSERTM). */
 int vg_connected_components(const unsigned char* mask, int* labels, int* counts, int n, int h, int w, void* workspace, long long workspace_bytes,
                             void* stream);
+/* ------------------------------------------------------------------------------------------------ fp32-grade arithmetic
+ * The mask logits are sensitive to the rounding of the mask decoder's operands (north_star: 1e-3 on mask logits; bf16 operands give ~5e-3,
+ * scripts/precision_study.py), so its contractions run as split-bf16 GEMMs and its small attentions in exact fp32:
+ * vg_split3: x fp32 [rows][ldx] (cols used) -> bf16 [rows][ldo >= 3*kp]: columns [0,kp) = hi = bf16(x), then (A side, b_side=0) lo = bf16(x - hi), hi
+ * or (B side, b_side=1) hi, lo; columns [cols,kp) of each third are zero (kp % 8 == 0). One vg_gemm over K' = 3*kp on an A-side and a B-side
+ * operand computes A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation (relative error ~2^-17).
+ * Replaces (at fp32 fidelity) the nn.Linear / ConvTranspose2d / hyper_in @ upscaled contractions of .../sam2/modeling/sam/mask_decoder.py:167-245,
+ * .../sam/transformer.py:160-260. */
+int vg_split3(const float* x, long long ldx, void* out, long long ldo, long long rows, int cols, int kp, int b_side, void* stream);
+/* vg_attention with fp32 q/k/v/o (same struct, strides in fp32 elements; no alignment requirement; D <= 256): exact fp32 softmax(scale QK^T)V with
+ * online softmax, expf and FMA accumulation; optional split over keys through `workspace` (ns*B*H*Nq*(D+2)*4 bytes) for few-query problems.
+ * Product path: the two-way transformer's attentions (.../sam/transformer.py:233-260: 9x9, 9x4096, 4096x9 tokens). Verification mode: every
+ * attention of the path (causal, sliding window and Hiera 2D windows supported; nk_dev / fused_rope_theta are not). */
+int vg_attention_f32(const VgAttention* a, void* stream);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

@@ -135,11 +135,28 @@ def ref_videoglamm(workdir=None):
     return ref, sd, ocfg, scfg
 
 
-def ref_e2e_run(ref):
+def ref_e2e_run(ref, with_logits=False):
+    """One call of the reference's inference(). with_logits: also records the fp32 video-resolution mask logits that propagate_in_video yields
+    (the tensors the reference thresholds at VideoGLaMM.py:870-875) by wrapping the predictor's generator — the reference code itself is untouched."""
     images, ctx, sam, ids = e2e_inputs()
-    with torch.no_grad():
-        out_ids, segs = ref.inference([images], [ctx], [sam], ids[None], None, [E2E_HW], max_new_tokens=E2E_NEW, use_sam2_video_branch=True)
+    seen = []
+    vm = ref.model.visual_model
+    orig = vm.propagate_in_video
+
+    def recording(*a, **k):
+        for fi, obj_ids, m in orig(*a, **k):
+            seen.append(m.detach().float().clone())
+            yield fi, obj_ids, m
+
+    vm.propagate_in_video = recording
+    try:
+        with torch.no_grad():
+            out_ids, segs = ref.inference([images], [ctx], [sam], ids[None], None, [E2E_HW], max_new_tokens=E2E_NEW, use_sam2_video_branch=True)
+    finally:
+        vm.propagate_in_video = orig
     masks = np.stack([np.stack([segs[0][t][o] for o in sorted(segs[0][t])]) for t in sorted(segs[0])])  # [T, n_obj, H, W] bool
+    if with_logits:
+        return out_ids[0].numpy(), masks, torch.stack(seen)[:, :, 0].numpy()                            # logits [T, n_obj, H, W] fp32
     return out_ids[0].numpy(), masks
 
 
@@ -148,9 +165,11 @@ def e2e_golden():
     composition (splice, greedy generate with use_cache=False, [SEG] mask shift, text_hidden_fcs gather, per-object add_new_text, propagate,
     threshold). Two forced [SEG] tokens -> two objects."""
     ref, *_ = ref_videoglamm()
-    out_ids, masks = ref_e2e_run(ref)
-    np.savez_compressed(os.path.join(OUT, "e2e_tiny.npz"), output_ids=out_ids, masks=np.packbits(masks, axis=-1), mask_shape=np.array(masks.shape))
-    print("e2e_tiny", out_ids.tolist(), masks.shape, masks.mean())
+    out_ids, masks, logits = ref_e2e_run(ref, with_logits=True)
+    assert np.array_equal(logits > 0, masks)
+    np.savez_compressed(os.path.join(OUT, "e2e_tiny.npz"), output_ids=out_ids, masks=np.packbits(masks, axis=-1), mask_shape=np.array(masks.shape),
+                        logits=logits.astype(np.float32))
+    print("e2e_tiny", out_ids.tolist(), masks.shape, masks.mean(), "logits rms", float(np.sqrt((logits ** 2).mean())))
 
 
 if __name__ == "__main__":

@@ -109,7 +109,9 @@ def sdpa_ref(q, k, v, scale, causal=False, window=0):
     (1, 32, 333, 333, 96, True, 0), (1, 4, 1, 500, 96, True, 0), (1, 4, 700, 700, 96, True, 128), (2, 1, 256, 1100, 256, False, 0),
     (3, 8, 9, 4096, 16, False, 0), (3, 8, 4096, 9, 16, False, 0), (2, 8, 9, 9, 32, False, 0), (1, 2, 130, 70, 128, False, 0),
     (1, 1, 4096, 8300, 256, False, 0), (2, 2, 300, 5000, 64, False, 0), (1, 1, 70, 2049, 96, False, 0),  # these three: split-K over keys
-    (1, 32, 1696, 1696, 96, True, 2047)])  # Phi-3 prefill: the sliding window never cuts -> tcgen05 causal path
+    (1, 32, 1696, 1696, 96, True, 2047),   # Phi-3 prefill: the sliding window never cuts -> tcgen05 causal path
+    (1, 32, 3378, 3378, 96, True, 2047),   # C4/C5 prefill (L > 2047): the band cuts -> tcgen05 kernel with band-edge masking
+    (1, 4, 1000, 1000, 96, True, 300), (1, 2, 200, 1500, 64, True, 64), (1, 4, 700, 700, 96, True, 127)])   # narrow bands, Nq != Nk
 def test_attention(B, H, Nq, Nk, D, causal, window):
     q = torch.randn(B, Nq, H, D, device=DEV).bfloat16()
     k = torch.randn(B, Nk, H, D, device=DEV).bfloat16()
@@ -429,3 +431,77 @@ def test_conv3x3s2_ln_gelu_gemm_path(cin, cout, hw):
     yb = ops.conv3x3s2_ln_gelu_gemm(xcl, W.permute(0, 2, 3, 1).reshape(cout, 9 * cin).bfloat16().contiguous(), b, lw, lb, 1e-6, n, hw, hw, cin, cout,
                                     out_dtype=torch.bfloat16)
     assert rel(yb, ref) < 4e-3
+
+
+# ---------------------------------------------------------------------------------------------------- fp32-grade ops (csrc/precise.cu)
+@pytest.mark.parametrize("M,N,K", [(9, 256, 256), (4096, 128, 256), (4096, 256, 256), (1, 256, 256), (300, 2048, 256), (16384, 128, 64), (77, 40, 52)])
+def test_split_bf16_gemm_is_fp32_grade(M, N, K):
+    """vg_split3 + vg_gemm over K' = 3K: A_hi B_hi + A_lo B_hi + A_hi B_lo with fp32 accumulation vs an fp64 reference (error ~2^-17 relative)."""
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    bias = torch.randn(N, device=DEV)
+    y = ops.gemm(a, ops.W3(w), bias=bias, out_dtype=torch.float32)
+    ref = (a.double() @ w.double().T + bias.double()).float()
+    assert rel(y, ref) < 2e-5, rel(y, ref)
+    assert rel(ops.gemm(a.bfloat16(), w.bfloat16(), bias=bias, out_dtype=torch.float32), ref) > 1e-3   # what the split buys
+
+
+def test_split_bf16_gemm_batched_activation_operand_and_epilogues():
+    B, M, N, K = 3, 4, 5000, 32
+    a, w = torch.randn(B, M, K, device=DEV), torch.randn(B, N, K, device=DEV)
+    y = ops.gemm3(a, w, out_dtype=torch.float32)                       # hyper_in @ upscaled: both operands are activations
+    assert rel(y, torch.bmm(a.double(), w.double().transpose(1, 2)).float()) < 2e-5
+    x = torch.randn(200, 256, device=DEV)
+    w1, w2 = torch.randn(512, 256, device=DEV) / 16, torch.randn(256, 512, device=DEV) / 22
+    h = ops.gemm(x, ops.W3(w1), act="relu", out_dtype=torch.float32)
+    y = ops.gemm(h, ops.W3(w2), resid=x, out=x.clone(), out_dtype=torch.float32)
+    ref = (x.double() + torch.relu(x.double() @ w1.double().T) @ w2.double().T).float()
+    assert rel(y, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,Nq,Nk,D,causal,window", [
+    (2, 8, 9, 4096, 16, False, 0),      # mask decoder token -> image (split over keys)
+    (2, 8, 4096, 9, 16, False, 0),      # image -> token
+    (3, 8, 9, 9, 32, False, 0),         # token self-attention
+    (1, 1, 256, 1856, 256, False, 0),   # memory attention (tiny test geometry)
+    (1, 4, 300, 300, 96, True, 0), (1, 4, 300, 300, 32, True, 100), (1, 4, 1, 333, 96, True, 0), (1, 2, 50, 210, 72, True, 64)])
+def test_attention_exact_fp32(B, H, Nq, Nk, D, causal, window):
+    q, k, v = torch.randn(B, Nq, H, D, device=DEV), torch.randn(B, Nk, H, D, device=DEV), torch.randn(B, Nk, H, D, device=DEV)
+    o = ops.attention(q, k, v, causal=causal, window=window)
+    assert o.dtype == torch.float32
+    assert rel(o, sdpa_ref(q, k, v, D ** -0.5, causal, window)) < 5e-6
+
+
+@pytest.mark.parametrize("pooled", [False, True])
+def test_attention_exact_fp32_hiera_windows(pooled):
+    n_img, gh, gw, win, H, D = 2, 16, 24, 8, 2, 72
+    qkv = torch.randn(n_img * gh * gw, 3, H, D, device=DEV)
+    q, k, v = qkv.unbind(1)
+    nwy, nwx = gh // win, gw // win
+
+    def part(t, g_h, g_w, ws):
+        t = t.reshape(n_img, g_h // ws, ws, g_w // ws, ws, H, D).permute(0, 1, 3, 2, 4, 5, 6)
+        return t.reshape(-1, ws * ws, H, D)
+
+    if pooled:
+        qp = F.max_pool2d(q.reshape(n_img, gh, gw, H * D).permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).reshape(-1, H, D).contiguous()
+        o = ops.attention(qp[None], k[None], v[None], q_win=(win // 2, gw // 2, nwx, nwy), k_win=(win, gw, nwx, nwy))
+        ref = sdpa_ref(part(qp, gh // 2, gw // 2, win // 2), part(k, gh, gw, win), part(v, gh, gw, win), D ** -0.5)
+        assert rel(part(o[0], gh // 2, gw // 2, win // 2), ref) < 5e-6
+    else:
+        o = ops.attention(q[None], k[None], v[None], q_win=(win, gw, nwx, nwy), k_win=(win, gw, nwx, nwy))
+        assert rel(part(o[0], gh, gw, win), sdpa_ref(part(q, gh, gw, win), part(k, gh, gw, win), part(v, gh, gw, win), D ** -0.5)) < 5e-6
+
+
+def test_rope_and_im2col_fp32_variants():
+    x = torch.randn(64 * 3, 256, device=DEV)
+    xb = x.bfloat16().float()
+    a = ops.rope2d_(xb.clone(), 256, 8, 8)
+    b = ops.rope2d_(xb.bfloat16(), 256, 8, 8)
+    assert rel(b, a) < 4e-3 and a.dtype == torch.float32
+    pos = torch.arange(5, 5 + 10, device=DEV, dtype=torch.int32)
+    qkv = torch.randn(10, 3 * 4 * 32, device=DEV).bfloat16().float()
+    assert rel(ops.rope_neox_(qkv.bfloat16(), pos, 8, 32, 10000.0), ops.rope_neox_(qkv.clone(), pos, 8, 32, 10000.0)) < 4e-3
+    img = torch.randn(2, 3, 28, 28, device=DEV)
+    c32, oh, ow = ops.im2col(img, 14, 14, 0, out_dtype=torch.float32)
+    assert torch.equal(c32[:, :588].view(2, 2, 2, 3, 14, 14), img.view(2, 3, 2, 14, 2, 14).permute(0, 2, 4, 1, 3, 5))

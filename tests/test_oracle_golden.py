@@ -99,3 +99,6 @@ def test_e2e_composition_matches_reference_golden():
     assert torch.equal(ids, want_ids)
     assert tuple(logits.shape) == tuple(want_masks.shape)
     assert torch.equal(logits > 0, want_masks)
+    want_logits = torch.from_numpy(np.load(os.path.join(G, "e2e_tiny.npz"))["logits"])   # the reference's own video-res logits (propagate_in_video)
+    err = ((logits - want_logits).norm() / want_logits.norm()).item()
+    assert err < 1e-4, err

@@ -1,6 +1,9 @@
-"""SAM2 engine (CUDA, bf16 operands / fp32 accumulate) vs the CPU fp32 oracle, stage by stage ON IDENTICAL INPUTS and end to end,
-on the shrunken Hiera config (true decoder/memory widths). Tolerances are relative L2 and reflect bf16 operand rounding
-(2^-9 per operand): one GEMM ~2e-3; stacks of them up to ~1e-2. Mask sign agreement is the integer-valued check."""
+"""SAM2 engine (CUDA) vs the CPU fp32 oracle, stage by stage ON IDENTICAL INPUTS and end to end, on the shrunken Hiera config (true
+decoder/memory widths). Tolerances are relative L2:
+  - mask decoder / SAM heads (product default: fp32-grade split-bf16 GEMMs + exact fp32 attention): <= 1e-3 (north_star's bar on mask logits);
+  - the decoder + memory path of a tracked session on identical image features (memory attention / encoder with bf16 operands): <= 1e-3;
+  - engine in verification mode (precise="all"): <= 1e-3 through Hiera too, bool masks IDENTICAL;
+  - Hiera with bf16 operands (the product default; the reference itself runs it under bf16 autocast): reported separately at ~1e-2."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -27,18 +30,46 @@ def ctx():
     sd = Wt.make_sam2_state_dict(ocfg, 1234)
     sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}  # matrices bf16-representable on both sides
     eng = Sam2Engine(sd, ecfg)
+    assert eng.precise == "heads"
     torch.manual_seed(5678)
     images = torch.randn(3, 3, ocfg.image_size, ocfg.image_size)
     text = torch.randn(2, 1, 256)
     fpn, pos = O.forward_image(sd, ocfg, images[:1])
-    return dict(ocfg=ocfg, sd=sd, eng=eng, images=images, text=text, fpn=fpn, pos=pos)
+    return dict(ocfg=ocfg, sd=sd, eng=eng, images=images, text=text, fpn=fpn, pos=pos, ecfg=ecfg)
 
 
-def test_image_encoder(ctx):
-    f = ctx["eng"].forward_image(ctx["images"][:1].cuda())
+@pytest.fixture(scope="module")
+def eng_all(ctx):
+    return Sam2Engine(ctx["sd"], ctx["ecfg"], precise="all")
+
+
+def oracle_features(eng, sd, ocfg, images):
+    """Replaces the engine's image encoder by the oracle's fp32 features of the same frames (identical inputs for the decoder/memory path)."""
+    feats = []
+    with torch.no_grad():
+        for t in range(images.shape[0]):
+            fpn, _ = O.forward_image(sd, ocfg, images[t:t + 1])
+            feats.append(dict(s0=tok(fpn[0]).cuda().contiguous(), s1=tok(fpn[1]).cuda().contiguous(), top=tok(fpn[2]).cuda().contiguous()))
+
+    def fake_forward_image(img):
+        n = img.shape[0]
+        for t0 in range(images.shape[0] - n + 1):
+            if torch.equal(img.cpu(), images[t0:t0 + n]):
+                return {k: torch.cat([feats[t0 + i][k] for i in range(n)], 0) for k in ("s0", "s1", "top")}
+        raise KeyError("unknown frames")
+
+    return fake_forward_image
+
+
+def test_image_encoder(ctx, eng_all):
+    f = ctx["eng"].forward_image(ctx["images"][:1].cuda())          # product default: bf16 operands in Hiera
+    assert f["s0"].dtype == torch.float32                            # high-res maps feed the precise heads unrounded
     assert rel(f["s0"], tok(ctx["fpn"][0])) < 1e-2
     assert rel(f["s1"], tok(ctx["fpn"][1])) < 1e-2
     assert rel(f["top"], tok(ctx["fpn"][2])) < 1e-2
+    f = eng_all.forward_image(ctx["images"][:1].cuda())              # verification mode
+    for k, i in (("s0", 0), ("s1", 1), ("top", 2)):
+        assert rel(f[k], tok(ctx["fpn"][i])) < 1e-4, (k, rel(f[k], tok(ctx["fpn"][i])))
 
 
 def test_constant_tables(ctx):
@@ -57,16 +88,31 @@ def test_mask_decoder(ctx, with_text):
     hi = [fpn[0].expand(B, -1, -1, -1), fpn[1].expand(B, -1, -1, -1)]
     om = O.mask_decoder(sd, ocfg, pix, O.dense_pe(sd, ocfg), sparse, dense, hi, True)
     pix_tok = pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous()
-    em = eng.mask_decoder(pix_tok, tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(), sparse.cuda())
+    s0, s1 = tok(fpn[0]).cuda().contiguous(), tok(fpn[1]).cuda().contiguous()
+    em = eng.mask_decoder(pix_tok, s0, s1, sparse.cuda())
     side = 4 * ocfg.feat_size
-    assert rel(em[0].view(B, 4, side, side), om[4]) < 1.5e-2
-    assert rel(em[1], om[5]) < 5e-3
-    assert rel(em[3], om[3]) < 1e-2
+    assert rel(em[0].view(B, 4, side, side), om[4]) < 1e-3, rel(em[0].view(B, 4, side, side), om[4])      # north_star: 1e-3 on mask logits
+    assert rel(em[1], om[5]) < 1e-3
+    assert rel(em[3], om[3]) < 1e-3
     oh = O.forward_sam_heads(sd, ocfg, pix, hi, text_inputs=ctx["text"] if with_text else None)
-    eh = eng.forward_sam_heads(pix_tok, tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(),
-                               ctx["text"].cuda() if with_text else None, B)
-    assert rel(eh["low_res_masks"], oh["low_res_masks"][:, 0]) < 1.5e-2
-    assert rel(eh["obj_ptr"], oh["obj_ptr"]) < 1e-2
+    eh = eng.forward_sam_heads(pix_tok, s0, s1, ctx["text"].cuda() if with_text else None, B)
+    assert rel(eh["low_res_masks"], oh["low_res_masks"][:, 0]) < 1e-3
+    assert rel(eh["obj_ptr"], oh["obj_ptr"]) < 1e-3
+    assert torch.equal(eh["low_res_masks"].cpu() > 0, oh["low_res_masks"][:, 0] > 0)
+
+
+def test_mask_decoder_bf16_mode_reported(ctx):
+    """precise="none": the round-1 arithmetic (bf16 operands everywhere) stays available; its error is what the split-bf16 heads remove."""
+    ocfg, sd, fpn = ctx["ocfg"], ctx["sd"], ctx["fpn"]
+    eng = Sam2Engine(sd, ctx["ecfg"], precise="none")
+    B = 2
+    pix = (fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)).expand(B, -1, -1, -1)
+    sparse, dense = O.prompt_encode(sd, ocfg, B, ctx["text"])
+    om = O.mask_decoder(sd, ocfg, pix, O.dense_pe(sd, ocfg), sparse, dense, [fpn[0].expand(B, -1, -1, -1), fpn[1].expand(B, -1, -1, -1)], True)
+    em = eng.mask_decoder(pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous(), tok(fpn[0]).cuda().bfloat16().contiguous(),
+                          tok(fpn[1]).cuda().bfloat16().contiguous(), sparse.cuda())
+    e = rel(em[0].view(B, 4, 4 * ocfg.feat_size, 4 * ocfg.feat_size), om[4])
+    assert 1e-3 < e < 1.5e-2, e
 
 
 def test_no_object_branch(ctx):
@@ -77,8 +123,7 @@ def test_no_object_branch(ctx):
     eng = Sam2Engine(sd, Sam2Config(**O.TINY))
     pix = fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)
     oh = O.forward_sam_heads(sd, ocfg, pix, fpn[:2], text_inputs=ctx["text"][:1])
-    eh = eng.forward_sam_heads(tok(pix).cuda().contiguous(), tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous(),
-                               ctx["text"][:1].cuda(), 1)
+    eh = eng.forward_sam_heads(tok(pix).cuda().contiguous(), tok(fpn[0]).cuda().contiguous(), tok(fpn[1]).cuda().contiguous(), ctx["text"][:1].cuda(), 1)
     assert torch.all(eh["low_res_masks"] == O.NO_OBJ_SCORE) and torch.all(oh["low_res_masks"] == O.NO_OBJ_SCORE)
     assert rel(eh["obj_ptr"], oh["obj_ptr"]) < 1e-6
 
@@ -107,6 +152,7 @@ def test_memory_attention(ctx):
 
 
 def test_video_session_end_to_end(ctx):
+    """Product default (bf16 Hiera, precise heads): the Hiera bf16 error is what remains (reported, not the 1e-3 gate)."""
     ocfg, sd, eng = ctx["ocfg"], ctx["sd"], ctx["eng"]
     ref = O.run_video(sd, ocfg, ctx["images"], ctx["text"], (60, 100))
     got = eng.run_video(ctx["images"].cuda(), ctx["text"].cuda(), (60, 100))
@@ -116,6 +162,35 @@ def test_video_session_end_to_end(ctx):
         assert rel(a, b) < 2.5e-2, (t, rel(a, b))
         assert ((a > 0) == (b > 0)).float().mean() > 0.99
         assert torch.equal(gotb[t].cpu().bool(), a > 0)
+
+
+def test_video_session_decoder_memory_path_on_identical_features(ctx):
+    """The 1e-3 gate of north_star on the SAM2 decoder / memory path: a 7-frame, 2-object session (memory attention over up to 6 previous
+    frames + pointers, memory encoder, mask decoder) on IDENTICAL fp32 image features, product-default arithmetic."""
+    ocfg, sd = ctx["ocfg"], ctx["sd"]
+    eng = Sam2Engine(sd, ctx["ecfg"])
+    torch.manual_seed(77)
+    images = torch.randn(7, 3, ocfg.image_size, ocfg.image_size)
+    eng.forward_image = oracle_features(eng, sd, ocfg, images)
+    eng.frames_per_encode = 1
+    ref = O.run_video(sd, ocfg, images, ctx["text"], (60, 100))
+    got = eng._run_video(images.cuda(), ctx["text"].cuda(), (60, 100))
+    for t in range(7):
+        a, b = got[t].cpu(), ref[t][:, 0]
+        assert rel(a, b) < 1e-3, (t, rel(a, b))
+        assert ((a > 0) != (b > 0)).sum().item() <= 2, (t, ((a > 0) != (b > 0)).sum().item())
+
+
+def test_video_session_verification_mode(ctx, eng_all):
+    """precise="all": fp32-grade arithmetic through Hiera, memory attention / encoder and the heads: <= 1e-3 on the mask logits from the raw
+    frames, bool masks identical."""
+    ocfg, sd = ctx["ocfg"], ctx["sd"]
+    ref = O.run_video(sd, ocfg, ctx["images"], ctx["text"], (60, 100))
+    got = eng_all._run_video(ctx["images"].cuda(), ctx["text"].cuda(), (60, 100))
+    for t in range(len(ref)):
+        a, b = got[t].cpu(), ref[t][:, 0]
+        assert rel(a, b) < 1e-3, (t, rel(a, b))
+        assert torch.equal(a > 0, b > 0)
 
 
 def test_framewise_branch(ctx):
@@ -169,20 +244,25 @@ def test_video_session_against_reference_golden():
     ocfg, ecfg = O.Sam2Cfg(**O.TINY), Sam2Config(**O.TINY)
     for name, bias, T, nobj in (("present", 4.0, 9, 2), ("absent", -100.0, 2, 1)):
         sd = Wt.make_sam2_state_dict(ocfg, 1234, obj_score_bias=bias)
-        eng = Sam2Engine(sd, ecfg)
         torch.manual_seed(5678)
         images, text = torch.randn(T, 3, ocfg.image_size, ocfg.image_size), torch.randn(nobj, 1, 256)
-        got = torch.stack([m.cpu() for m in eng.run_video(images.cuda(), text.cuda(), (60, 100))])
         ref = torch.from_numpy(g[name])[:, :, 0]
-        assert got.shape == ref.shape
-        if name == "absent":
-            assert torch.all(got == O.NO_OBJ_SCORE)
-            continue
-        for t in range(T):   # bf16 operands against the reference's fp32: error grows along the 9-frame recurrence
-            assert rel(got[t], ref[t]) < 4e-2, (t, rel(got[t], ref[t]))
-        decided = ref.abs() > 0.05 * ref.abs().max()
-        assert torch.equal(got[decided] > 0, ref[decided] > 0)
-        assert ((got > 0) == (ref > 0)).float().mean() > 0.99
+        for precise in ("all", "heads"):
+            eng = Sam2Engine(sd, ecfg, precise=precise)
+            got = torch.stack([m.cpu() for m in eng.run_video(images.cuda(), text.cuda(), (60, 100))])
+            assert got.shape == ref.shape
+            if name == "absent":
+                assert torch.all(got == O.NO_OBJ_SCORE)
+                continue
+            errs = [rel(got[t], ref[t]) for t in range(T)]
+            if precise == "all":   # verification mode vs the UNMODIFIED reference: 3e-3 bar (measured ~1e-4), bool masks identical
+                assert max(errs) < 3e-3, errs
+                assert torch.equal(got > 0, ref > 0)
+            else:                  # product default: bf16 Hiera against the reference's fp32, error grows along the 9-frame recurrence
+                assert max(errs) < 4e-2, errs
+                decided = ref.abs() > 0.05 * ref.abs().max()
+                assert torch.equal(got[decided] > 0, ref[decided] > 0)
+                assert ((got > 0) == (ref > 0)).float().mean() > 0.99
 
 
 def test_long_session_four_objects(ctx):

@@ -29,6 +29,7 @@ struct AttnTcParams {
   int dpm;    // row width of the partials (128 or 256)
   int win, gridw, nwx;  // Hiera 2D windows (win > 0): batch entry b is window (b / nwx, b % nwx) of a [rows_y, gridw] token grid; tile rows are
                         // (ty, tx) = (r / win, r % win) and the tensor maps are {D, H, x, y} with boxes of win x (rows / win) tokens
+  int window;           // > 0 (causal only): query i additionally sees only keys j >= i + (Nk - Nq) - window (Phi-3 sliding window, transformers 4.41)
   int s_col, tmem_cols; // TMEM column of S and the allocation size: 128/256 when O needs <= 128 columns (two blocks per SM), else 256/512
 };
 
@@ -65,6 +66,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   const int off = p.Nk - p.Nq;
   int k_begin = 0, k_end = p.Nk;
   if (p.causal) k_end = min(p.Nk, q0 + BM + off);
+  if (p.window > 0) k_begin = max(0, q0 + off - p.window) / BN * BN;  // the first row of the tile reaches furthest back
   if (p.nsplit > 1) {
     const int per = ((p.Nk + p.nsplit - 1) / p.nsplit + BN - 1) / BN * BN;
     k_begin = split * per;
@@ -189,8 +191,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       tc_fence_after();
       const int k0 = k_begin + j * BN;
       const int col_lim = p.causal ? min(p.Nk, row + off + 1) : p.Nk;  // valid columns are < col_lim
-      // masking is only needed on tiles that cross the key limit of some row of this warp (the last tile / the causal diagonal)
-      const bool need_mask = __any_sync(0xffffffffu, k0 + BN > col_lim);
+      const int col_lo = p.window > 0 ? row + off - p.window : 0;      // ... and >= col_lo (sliding window band)
+      // masking is only needed on tiles that cross a key limit of some row of this warp (the last tile / the causal diagonal / the band edge)
+      const bool need_mask = __any_sync(0xffffffffu, k0 + BN > col_lim || k0 < col_lo);
       float sv[BN];
       float mx = -INFINITY;
 #pragma unroll
@@ -201,7 +204,8 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (need_mask) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float x = (k0 + c * 32 + i < col_lim) ? __uint_as_float(raw[i]) : -INFINITY;
+            const int col = k0 + c * 32 + i;
+            const float x = (col < col_lim && col >= col_lo) ? __uint_as_float(raw[i]) : -INFINITY;
             sv[c * 32 + i] = x;
             mx = fmaxf(mx, x);
           }
@@ -421,7 +425,7 @@ static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
 // Returns VG_OK if the tcgen05 kernel handled the call, VG_ENOSUP if the caller should use the generic kernel.
 int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int* dpm_out) {
   *nsplit_out = 1;
-  if (a->window != 0 || a->nk_dev != nullptr) return VG_ENOSUP;
+  if ((a->window != 0 && !a->causal) || a->window < 0 || a->nk_dev != nullptr) return VG_ENOSUP;
   const bool windowed = a->q_win != 0 || a->k_win != 0;
   if (windowed && !(a->q_win == a->k_win && a->q_gridw == a->k_gridw && a->q_nwx == a->k_nwx && a->q_nwy == a->k_nwy && a->q_win > 0 &&
                     128 % a->q_win == 0 && 64 % a->q_win == 0 && a->Nq == a->q_win * a->q_win && a->Nq % 128 == 0 && !a->causal && a->D <= 128))
@@ -437,6 +441,7 @@ int attention_tc_try(const VgAttention* a, cudaStream_t s, int* nsplit_out, int*
   p.o_bs = a->o_bs; p.o_hs = a->o_hs; p.o_rs = a->o_rs;
   p.ws = nullptr; p.nsplit = 1;
   p.dpm = a->D <= 128 ? 128 : 256;
+  p.window = a->window;
   p.win = windowed ? a->q_win : 0;
   p.gridw = a->q_gridw;
   p.nwx = a->q_nwx;

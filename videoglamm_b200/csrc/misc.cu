@@ -9,6 +9,7 @@ namespace vg {
 __device__ __forceinline__ float ld(const void* p, int dt, long long i) {
   return dt == VG_F32 ? reinterpret_cast<const float*>(p)[i] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
 }
+__device__ __forceinline__ float ld_(const void* p, int dt, long long i) { return ld(p, dt, i); }  // `ld` is shadowed by stride parameters in some kernels
 __device__ __forceinline__ void st(void* p, int dt, long long i, float v) {
   if (dt == VG_F32)
     reinterpret_cast<float*>(p)[i] = v;
@@ -261,7 +262,7 @@ __global__ void convt2x2_epilogue_kernel(const void* g, int gdt, const float* bi
   }
 }
 
-__global__ void im2col_kernel(const void* x, int xdt, __nv_bfloat16* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow,
+__global__ void im2col_kernel(const void* x, int xdt, void* out, int odt, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow,
                               int kpad) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
@@ -280,7 +281,7 @@ __global__ void im2col_kernel(const void* x, int xdt, __nv_bfloat16* out, int n,
     const int iy = oy * s - p + ky, ix = ox * s - p + kx;
     if (iy >= 0 && iy < h && ix >= 0 && ix < w) v = ld(x, xdt, ((static_cast<long long>(img) * cin + ci) * h + iy) * w + ix);
   }
-  out[i] = __float2bfloat16(v);
+  st(out, odt, i, v);
 }
 
 __global__ void dwconv_kernel(const void* x, int xdt, const float* wt, const float* bias, void* y, int ydt, int n, int h, int w, int c, int k) {
@@ -504,7 +505,7 @@ __global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, 
   reinterpret_cast<float*>(y)[i] = o;
 }
 
-__global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim, int gw, int gh) {
+__global__ void rope2d_kernel(void* x, int xdt, long long ld, int nrows, int dim, int gw, int gh) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
@@ -519,13 +520,13 @@ __global__ void rope2d_kernel(__nv_bfloat16* x, long long ld, int nrows, int dim
   const float ang = (pr < quarter ? px : py) * freq;
   float sn, cs;
   sincosf(ang, &sn, &cs);
-  __nv_bfloat16* p = x + r * ld + 2 * pr;
-  const float a = __bfloat162float(p[0]), b = __bfloat162float(p[1]);
-  p[0] = __float2bfloat16(a * cs - b * sn);
-  p[1] = __float2bfloat16(a * sn + b * cs);
+  const long long e = r * ld + 2 * pr;
+  const float a = ld_(x, xdt, e), b = ld_(x, xdt, e + 1);
+  st(x, xdt, e, a * cs - b * sn);
+  st(x, xdt, e + 1, a * sn + b * cs);
 }
 
-__global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
+__global__ void rope_neox_kernel(void* qkv, int xdt, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
   // one thread per (row, group of 8 heads, rotation pair): the angle (powf + sincosf, ~100 instructions) is computed once per 8 heads, and the
@@ -541,21 +542,21 @@ __global__ void rope_neox_kernel(__nv_bfloat16* qkv, long long ld, const int* po
   const float inv = powf(theta, -2.0f * j / hd);
   float sn, cs;
   sincosf(pos[r] * inv, &sn, &cs);
-  __nv_bfloat16* p = qkv + r * ld + static_cast<long long>(hg) * HG * hd + j;
+  const long long e = r * ld + static_cast<long long>(hg) * HG * hd + j;
   const int nh = min(HG, nheads - hg * HG);
   float a[HG], b[HG];
 #pragma unroll
   for (int u = 0; u < HG; ++u) {
     if (u < nh) {
-      a[u] = __bfloat162float(p[u * hd]);
-      b[u] = __bfloat162float(p[u * hd + half]);
+      a[u] = ld_(qkv, xdt, e + u * hd);
+      b[u] = ld_(qkv, xdt, e + u * hd + half);
     }
   }
 #pragma unroll
   for (int u = 0; u < HG; ++u) {
     if (u < nh) {
-      p[u * hd] = __float2bfloat16(a[u] * cs - b[u] * sn);
-      p[u * hd + half] = __float2bfloat16(b[u] * cs + a[u] * sn);
+      st(qkv, xdt, e + u * hd, a[u] * cs - b[u] * sn);
+      st(qkv, xdt, e + u * hd + half, b[u] * cs + a[u] * sn);
     }
   }
 }
@@ -817,10 +818,10 @@ extern "C" int vg_convt2x2_epilogue(const void* g, int g_dtype, const float* bia
   return check_launch("convt2x2_epilogue_kernel");
 }
 
-extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
+extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int out_dtype, int n, int cin, int h, int w, int k, int s, int p, int oh, int ow, int kpad,
                          void* stream) {
   if (!x || !out || kpad < cin * k * k) return set_error(VG_EINVAL, "vg_im2col: bad argument");
-  launch_k(im2col_kernel, dim3(blocks_for(static_cast<long long>(n) * oh * ow * kpad, 256)), dim3(256), 0, STREAM, x, x_dtype, static_cast<__nv_bfloat16*>(out), n,
+  launch_k(im2col_kernel, dim3(blocks_for(static_cast<long long>(n) * oh * ow * kpad, 256)), dim3(256), 0, STREAM, x, x_dtype, out, out_dtype, n,
                                                                                                   cin, h, w, k, s, p, oh, ow, kpad);
   count_launch();
   return check_launch("im2col_kernel");
@@ -866,17 +867,17 @@ extern "C" int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int o
   return check_launch("bilinear_kernel");
 }
 
-extern "C" int vg_rope2d(void* x, long long ld, int nrows, int dim, int gw, int gh, void* stream) {
+extern "C" int vg_rope2d(void* x, int x_dtype, long long ld, int nrows, int dim, int gw, int gh, void* stream) {
   if (!x || dim % 4) return set_error(VG_EINVAL, "vg_rope2d: dim must be a multiple of 4");
-  launch_k(rope2d_kernel, dim3(blocks_for(static_cast<long long>(nrows) * dim / 2, 256)), dim3(256), 0, STREAM, static_cast<__nv_bfloat16*>(x), ld, nrows, dim, gw, gh);
+  launch_k(rope2d_kernel, dim3(blocks_for(static_cast<long long>(nrows) * dim / 2, 256)), dim3(256), 0, STREAM, x, x_dtype, ld, nrows, dim, gw, gh);
   count_launch();
   return check_launch("rope2d_kernel");
 }
 
-extern "C" int vg_rope_neox(void* qkv, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
+extern "C" int vg_rope_neox(void* qkv, int x_dtype, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {
   if (!qkv || !pos || head_dim % 2) return set_error(VG_EINVAL, "vg_rope_neox: bad argument");
   launch_k(rope_neox_kernel, dim3(blocks_for(static_cast<long long>(rows) * ((n_heads_total + 7) / 8) * (head_dim / 2), 128)), dim3(128), 0, STREAM, 
-      static_cast<__nv_bfloat16*>(qkv), ld, pos, rows, n_heads_total, head_dim, theta);
+      qkv, x_dtype, ld, pos, rows, n_heads_total, head_dim, theta);
   count_launch();
   return check_launch("rope_neox_kernel");
 }

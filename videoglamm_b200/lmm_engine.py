@@ -26,11 +26,22 @@ IMAGE_TOKEN_INDEX = -200
 class _Lin:
     w: torch.Tensor
     b: torch.Tensor | None
+    w3: "ops.W3 | None" = None      # split-bf16 copy of the fp32 weight (verification mode, ops.gemm3)
+
+    def W(self, precise: bool):
+        if precise:
+            assert self.w3 is not None, "weight was packed without its split-bf16 copy"
+            return self.w3
+        return self.w
 
 
 class _Packer:
-    def __init__(self, sd: dict, dev: torch.device):
-        self.sd, self.dev = sd, dev
+    def __init__(self, sd: dict, dev: torch.device, precise: bool = False):
+        self.sd, self.dev, self.precise = sd, dev, precise
+
+    def mk(self, w: torch.Tensor, b) -> _Lin:
+        w = w.contiguous()
+        return _Lin(w.to(BF).contiguous(), b, ops.W3(w) if self.precise else None)
 
     def t(self, k):
         return self.sd[k].detach().to(self.dev, F32)
@@ -43,20 +54,22 @@ class _Packer:
             wp[:, : w.shape[1]] = w
             w = wp
         b = self.sd.get(p + ".bias")
-        return _Lin(w.to(BF).contiguous(), None if b is None else b.detach().to(self.dev, F32).contiguous())
+        return self.mk(w, None if b is None else b.detach().to(self.dev, F32).contiguous())
 
     def cat_lin(self, ps) -> _Lin:
-        ls = [self.lin(p) for p in ps]
-        return _Lin(torch.cat([l.w for l in ls]).contiguous(), torch.cat([l.b for l in ls]).contiguous() if ls[0].b is not None else None)
+        ws = [self.t(p + ".weight") for p in ps]
+        bs = [self.sd.get(p + ".bias") for p in ps]
+        return self.mk(torch.cat([w.reshape(w.shape[0], -1) for w in ws]),
+                       torch.cat([b.detach().to(self.dev, F32) for b in bs]).contiguous() if bs[0] is not None else None)
 
     def vec(self, k):
         return self.t(k).reshape(-1).contiguous()
 
 
-def _patchify_gemm(images: torch.Tensor, patch: int, w: _Lin, kpad: int, out_rows: torch.Tensor, resid: torch.Tensor):
+def _patchify_gemm(images: torch.Tensor, patch: int, w: _Lin, kpad: int, out_rows: torch.Tensor, resid: torch.Tensor, P: bool = False):
     """Non-overlapping patch conv as im2col + GEMM, one image group at a time; out_rows/resid are [rows, width] views."""
-    cols, _, _ = ops.im2col(images, patch, patch, 0, kpad)
-    ops.gemm(cols, w.w, bias=w.b, resid=resid, out=out_rows)
+    cols, _, _ = ops.im2col(images, patch, patch, 0, kpad, out_dtype=F32 if P else BF)
+    ops.gemm(cols, w.W(P), bias=w.b, resid=resid, out=out_rows)
 
 
 class ClipTower:
@@ -64,6 +77,7 @@ class ClipTower:
 
     def __init__(self, pk: _Packer, p: str, cfg: ClipConfig):
         self.cfg, v = cfg, p + ".vision_model"
+        self.P = pk.precise
         self.kpad = (3 * cfg.patch ** 2 + 7) // 8 * 8
         self.patch = pk.lin(v + ".embeddings.patch_embedding", self.kpad)
         pos = pk.t(v + ".embeddings.position_embedding.weight")
@@ -85,19 +99,21 @@ class ClipTower:
         T, W, N = images.shape[0], cfg.width, 1 + cfg.grid ** 2
         x = torch.empty((T, N, W), device=images.device, dtype=F32)
         x[:, 0] = self.cls_row
+        P = self.P
+        adt = F32 if P else BF
         for t in range(T):
-            _patchify_gemm(images[t:t + 1].contiguous(), cfg.patch, self.patch, self.kpad, x[t, 1:], self.pos_patches)
+            _patchify_gemm(images[t:t + 1].contiguous(), cfg.patch, self.patch, self.kpad, x[t, 1:], self.pos_patches, P)
         x = x.view(T * N, W)
         x = ops.norm(x, *self.pre, eps=1e-5, out_dtype=F32)
         hd = W // cfg.heads
         for L in self.layers:
-            h = ops.norm(x, *L["ln1"], eps=1e-5)
-            qkv = ops.gemm(h, L["qkv"].w, bias=L["qkv"].b).view(T, N, 3, cfg.heads, hd)
+            h = ops.norm(x, *L["ln1"], eps=1e-5, out_dtype=adt)
+            qkv = ops.gemm(h, L["qkv"].W(P), bias=L["qkv"].b, out_dtype=adt).view(T, N, 3, cfg.heads, hd)
             o = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=hd ** -0.5)
-            x = ops.gemm(o.view(T * N, W), L["out"].w, bias=L["out"].b, resid=x, out=x)
-            h = ops.norm(x, *L["ln2"], eps=1e-5)
-            h = ops.gemm(h, L["fc1"].w, bias=L["fc1"].b, act="quick_gelu")
-            x = ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=x, out=x)
+            x = ops.gemm(o.view(T * N, W), L["out"].W(P), bias=L["out"].b, resid=x, out=x)
+            h = ops.norm(x, *L["ln2"], eps=1e-5, out_dtype=adt)
+            h = ops.gemm(h, L["fc1"].W(P), bias=L["fc1"].b, act="quick_gelu", out_dtype=adt)
+            x = ops.gemm(h, L["fc2"].W(P), bias=L["fc2"].b, resid=x, out=x)
         return x.view(T, N, W)
 
 
@@ -107,6 +123,7 @@ class Iv2Tower:
 
     def __init__(self, pk: _Packer, p: str, cfg: Iv2Config):
         self.cfg, e = cfg, p + ".vision_encoder"
+        self.P = pk.precise
         self.kpad = (3 * cfg.patch ** 2 + 7) // 8 * 8
         self.patch = pk.lin(e + ".patch_embed.proj", self.kpad)
         pos = pk.t(e + ".pos_embed")[0]
@@ -126,30 +143,35 @@ class Iv2Tower:
         N = 1 + cfg.frames * cfg.grid ** 2
         x = torch.empty((n, N, W), device=chunks.device, dtype=F32)
         x[:, 0] = self.cls_row
+        P = self.P
+        adt = F32 if P else BF
         for c in range(n):  # Conv3d(1 x p x p) == per-frame 2D patch conv; the 4 frames of a chunk are consecutive token blocks
-            _patchify_gemm(chunks[c].contiguous(), cfg.patch, self.patch, self.kpad, x[c, 1:], self.pos_patches)
+            _patchify_gemm(chunks[c].contiguous(), cfg.patch, self.patch, self.kpad, x[c, 1:], self.pos_patches, P)
         x = x.view(n * N, W)
         hd = W // cfg.heads
         for B in self.blocks:
-            h = ops.norm(x, B["n1"], eps=1e-6, rms=True)
-            qkv = ops.gemm(h, B["qkv"].w)
+            h = ops.norm(x, B["n1"], eps=1e-6, rms=True, out_dtype=adt)
+            qkv = ops.gemm(h, B["qkv"].W(P), out_dtype=adt)
             ops.norm(qkv[:, :W], B["qn"], eps=1e-6, rms=True, out=qkv[:, :W])
             ops.norm(qkv[:, W:2 * W], B["kn"], eps=1e-6, rms=True, out=qkv[:, W:2 * W])
             q5 = qkv.view(n, N, 3, cfg.heads, hd)
             o = ops.attention(q5[:, :, 0], q5[:, :, 1], q5[:, :, 2], scale=hd ** -0.5)
-            x = ops.gemm(o.view(n * N, W), B["proj"].w, bias=B["proj"].b, col_scale=B["ls1"], resid=x, out=x)
-            h = ops.norm(x, B["n2"], eps=1e-6, rms=True)
-            h = ops.gemm(h, B["fc1"].w, bias=B["fc1"].b, act="gelu")
-            x = ops.gemm(h, B["fc2"].w, bias=B["fc2"].b, col_scale=B["ls2"], resid=x, out=x)
+            x = ops.gemm(o.view(n * N, W), B["proj"].W(P), bias=B["proj"].b, col_scale=B["ls1"], resid=x, out=x)
+            h = ops.norm(x, B["n2"], eps=1e-6, rms=True, out_dtype=adt)
+            h = ops.gemm(h, B["fc1"].W(P), bias=B["fc1"].b, act="gelu", out_dtype=adt)
+            x = ops.gemm(h, B["fc2"].W(P), bias=B["fc2"].b, col_scale=B["ls2"], resid=x, out=x)
         return x.view(n, N, W)
 
 
 class LmmEngine:
-    def __init__(self, sd: dict, cfg: LmmConfig, device: str = "cuda"):
+    def __init__(self, sd: dict, cfg: LmmConfig, device: str = "cuda", precise: bool = False):
+        """precise=True: verification mode — every contraction is a split-bf16 (fp32-grade) GEMM, every attention exact fp32, the KV cache fp32, no
+        decode fusions or graphs (parity with the fp32 reference at ~1e-5; ~3x the GEMM work). Default: bf16 operands, fp32 accumulation."""
         self.cfg, self.dev = cfg, torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("LmmEngine needs a CUDA device (there is no CPU path)")
-        pk = _Packer(sd, self.dev)
+        self.P = precise
+        pk = _Packer(sd, self.dev, precise)
         self.clip = ClipTower(pk, "model.image_vision_tower.vision_tower", cfg.clip)
         self.iv2 = Iv2Tower(pk, "model.vision_tower", cfg.iv2)
         self.vid_proj = [pk.lin(f"model.mm_projector.{2 * j}") for j in range(cfg.proj_depth)]
@@ -157,10 +179,11 @@ class LmmEngine:
         self.fc = [pk.lin("model.text_hidden_fcs.0.0"), pk.lin("model.text_hidden_fcs.0.2")]
         ph = cfg.phi
         self.embed = pk.t("model.embed_tokens.weight").to(BF).contiguous()
+        self.embed32 = pk.t("model.embed_tokens.weight").contiguous() if precise else None   # verification mode: un-rounded rows (a gather, no arithmetic)
         self.final_norm = pk.vec("model.norm.weight")
         # RMSNorm weights are folded into the following projection (W' = W diag(g), in fp32 before the bf16 rounding): the prefill norm
         # kernel then runs weight-less and the decode GEMV fuses the whole normalisation (x * rsqrt(mean x^2 + eps)) into its A loads.
-        self.lm_head = _Lin((pk.t("lm_head.weight") * self.final_norm[None]).to(BF).contiguous(), None)
+        self.lm_head = pk.mk(pk.t("lm_head.weight") * self.final_norm[None], None)
         self.ones = torch.ones(ph.hidden, device=self.dev)
         self.layers = []
         I = ph.inter
@@ -170,8 +193,8 @@ class LmmEngine:
             # interleave [16 gate | 16 up] row blocks so the GEMM epilogue computes silu(gate)*up in registers (include/vglamm.h, glu)
             gu = torch.stack([gu[:I].view(I // 16, 16, -1), gu[I:].view(I // 16, 16, -1)], dim=1).reshape(2 * I, -1)
             n1, n2 = pk.vec(p + ".input_layernorm.weight"), pk.vec(p + ".post_attention_layernorm.weight")
-            qkv = _Lin((pk.t(p + ".self_attn.qkv_proj.weight") * n1[None]).to(BF).contiguous(), None)
-            self.layers.append(dict(qkv=qkv, o=pk.lin(p + ".self_attn.o_proj"), gu=(gu * n2[None]).to(BF).contiguous(), down=pk.lin(p + ".mlp.down_proj")))
+            qkv = pk.mk(pk.t(p + ".self_attn.qkv_proj.weight") * n1[None], None)
+            self.layers.append(dict(qkv=qkv, o=pk.lin(p + ".self_attn.o_proj"), gu=pk.mk(gu * n2[None], None), down=pk.lin(p + ".mlp.down_proj")))
         self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
         self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
@@ -185,13 +208,14 @@ class LmmEngine:
     def _project(self, x3: torch.Tensor, layers) -> torch.Tensor:
         """mlpNx_gelu projector (multimodal_projector/builder.py:38-46) on a [B, n, width] fp32 view (CLS already sliced off)."""
         B, n, W = x3.shape
-        a = torch.empty((B, n, W), device=self.dev, dtype=BF)
+        P = self.P
+        a = torch.empty((B, n, W), device=self.dev, dtype=F32 if P else BF)
         for b in range(B):
             ops.add(x3[b], None, out=a[b])
         h = a.view(B * n, W)
         for j, L in enumerate(layers):
             last = j == len(layers) - 1
-            h = ops.gemm(h, L.w, bias=L.b, act=None if last else "gelu", out_dtype=F32 if last else BF)
+            h = ops.gemm(h, L.W(P), bias=L.b, act=None if last else "gelu", out_dtype=F32 if (last or P) else BF)
         return h
 
     def visual_tokens(self, images: torch.Tensor, context_images: torch.Tensor) -> torch.Tensor:
@@ -214,7 +238,7 @@ class LmmEngine:
         ph = self.cfg.phi
         if self.kv is None or self.kv[0].shape[0] < max_len:
             n = max(max_len, ph.max_len)                 # allocate once at the model's context length: graphs keep these pointers
-            self.kv = [torch.zeros((n, 3 * ph.hidden), device=self.dev, dtype=BF) for _ in range(ph.layers)]
+            self.kv = [torch.zeros((n, 3 * ph.hidden), device=self.dev, dtype=F32 if self.P else BF) for _ in range(ph.layers)]
             self.g_prefill.entries.clear()
             self.g_decode.entries.clear()
 
@@ -239,7 +263,7 @@ class LmmEngine:
             o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=self.dec_nk, decode_ws=self.dec_ws,
                               fused_rope_theta=ph.rope_theta)
             x = ops.gemm(o.view(1, D), L["o"].w, resid=x, out=x)
-            h = ops.gemm(x, L["gu"], glu=True, act="silu", a_rms_eps=ph.eps)                   # post-attention RMSNorm fused
+            h = ops.gemm(x, L["gu"].w, glu=True, act="silu", a_rms_eps=ph.eps)                 # post-attention RMSNorm fused
             x = ops.gemm(h, L["down"].w, resid=x, out=x)
         nxt = self._logits_argmax(x)
         self.dec_tok.copy_(nxt)                            # greedy continuation; the host overwrites dec_tok when a token is forced
@@ -254,27 +278,35 @@ class LmmEngine:
         n, H, hd, D = x.shape[0], ph.heads, ph.head_dim, ph.hidden
         pos = torch.arange(pos0, pos0 + n, device=self.dev, dtype=torch.int32)
         end = pos0 + n
+        P = self.P
+        adt = F32 if P else BF
         for l, L in enumerate(self.layers):
             cache = self.kv[l]
-            h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=adt)
             rows = cache[pos0:end]
-            ops.gemm(h, L["qkv"].w, out=rows)
+            ops.gemm(h, L["qkv"].W(P), out=rows)
             ops.rope_neox_(rows, pos, 2 * H, hd, ph.rope_theta)
             q = rows[:, :D].unflatten(1, (H, hd))[None]
             k = cache[:end, D:2 * D].unflatten(1, (H, hd))[None]
             v = cache[:end, 2 * D:].unflatten(1, (H, hd))[None]
             o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0)
-            x = ops.gemm(o.view(n, D), L["o"].w, resid=x, out=x)
-            h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
-            h = ops.gemm(h, L["gu"], glu=True, act="silu")
-            x = ops.gemm(h, L["down"].w, resid=x, out=x)
+            x = ops.gemm(o.view(n, D), L["o"].W(P), resid=x, out=x)
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=adt)
+            h = ops.gemm(h, L["gu"].W(P), glu=True, act="silu", out_dtype=adt)
+            x = ops.gemm(h, L["down"].W(P), resid=x, out=x)
         if last_only:
             return x[-1:].contiguous()                      # un-normalised residual row: the consumers fuse the final norm
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
 
     def _logits_argmax(self, x_last: torch.Tensor) -> torch.Tensor:
         """final RMSNorm (fused, weight folded into lm_head) -> lm_head -> argmax on one residual row [1, hidden] fp32."""
+        if self.P:
+            h = ops.norm(x_last, self.ones, eps=self.cfg.phi.eps, rms=True, out_dtype=F32)
+            return ops.argmax(ops.gemm(h, self.lm_head.w3, out_dtype=F32))
         return ops.argmax(ops.gemm(x_last, self.lm_head.w, out_dtype=F32, a_rms_eps=self.cfg.phi.eps))
+
+    def _embed(self, ids: torch.Tensor) -> torch.Tensor:
+        return self.embed32.index_select(0, ids) if self.P else ops.embedding(self.embed, ids)
 
     def embed_prompt(self, input_ids: torch.Tensor, vis: torch.Tensor) -> torch.Tensor:
         """prepare_inputs_labels_for_multimodal arch.py:283-379 (video case): embed(ids before the -200 run) + visual + embed(rest)."""
@@ -282,7 +314,7 @@ class LmmEngine:
         idx = torch.where(ids_host == IMAGE_TOKEN_INDEX)[0]
         start, end = int(idx[0]), int(idx[-1])
         text = torch.cat([ids_host[:start], ids_host[end + 1:]]).to(self.dev)
-        emb = ops.embedding(self.embed, text) if text.numel() else torch.zeros((0, self.embed.shape[1]), device=self.dev)
+        emb = self._embed(text) if text.numel() else torch.zeros((0, self.embed.shape[1]), device=self.dev)
         return torch.cat([emb[:start], vis, emb[start:]], 0).contiguous()
 
     @torch.no_grad()
@@ -292,13 +324,18 @@ class LmmEngine:
         returns (output_ids int64 [1, L_txt+N] incl. -200 sentinels, pred_embeddings fp32 [n_seg, out_dim]).
         The hidden state that PREDICTED each [SEG] (mask shifted by one, :803-806) is the final-norm hidden of the step that emitted it."""
         cfg = self.cfg
-        vis = self.g_vis((tuple(images.shape), tuple(context_images.shape)), self.visual_tokens, images=images, context_images=context_images)
+        if self.P:
+            vis = self.visual_tokens(images, context_images)
+        else:
+            vis = self.g_vis((tuple(images.shape), tuple(context_images.shape)), self.visual_tokens, images=images, context_images=context_images)
         x = self.embed_prompt(input_ids, vis)
         L0 = x.shape[0]
         self._alloc_cache(L0 + max_new_tokens + 1)
         dbg = None
         if return_debug:
             raise NotImplementedError("return_debug was removed with the fused decode path; use _llm() directly")
+        elif self.P:
+            x_last = self._prefill_last(x)
         else:
             x_last = self.g_prefill((L0,), self._prefill_last, x=x)
         new_ids, seg_hidden = [], []
@@ -313,6 +350,11 @@ class LmmEngine:
                 seg_hidden.append(ops.norm(x_last, self.final_norm, eps=cfg.phi.eps, rms=True, out_dtype=F32))
             if nxt in eos_ids or step == max_new_tokens - 1:
                 break
+            if self.P:   # verification mode: one un-fused, un-captured KV-cached forward per token
+                tok = torch.tensor([nxt], device=self.dev, dtype=torch.int64)
+                x_last = self._llm(self._embed(tok), L0 + step, last_only=True)
+                nxt_dev = self._logits_argmax(x_last)
+                continue
             if step == 0:
                 self.dec_pos.fill_(L0)
                 self.dec_nk.fill_(L0 + 1)
@@ -321,8 +363,10 @@ class LmmEngine:
             x_last, nxt_dev = self.g_decode((kv_bound,), lambda: self._decode_step(kv_bound), mutable_state=(self.dec_tok, self.dec_pos, self.dec_nk))
         out_ids = torch.cat([input_ids.reshape(1, -1), torch.tensor([new_ids], device=input_ids.device, dtype=torch.int64)], dim=1)
         if seg_hidden:
-            hs = ops.cast(torch.cat(seg_hidden, 0), BF)
-            emb = ops.gemm(ops.gemm(hs, self.fc[0].w, bias=self.fc[0].b, act="relu"), self.fc[1].w, bias=self.fc[1].b, out_dtype=F32)
+            P = self.P
+            hs = torch.cat(seg_hidden, 0) if P else ops.cast(torch.cat(seg_hidden, 0), BF)
+            emb = ops.gemm(ops.gemm(hs, self.fc[0].W(P), bias=self.fc[0].b, act="relu", out_dtype=F32 if P else BF), self.fc[1].W(P), bias=self.fc[1].b,
+                           out_dtype=F32)
         else:
             emb = torch.zeros((0, cfg.out_dim), device=self.dev)
         return (out_ids, emb, dbg) if return_debug else (out_ids, emb)

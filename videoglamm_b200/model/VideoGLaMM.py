@@ -26,14 +26,16 @@ class VideoGLaMMForCausalLM:
     """Inference engine behind the reference's class name. Not an nn.Module: weights are packed once for the kernels."""
 
     def __init__(self, state_dict: dict, lmm_cfg: LmmConfig | None = None, sam_cfg: Sam2Config | None = None, *, use_sam2_video_branch: bool = True,
-                 eos_token_ids=(), device: str = "cuda", validate: bool = True):
+                 eos_token_ids=(), device: str = "cuda", validate: bool = True, precise: str = "heads"):
+        """precise: "heads" (default: SAM2 mask decoder in fp32-grade arithmetic, everything else bf16 operands), "none", or "all" (verification
+        mode: every GEMM split-bf16, every attention exact fp32 — see Sam2Engine / LmmEngine)."""
         self.lmm_cfg = lmm_cfg or make_lmm_config()
         self.sam_cfg = sam_cfg or Sam2Config()
         if validate:
             validate_state_dict(state_dict, videoglamm_param_shapes(self.lmm_cfg, self.sam_cfg))
         self.device = torch.device(device)
-        self.lmm = LmmEngine(state_dict, self.lmm_cfg, device)
-        self.sam = Sam2Engine(state_dict, self.sam_cfg, device, prefix=SAM_PREFIX)
+        self.lmm = LmmEngine(state_dict, self.lmm_cfg, device, precise=precise == "all")
+        self.sam = Sam2Engine(state_dict, self.sam_cfg, device, prefix=SAM_PREFIX, precise=precise)
         self.use_sam2 = True
         self.use_sam2_video_branch = use_sam2_video_branch
         self.config = SimpleNamespace(seg_token_idx=self.lmm_cfg.seg_token_idx, use_sam2=True, eos_token_id=list(eos_token_ids),
@@ -100,7 +102,7 @@ class VideoGLaMMForCausalLM:
     # ---- inference -------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def inference(self, images, context_images, images_for_sam, input_ids, resize_list, original_size_list, max_new_tokens: int = 32,
-                  use_sam2_video_branch: bool = False, forced_tokens: dict | None = None):
+                  use_sam2_video_branch: bool = False, forced_tokens: dict | None = None, return_logits: bool = False):
         """Same contract as the reference (VideoGLaMM.py:560-596): lists of length 1 (batch 1 is asserted by the callers,
         chat.py:570); returns (output_ids int64 [1, L_txt+N], video_segments_batch: [ {frame_idx: {obj_id: bool ndarray [H,W]}} ])."""
         if not self.use_sam2 and use_sam2_video_branch:
@@ -128,6 +130,11 @@ class VideoGLaMMForCausalLM:
         if copy_done is not None:
             torch.cuda.current_stream(dev).wait_event(copy_done)
             sam_in.record_stream(torch.cuda.current_stream(dev))
+        if return_logits:   # parity tests: the fp32 video-resolution logits the masks are thresholded from (VideoGLaMM.py:870-875), as a third value
+            logits = torch.stack(run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary=False)).cpu()
+            stacked = (logits > 0).numpy()
+            segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}
+            return out_ids, [segs], logits
         frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
         stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)                 # ONE device->host copy per clip
         segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}

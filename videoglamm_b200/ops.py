@@ -30,12 +30,55 @@ def _require_cuda(*ts: torch.Tensor | None) -> None:
             raise RuntimeError("videoglamm_b200 ops run on CUDA tensors only (there is no CPU path)")
 
 
+class W3:
+    """B-side operand of a split-bf16 ("x3") GEMM: w fp32 [N,K] (or [B,N,K]) stored as bf16 [.., N, 3*Kp] = [hi | hi | lo] (include/vglamm.h,
+    vg_split3). Built once at load time for weights; `gemm` accepts it in place of a bf16 weight and then takes an fp32 A."""
+
+    def __init__(self, w: torch.Tensor):
+        _require_cuda(w)
+        assert w.dtype == torch.float32 and w.dim() in (2, 3)
+        self.shape = tuple(w.shape)
+        self.K = w.shape[-1]
+        self.w3 = split3(w.reshape(-1, self.K), b_side=True).view(*w.shape[:-1], -1)
+        self.Kp = self.w3.shape[-1] // 3
+
+    def dim(self):
+        return len(self.shape)
+
+
+def split3(x: torch.Tensor, b_side: bool = False) -> torch.Tensor:
+    """fp32 [rows, K] (row stride arbitrary) -> bf16 [rows, 3*Kp], Kp = K rounded up to 8: [hi | lo | hi] (A side) or [hi | hi | lo] (B side)."""
+    _require_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    kp = (K + 7) // 8 * 8
+    out = torch.empty((rows, 3 * kp), device=x.device, dtype=torch.bfloat16)
+    L.check(L.lib().vg_split3(_ptr(x), C.c_longlong(x.stride(0)), _ptr(out), C.c_longlong(3 * kp), C.c_longlong(rows), K, kp, int(b_side), _stream()),
+            "vg_split3")
+    return out
+
+
+def gemm3(a: torch.Tensor, w: "W3 | torch.Tensor", **kw) -> torch.Tensor:
+    """fp32-grade GEMM on the bf16 tensor cores: a fp32 [M,K] / [B,M,K]; w a W3 (weights) or an fp32 activation [N,K] / [B,N,K] (split on the fly)."""
+    assert a.dtype == torch.float32 and a.stride(-1) == 1
+    if not isinstance(w, W3):
+        w = W3(w.contiguous())
+    assert a.shape[-1] == w.K, (a.shape, w.shape)
+    a2 = a.reshape(-1, w.K) if a.is_contiguous() else a
+    assert a2.dim() == 2
+    a3 = split3(a2).view(*a.shape[:-1], -1)
+    return gemm(a3, w.w3, **kw)
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: torch.Tensor | None = None, act: str | None = None, glu: bool = False,
          col_scale: torch.Tensor | None = None, resid: torch.Tensor | None = None, out: torch.Tensor | None = None,
          out_dtype: torch.dtype = torch.bfloat16, alpha: float = 1.0, force_block_n: int = 0, naive: bool = False,
          a_rms_eps: float | None = None) -> torch.Tensor:
     """out = epilogue(alpha * a @ w^T). a: bf16 [M,K] or [B,M,K]; w: bf16 [N,K] or [B,N,K] (nn.Linear layout).
     Rows of `a`/`w` may be strided (last dim contiguous)."""
+    if isinstance(w, W3):
+        assert a_rms_eps is None and not naive
+        return gemm3(a, w, bias=bias, act=act, glu=glu, col_scale=col_scale, resid=resid, out=out, out_dtype=out_dtype, alpha=alpha)
     _require_cuda(a, w, bias, col_scale, resid, out)
     if a_rms_eps is not None:  # fp32 A rows, RMS-normalised on the fly (skinny path only)
         assert a.dtype == torch.float32 and a.dim() == 2 and a.shape[0] <= 8 and not naive
@@ -135,7 +178,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     q_win/k_win = (win, gridw, nwx, nwy): Hiera 2D window addressing; then B = images*nwx*nwy and the tensors passed are the
     un-partitioned [images*gridh*gridw, H, D] views (dim 0 of size 1 is added by the caller: shape [1, rows, H, D])."""
     _require_cuda(q, k, v, out)
-    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.dtype == k.dtype == v.dtype and q.dtype in (torch.bfloat16, torch.float32)
+    exact = q.dtype == torch.float32                    # fp32 operands -> the exact fp32 kernel (vg_attention_f32)
     a = L.VgAttention()
     if q_win is None:
         B, Nq, H, D = q.shape
@@ -149,7 +193,8 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         a.q_win, a.q_gridw, a.q_nwx, a.q_nwy = q_win
         a.k_win, a.k_gridw, a.k_nwx, a.k_nwy = kw
     if out is None:
-        out = torch.empty(q.shape, device=q.device, dtype=torch.bfloat16)
+        out = torch.empty(q.shape, device=q.device, dtype=q.dtype)
+    assert out.dtype == q.dtype
     for t in (q, k, v, out):
         assert t.stride(-1) == 1
     a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
@@ -161,6 +206,13 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
     a.scale = float(scale if scale is not None else D ** -0.5)
     a.causal, a.window = int(causal), int(window)
     a.force_legacy = int(legacy)
+    if exact:
+        assert nk_dev is None and decode_ws is None and not fused_rope_theta, "decode-graph features exist on the bf16 path only"
+        if q_win is None and not causal and not window and Nk >= 256 and B * H * ((Nq + 15) // 16) < 148:
+            ws = torch.empty((16 * B * H * Nq * (D + 2),), device=q.device, dtype=torch.float32)
+            a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+        L.check(L.lib().vg_attention_f32(C.byref(a), _stream()), "vg_attention_f32")
+        return out
     if nk_dev is not None:
         assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
         a.nk_dev = nk_dev.data_ptr()
@@ -256,16 +308,16 @@ def convt2x2_epilogue(g: torch.Tensor, bias: torch.Tensor, feat: torch.Tensor | 
     return out
 
 
-def im2col(x: torch.Tensor, k: int, s: int, p: int, kpad: int | None = None) -> tuple[torch.Tensor, int, int]:
-    """x NCHW (fp32/bf16, contiguous) -> bf16 [n*oh*ow, kpad]"""
+def im2col(x: torch.Tensor, k: int, s: int, p: int, kpad: int | None = None, out_dtype: torch.dtype = torch.bfloat16) -> tuple[torch.Tensor, int, int]:
+    """x NCHW (fp32/bf16, contiguous) -> bf16 (or fp32) [n*oh*ow, kpad]"""
     _require_cuda(x)
     assert x.is_contiguous() and x.dim() == 4
     n, cin, h, w = x.shape
     oh, ow = (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
     kk = cin * k * k
     kpad = kpad or (kk + 7) // 8 * 8
-    out = torch.empty((n * oh * ow, kpad), device=x.device, dtype=torch.bfloat16)
-    L.check(L.lib().vg_im2col(_ptr(x), _dt(x.dtype), _ptr(out), n, cin, h, w, k, s, p, oh, ow, kpad, _stream()), "vg_im2col")
+    out = torch.empty((n * oh * ow, kpad), device=x.device, dtype=out_dtype)
+    L.check(L.lib().vg_im2col(_ptr(x), _dt(x.dtype), _ptr(out), _dt(out_dtype), n, cin, h, w, k, s, p, oh, ow, kpad, _stream()), "vg_im2col")
     return out, oh, ow
 
 
@@ -300,17 +352,17 @@ def bilinear(x: torch.Tensor, oh: int, ow: int, *, mode: int = 0, scale: float =
 
 
 def rope2d_(x: torch.Tensor, dim: int, gw: int, gh: int) -> torch.Tensor:
-    """in place on bf16 [rows, >=dim] (row stride arbitrary)"""
+    """in place on bf16 / fp32 [rows, >=dim] (row stride arbitrary)"""
     _require_cuda(x)
-    assert x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
-    L.check(L.lib().vg_rope2d(_ptr(x), C.c_longlong(x.stride(0)), x.shape[0], dim, gw, gh, _stream()), "vg_rope2d")
+    assert x.dim() == 2 and x.stride(1) == 1
+    L.check(L.lib().vg_rope2d(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), x.shape[0], dim, gw, gh, _stream()), "vg_rope2d")
     return x
 
 
 def rope_neox_(qkv: torch.Tensor, pos: torch.Tensor, n_heads_total: int, head_dim: int, theta: float) -> torch.Tensor:
     _require_cuda(qkv, pos)
-    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 2 and qkv.stride(1) == 1 and pos.dtype == torch.int32
-    L.check(L.lib().vg_rope_neox(_ptr(qkv), C.c_longlong(qkv.stride(0)), _ptr(pos), qkv.shape[0], n_heads_total, head_dim, C.c_float(theta),
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and pos.dtype == torch.int32
+    L.check(L.lib().vg_rope_neox(_ptr(qkv), _dt(qkv.dtype), C.c_longlong(qkv.stride(0)), _ptr(pos), qkv.shape[0], n_heads_total, head_dim, C.c_float(theta),
                                  _stream()), "vg_rope_neox")
     return qkv
 

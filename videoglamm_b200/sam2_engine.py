@@ -27,6 +27,13 @@ BF, F32 = torch.bfloat16, torch.float32
 class _Lin:
     w: torch.Tensor  # bf16 [N, K]
     b: torch.Tensor | None  # fp32 [N]
+    w3: "ops.W3 | None" = None  # split-bf16 copy of the fp32 weight (fp32-grade GEMMs, ops.gemm3)
+
+    def W(self, precise: bool):
+        if precise:
+            assert self.w3 is not None, "weight was packed without its split-bf16 copy"
+            return self.w3
+        return self.w
 
 
 @dataclass
@@ -37,11 +44,18 @@ class FrameMem:
 
 
 class Sam2Engine:
-    def __init__(self, sd: dict, cfg: Sam2Config | None = None, device: str = "cuda", prefix: str = ""):
+    def __init__(self, sd: dict, cfg: Sam2Config | None = None, device: str = "cuda", prefix: str = "", precise: str = "heads"):
+        """precise: which stages run in fp32-grade arithmetic (split-bf16 tensor-core GEMMs, exact fp32 attention; include/vglamm.h vg_split3):
+        "heads" (default) = the mask decoder + IoU / object-score / object-pointer MLPs, whose rounding dominates the mask-logit error
+        (scripts/precision_study.py: bf16 there -> 5e-3, fp32-grade there -> <= 4e-4 with everything else bf16); "none" = bf16 operands everywhere;
+        "all" = every stage incl. Hiera and the memory path (verification mode: parity to the fp32 reference at ~1e-5, ~3x the GEMM work)."""
         self.cfg = cfg or Sam2Config()
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
             raise RuntimeError("Sam2Engine needs a CUDA device (there is no CPU path)")
+        assert precise in ("none", "heads", "all"), precise
+        self.precise = precise
+        self.p_heads, self.p_all = precise != "none", precise == "all"
         self.frames_per_encode = 8
         self.g_video = GraphedStage("sam2_video")
         self._sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
@@ -52,17 +66,21 @@ class Sam2Engine:
     def _t(self, k):
         return self._sd[k].detach().to(self.dev, F32)
 
-    def _lin(self, p) -> _Lin:
+    def _mk(self, w: torch.Tensor, b, precise: bool) -> _Lin:
+        w = w.contiguous()
+        return _Lin(w.to(BF).contiguous(), b, ops.W3(w) if precise else None)
+
+    def _lin(self, p, precise: bool | None = None) -> _Lin:
         w = self._t(p + ".weight")
         w = w.reshape(w.shape[0], -1)
         b = self._sd.get(p + ".bias")
-        return _Lin(w.to(BF).contiguous(), None if b is None else b.detach().to(self.dev, F32).contiguous())
+        return self._mk(w, None if b is None else b.detach().to(self.dev, F32).contiguous(), self.p_all if precise is None else precise)
 
     def _ln(self, p):
         return self._t(p + ".weight").contiguous(), self._t(p + ".bias").contiguous()
 
-    def _attn_w(self, p):
-        return {n: self._lin(f"{p}.{n}_proj") for n in ("q", "k", "v", "out")}
+    def _attn_w(self, p, precise: bool | None = None):
+        return {n: self._lin(f"{p}.{n}_proj", precise) for n in ("q", "k", "v", "out")}
 
     def _pack(self):
         cfg, t = self.cfg, "image_encoder.trunk"
@@ -72,7 +90,7 @@ class Sam2Engine:
         self.pe_kpad = (w.shape[1] + 7) // 8 * 8
         wp = torch.zeros(cfg.embed_dim, self.pe_kpad, device=self.dev)
         wp[:, : w.shape[1]] = w
-        self.patch = _Lin(wp.to(BF).contiguous(), self._t(t + ".patch_embed.proj.bias"))
+        self.patch = self._mk(wp, self._t(t + ".patch_embed.proj.bias"), self.p_all)
         # Hiera._get_pos_embed (backbones/hieradet.py:269-277): constant of the weights, folded at load time
         g = cfg.image_size // 4
         pe = F.interpolate(self._t(t + ".pos_embed"), size=(g, g), mode="bicubic")
@@ -94,7 +112,7 @@ class Sam2Engine:
 
         def fold(outer: str, inner: _Lin):
             wo, bo = self._t(outer + ".weight").reshape(-1, C), self._t(outer + ".bias")
-            return _Lin((wo @ inner.w.float()).to(BF).contiguous(), (wo @ inner.b + bo).contiguous())
+            return self._mk(wo @ inner.w.float(), (wo @ inner.b + bo).contiguous(), self.p_all)
 
         w2 = self._t("image_encoder.neck.convs.2.conv.weight").reshape(C, -1)
         w3 = self._t("image_encoder.neck.convs.3.conv.weight").reshape(C, -1)
@@ -122,26 +140,28 @@ class Sam2Engine:
         self.dec_layers = []
         for i in range(cfg.dec_depth):
             l = f"{md}.transformer.layers.{i}"
-            self.dec_layers.append(dict(sa=self._attn_w(l + ".self_attn"), t2i=self._attn_w(l + ".cross_attn_token_to_image"),
-                                        i2t=self._attn_w(l + ".cross_attn_image_to_token"), n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"),
-                                        n3=self._ln(l + ".norm3"), n4=self._ln(l + ".norm4"), fc1=self._lin(l + ".mlp.layers.0"),
-                                        fc2=self._lin(l + ".mlp.layers.1")))
-        self.dec_final = self._attn_w(md + ".transformer.final_attn_token_to_image")
+            PH = self.p_heads
+            self.dec_layers.append(dict(sa=self._attn_w(l + ".self_attn", PH), t2i=self._attn_w(l + ".cross_attn_token_to_image", PH),
+                                        i2t=self._attn_w(l + ".cross_attn_image_to_token", PH), n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"),
+                                        n3=self._ln(l + ".norm3"), n4=self._ln(l + ".norm4"), fc1=self._lin(l + ".mlp.layers.0", PH),
+                                        fc2=self._lin(l + ".mlp.layers.1", PH)))
+        PH = self.p_heads
+        self.dec_final = self._attn_w(md + ".transformer.final_attn_token_to_image", PH)
         self.dec_nf = self._ln(md + ".transformer.norm_final_attn")
         # ConvTranspose2d weight [Cin, Cout, 2, 2] -> GEMM weight rows (dy,dx,co), cols ci (mask_decoder.py:66-77)
         for name, key in (("up1", ".output_upscaling.0"), ("up2", ".output_upscaling.3")):
             wt = self._t(md + key + ".weight")
-            setattr(self, name, _Lin(wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]).to(BF).contiguous(), self._t(md + key + ".bias")))
+            setattr(self, name, self._mk(wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]), self._t(md + key + ".bias"), PH))
         self.up_ln = self._ln(md + ".output_upscaling.1")
         # 4 hypernetwork MLPs as batched GEMMs: [4, out, in] weights, [4, out] biases
         self.hyper = []
         for j in range(3):
             ws = torch.stack([self._t(f"{md}.output_hypernetworks_mlps.{i}.layers.{j}.weight") for i in range(4)])
             bs = torch.stack([self._t(f"{md}.output_hypernetworks_mlps.{i}.layers.{j}.bias") for i in range(4)])
-            self.hyper.append(_Lin(ws.to(BF).contiguous(), bs.contiguous()))
-        self.iou_head = [self._lin(f"{md}.iou_prediction_head.layers.{j}") for j in range(3)]
-        self.obj_head = [self._lin(f"{md}.pred_obj_score_head.layers.{j}") for j in range(3)]
-        self.obj_ptr_proj = [self._lin(f"obj_ptr_proj.layers.{j}") for j in range(3)]
+            self.hyper.append(self._mk(ws, bs.contiguous(), PH))
+        self.iou_head = [self._lin(f"{md}.iou_prediction_head.layers.{j}", PH) for j in range(3)]
+        self.obj_head = [self._lin(f"{md}.pred_obj_score_head.layers.{j}", PH) for j in range(3)]
+        self.obj_ptr_proj = [self._lin(f"obj_ptr_proj.layers.{j}", PH) for j in range(3)]
         # memory encoder (memory_encoder.py)
         me = "memory_encoder"
         self.ds = []
@@ -163,7 +183,8 @@ class Sam2Engine:
         for i in range(cfg.mem_attn_layers):
             l = f"memory_attention.layers.{i}"
             sa, ca = self._attn_w(l + ".self_attn"), self._attn_w(l + ".cross_attn_image")
-            qkv = _Lin(torch.cat([sa["q"].w, sa["k"].w, sa["v"].w]).contiguous(), torch.cat([sa["q"].b, sa["k"].b, sa["v"].b]).contiguous())
+            qkv = self._mk(torch.cat([self._t(f"{l}.self_attn.{n}_proj.weight") for n in "qkv"]), torch.cat([sa["q"].b, sa["k"].b, sa["v"].b]).contiguous(),
+                           self.p_all)
             self.ma_layers.append(dict(qkv=qkv, sa_out=sa["out"], ca=ca, n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"), n3=self._ln(l + ".norm3"),
                                        fc1=self._lin(l + ".linear1"), fc2=self._lin(l + ".linear2")))
         self.ma_norm = self._ln("memory_attention.norm")
@@ -186,16 +207,17 @@ class Sam2Engine:
     def _hiera_block(self, x, blk, n, H, W):
         """MultiScaleBlock.forward backbones/hieradet.py:136-168. x fp32 [n*H*W, dim] -> (fp32 [n*H'*W', dim_out], H', W')."""
         dim, dim_out, heads, window, qs = blk["spec"]
+        P = self.p_all
+        adt = F32 if P else BF
         hd = dim_out // heads
-        xn = ops.norm(x, *blk["n1"], eps=1e-6)
+        xn = ops.norm(x, *blk["n1"], eps=1e-6, out_dtype=adt)
         if dim != dim_out:
-            sc = ops.gemm(xn, blk["dproj"].w, bias=blk["dproj"].b, out_dtype=F32)
+            sc = ops.gemm(xn, blk["dproj"].W(P), bias=blk["dproj"].b, out_dtype=F32)
             if qs:
                 sc = ops.pool2x2(sc, n, H, W, is_max=True)
         else:
             sc = x
-        qkv = ops.gemm(xn, blk["qkv"].w, bias=blk["qkv"].b)  # [rows, 3*dim_out] = (3, heads, hd)
-        rows = n * H * W
+        qkv = ops.gemm(xn, blk["qkv"].W(P), bias=blk["qkv"].b, out_dtype=adt)  # [rows, 3*dim_out] = (3, heads, hd)
         q, k, v = (qkv[:, j * dim_out:(j + 1) * dim_out].unflatten(1, (heads, hd)) for j in range(3))
         Hq, Wq = H, W
         if qs:
@@ -208,61 +230,70 @@ class Sam2Engine:
         else:
             o = ops.attention(q.unflatten(0, (n, Hq * Wq)), k.unflatten(0, (n, H * W)), v.unflatten(0, (n, H * W)), scale=hd ** -0.5)
         o = o.reshape(n * Hq * Wq, dim_out)
-        x = ops.gemm(o, blk["proj"].w, bias=blk["proj"].b, resid=sc, out=sc)  # in place: aliasing residual -> TMA reduce-add epilogue
-        xn = ops.norm(x, *blk["n2"], eps=1e-6)
-        h = ops.gemm(xn, blk["fc1"].w, bias=blk["fc1"].b, act="gelu")
-        x = ops.gemm(h, blk["fc2"].w, bias=blk["fc2"].b, resid=x, out=x)
+        x = ops.gemm(o, blk["proj"].W(P), bias=blk["proj"].b, resid=sc, out=sc, out_dtype=F32)  # in place: aliasing residual -> TMA reduce-add epilogue
+        xn = ops.norm(x, *blk["n2"], eps=1e-6, out_dtype=adt)
+        h = ops.gemm(xn, blk["fc1"].W(P), bias=blk["fc1"].b, act="gelu", out_dtype=adt)
+        x = ops.gemm(h, blk["fc2"].W(P), bias=blk["fc2"].b, resid=x, out=x, out_dtype=F32)
         return x, Hq, Wq
 
     def forward_image(self, img: torch.Tensor) -> dict:
         """SAM2Base.forward_image sam2_base.py:465-477 (Hiera hieradet.py:279-295 + FpnNeck image_encoder.py:101-133 + conv_s0/s1).
-        img [n,3,S,S] fp32 -> {"s0": bf16 [n*(S/4)^2, 32], "s1": bf16 [n*(S/8)^2, 64], "top": fp32 [n*(S/16)^2, 256]}"""
+        img [n,3,S,S] fp32 -> {"s0": [n*(S/4)^2, 32], "s1": [n*(S/8)^2, 64] (bf16; fp32 when the heads are precise), "top": fp32 [n*(S/16)^2, 256]}"""
         cfg = self.cfg
+        P = self.p_all
+        adt = F32 if P else BF
         n = img.shape[0]
         assert img.shape[1:] == (3, cfg.image_size, cfg.image_size) and img.is_cuda
         img = img.contiguous()
         g = cfg.image_size // 4
         x = torch.empty((n * g * g, cfg.embed_dim), device=self.dev, dtype=F32)
         for i in range(n):  # pos-embed residual is per image
-            cols, _, _ = ops.im2col(img[i:i + 1], 7, 4, 3, self.pe_kpad)
-            ops.gemm(cols, self.patch.w, bias=self.patch.b, resid=self.hiera_pos, out=x[i * g * g:(i + 1) * g * g])
+            cols, _, _ = ops.im2col(img[i:i + 1], 7, 4, 3, self.pe_kpad, out_dtype=adt)
+            ops.gemm(cols, self.patch.W(P), bias=self.patch.b, resid=self.hiera_pos, out=x[i * g * g:(i + 1) * g * g])
         H = W = g
         stage_out = []
         ends = cfg.stage_ends
         for i, blk in enumerate(self.blocks):
             x, H, W = self._hiera_block(x, blk, n, H, W)
             if i in ends:
-                stage_out.append((ops.cast(x, BF), H, W))
+                stage_out.append((x.clone() if P else ops.cast(x, BF), H, W))
         (x0, H0, W0), (x1, H1, W1), (x2, H2, W2), (x3, H3, W3) = stage_out
-        lat3 = ops.gemm(x3, self.neck3.w, bias=self.neck3.b, out_dtype=F32)
-        lat2 = ops.gemm(x2, self.neck2.w, bias=self.neck2.b, out_dtype=F32)
+        lat3 = ops.gemm(x3, self.neck3.W(P), bias=self.neck3.b, out_dtype=F32)
+        lat2 = ops.gemm(x2, self.neck2.W(P), bias=self.neck2.b, out_dtype=F32)
         top = ops.upsample2x_add(lat2, lat3, n, H3, W3)
-        s1 = ops.gemm(x1, self.s1.w, bias=self.s1.b)
-        s0 = ops.gemm(x0, self.s0.w, bias=self.s0.b)
+        hdt = F32 if self.p_heads else BF     # the high-res maps are summands of the upscaled mask features: keep them unrounded for the precise heads
+        s1 = ops.gemm(x1, self.s1.W(P), bias=self.s1.b, out_dtype=hdt)
+        s0 = ops.gemm(x0, self.s0.W(P), bias=self.s0.b, out_dtype=hdt)
         return dict(s0=s0, s1=s1, top=top)
 
     # ------------------------------------------------------------------------------------------------ mask decoder
-    def _attn(self, w, q_in, k_in, v_in, B, Nq, Nk, resid=None):
-        """Attention.forward sam/transformer.py:233-260 on bf16 [B*N, C] inputs -> fp32 [B*Nq, C] (+ residual)."""
+    def _attn(self, w, q_in, k_in, v_in, B, Nq, Nk, resid=None, P=False):
+        """Attention.forward sam/transformer.py:233-260 on [B*N, C] inputs (bf16, or fp32 when P) -> fp32 [B*Nq, C] (+ residual)."""
         H = self.cfg.dec_heads
-        q = ops.gemm(q_in, w["q"].w, bias=w["q"].b)
-        k = ops.gemm(k_in, w["k"].w, bias=w["k"].b)
-        v = ops.gemm(v_in, w["v"].w, bias=w["v"].b)
+        adt = F32 if P else BF
+        q = ops.gemm(q_in, w["q"].W(P), bias=w["q"].b, out_dtype=adt)
+        k = ops.gemm(k_in, w["k"].W(P), bias=w["k"].b, out_dtype=adt)
+        v = ops.gemm(v_in, w["v"].W(P), bias=w["v"].b, out_dtype=adt)
         d = q.shape[1] // H
         o = ops.attention(q.view(B, Nq, H, d), k.view(B, Nk, H, d), v.view(B, Nk, H, d), scale=d ** -0.5)
-        return ops.gemm(o.view(B * Nq, H * d), w["out"].w, bias=w["out"].b, resid=resid, out=resid, out_dtype=F32)  # in place when residual
+        return ops.gemm(o.view(B * Nq, H * d), w["out"].W(P), bias=w["out"].b, resid=resid, out=resid, out_dtype=F32)  # in place when residual
 
-    def _mlp3(self, layers, x_bf, final_act=None):
-        h = ops.gemm(x_bf, layers[0].w, bias=layers[0].b, act="relu")
-        h = ops.gemm(h, layers[1].w, bias=layers[1].b, act="relu")
-        return ops.gemm(h, layers[2].w, bias=layers[2].b, act=final_act, out_dtype=F32)
+    def _mlp3(self, layers, x, final_act=None, P=False):
+        adt = F32 if P else BF
+        h = ops.gemm(x, layers[0].W(P), bias=layers[0].b, act="relu", out_dtype=adt)
+        h = ops.gemm(h, layers[1].W(P), bias=layers[1].b, act="relu", out_dtype=adt)
+        return ops.gemm(h, layers[2].W(P), bias=layers[2].b, act=final_act, out_dtype=F32)
 
     def mask_decoder(self, pix: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, sparse: torch.Tensor, debug: dict | None = None):
         """PromptEncoder dense part + MaskDecoder.predict_masks (sam/mask_decoder.py:167-245), TwoWayTransformer
         (sam/transformer.py:63-115, 160-193). pix fp32 [B*HW, C] image embedding (one row block per object), s0/s1 the
         high-res maps of the ONE image shared by the B objects, sparse fp32 [B, Ns, C].
-        Returns all-4 masks fp32 [B,4,(4fs)^2], iou [B,4] (sigmoid), mask tokens fp32 [B,4,C], object score logits [B,1]."""
+        Returns all-4 masks fp32 [B,4,(4fs)^2], iou [B,4] (sigmoid), mask tokens fp32 [B,4,C], object score logits [B,1].
+        With precise heads (default) every contraction is a split-bf16 GEMM and every attention exact fp32 (activations stay fp32)."""
         cfg, HW, C = self.cfg, self.HW, self.cfg.d_model
+        P = self.p_heads
+        adt = F32 if P else BF
+        act = (lambda t: t) if P else (lambda t: ops.cast(t, BF))     # GEMM-operand view of an fp32 activation
         B = sparse.shape[0]
         tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(-1, C).contiguous()
         Nt = tokens.shape[0] // B
@@ -271,42 +302,45 @@ class Sam2Engine:
         k_pe = v_k = None
         for i, L in enumerate(self.dec_layers):
             if i == 0:
-                qb = ops.cast(queries, BF)
-                queries = self._attn(L["sa"], qb, qb, qb, B, Nt, Nt)
+                qb = act(queries)
+                queries = self._attn(L["sa"], qb, qb, qb, B, Nt, Nt, P=P)
             else:
-                q = ops.add(queries, tokens, out_dtype=BF)
-                queries = self._attn(L["sa"], q, q, ops.cast(queries, BF), B, Nt, Nt, resid=queries)
+                q = ops.add(queries, tokens, out_dtype=adt)
+                queries = self._attn(L["sa"], q, q, act(queries), B, Nt, Nt, resid=queries, P=P)
             queries = ops.norm(queries, *L["n1"], eps=1e-5, out_dtype=F32)
-            q = ops.add(queries, tokens, out_dtype=BF)
-            k_pe = ops.add(keys, self.dense_pe, out_dtype=BF)
-            v_k = ops.cast(keys, BF)
-            queries = ops.norm(self._attn(L["t2i"], q, k_pe, v_k, B, Nt, HW, resid=queries), *L["n2"], eps=1e-5, out_dtype=F32)
-            h = ops.gemm(ops.cast(queries, BF), L["fc1"].w, bias=L["fc1"].b, act="relu")
-            queries = ops.norm(ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=queries, out=queries), *L["n3"], eps=1e-5, out_dtype=F32)
-            q = ops.add(queries, tokens, out_dtype=BF)
-            keys = ops.norm(self._attn(L["i2t"], k_pe, q, ops.cast(queries, BF), B, HW, Nt, resid=keys), *L["n4"], eps=1e-5, out_dtype=F32)
-        q = ops.add(queries, tokens, out_dtype=BF)
-        k_pe = ops.add(keys, self.dense_pe, out_dtype=BF)
-        v_k = ops.cast(keys, BF)
-        queries = ops.norm(self._attn(self.dec_final, q, k_pe, v_k, B, Nt, HW, resid=queries), *self.dec_nf, eps=1e-5, out_dtype=F32)
+            q = ops.add(queries, tokens, out_dtype=adt)
+            k_pe = ops.add(keys, self.dense_pe, out_dtype=adt)
+            v_k = act(keys)
+            queries = ops.norm(self._attn(L["t2i"], q, k_pe, v_k, B, Nt, HW, resid=queries, P=P), *L["n2"], eps=1e-5, out_dtype=F32)
+            h = ops.gemm(act(queries), L["fc1"].W(P), bias=L["fc1"].b, act="relu", out_dtype=adt)
+            queries = ops.norm(ops.gemm(h, L["fc2"].W(P), bias=L["fc2"].b, resid=queries, out=queries, out_dtype=F32), *L["n3"], eps=1e-5, out_dtype=F32)
+            q = ops.add(queries, tokens, out_dtype=adt)
+            keys = ops.norm(self._attn(L["i2t"], k_pe, q, act(queries), B, HW, Nt, resid=keys, P=P), *L["n4"], eps=1e-5, out_dtype=F32)
+        q = ops.add(queries, tokens, out_dtype=adt)
+        k_pe = ops.add(keys, self.dense_pe, out_dtype=adt)
+        v_k = act(keys)
+        queries = ops.norm(self._attn(self.dec_final, q, k_pe, v_k, B, Nt, HW, resid=queries, P=P), *self.dec_nf, eps=1e-5, out_dtype=F32)
         hs = queries.view(B, Nt, C)
         # upscaling: ConvT(k2,s2) as GEMM + pixel-shuffle epilogue (+feat_s1, LayerNorm2d, GELU), then again (+feat_s0, GELU)
         fs = cfg.feat_size
-        g1 = ops.gemm(v_k, self.up1.w, out_dtype=F32)
-        up1 = ops.convt2x2_epilogue(g1, self.up1.b, s1, self.up_ln[0], self.up_ln[1], 1e-6, B, fs, fs, C // 4, feat_bcast=True)
-        g2 = ops.gemm(up1, self.up2.w, out_dtype=F32)
-        up2 = ops.convt2x2_epilogue(g2, self.up2.b, s0, None, None, 0.0, B, 2 * fs, 2 * fs, C // 8, feat_bcast=True)
+        g1 = ops.gemm(v_k, self.up1.W(P), out_dtype=F32)
+        up1 = ops.convt2x2_epilogue(g1, self.up1.b, s1, self.up_ln[0], self.up_ln[1], 1e-6, B, fs, fs, C // 4, feat_bcast=True, out_dtype=adt)
+        g2 = ops.gemm(up1, self.up2.W(P), out_dtype=F32)
+        up2 = ops.convt2x2_epilogue(g2, self.up2.b, s0, None, None, 0.0, B, 2 * fs, 2 * fs, C // 8, feat_bcast=True, out_dtype=adt)
         # hypernetwork MLPs, batched over the 4 mask tokens
         mt = hs[:, 2:6]                                                # [B,4,C]
-        h = ops.cast(mt.transpose(0, 1).contiguous(), BF)              # [4,B,C]
-        h = ops.gemm(h, self.hyper[0].w, bias=self.hyper[0].b, act="relu")
-        h = ops.gemm(h, self.hyper[1].w, bias=self.hyper[1].b, act="relu")
-        hyper_in = ops.gemm(h, self.hyper[2].w, bias=self.hyper[2].b).transpose(0, 1).contiguous()   # [B,4,C/8] bf16
-        masks = ops.gemm(hyper_in, up2.view(B, -1, C // 8), out_dtype=F32)                             # [B,4,(4fs)^2]
+        h = act(mt.transpose(0, 1).contiguous())                       # [4,B,C]
+        h = ops.gemm(h, self.hyper[0].W(P), bias=self.hyper[0].b, act="relu", out_dtype=adt)
+        h = ops.gemm(h, self.hyper[1].W(P), bias=self.hyper[1].b, act="relu", out_dtype=adt)
+        hyper_in = ops.gemm(h, self.hyper[2].W(P), bias=self.hyper[2].b, out_dtype=adt).transpose(0, 1).contiguous()   # [B,4,C/8]
+        if P:
+            masks = ops.gemm3(hyper_in, up2.view(B, -1, C // 8), out_dtype=F32)                        # both operands are activations: split both
+        else:
+            masks = ops.gemm(hyper_in, up2.view(B, -1, C // 8), out_dtype=F32)                         # [B,4,(4fs)^2]
         if debug is not None:
             debug.update(hs=hs, keys=keys, up1=up1, up2=up2, hyper_in=hyper_in)
-        iou = self._mlp3(self.iou_head, ops.cast(hs[:, 1].contiguous(), BF), final_act="sigmoid")
-        obj = self._mlp3(self.obj_head, ops.cast(hs[:, 0].contiguous(), BF))
+        iou = self._mlp3(self.iou_head, act(hs[:, 1].contiguous()), final_act="sigmoid", P=P)
+        obj = self._mlp3(self.obj_head, act(hs[:, 0].contiguous()), P=P)
         return masks, iou, mt, obj
 
     def forward_sam_heads(self, pix, s0, s1, text_embeds: torch.Tensor | None, B: int):
@@ -324,7 +358,7 @@ class Sam2Engine:
         bi = torch.arange(B, device=self.dev)
         low = low_multi[bi, best].reshape(B, side, side).contiguous()
         tok = toks[bi, best].contiguous()
-        ptr = self._mlp3(self.obj_ptr_proj, ops.cast(tok, BF))
+        ptr = self._mlp3(self.obj_ptr_proj, tok if self.p_heads else ops.cast(tok, BF), P=self.p_heads)
         lam = is_obj.float()
         ptr = lam * ptr + (1 - lam) * self.no_obj_ptr
         return dict(low_res_masks=low, obj_ptr=ptr, ious=iou, object_score_logits=obj, low_res_multimasks=low_multi.view(B, 3, side, side))
@@ -334,59 +368,64 @@ class Sam2Engine:
         """_encode_new_memory sam2_base.py:666-704 + MemoryEncoder.forward memory_encoder.py:159-182.
         top fp32 [HW, C] (raw top-level feature of the frame), low_res_masks fp32 [B, 4fs, 4fs] -> maskmem bf16 [B, HW, mem_dim]."""
         cfg, C = self.cfg, self.cfg.d_model
+        P = self.p_all
+        adt = F32 if P else BF
         B, S = low_res_masks.shape[0], cfg.image_size
         m = ops.bilinear(low_res_masks, S, S, mode=2 if binarize else 1, scale=cfg.sigmoid_scale_for_mem_enc, bias=cfg.sigmoid_bias_for_mem_enc)
         m = m.view(B * S * S, 1)
         side = S
         for j, d in enumerate(self.ds):
-            conv = ops.conv3x3s2_ln_gelu_gemm if d["cin"] >= 16 else ops.conv3x3s2_ln_gelu     # wide stages: im2col + tcgen05 GEMM
-            m = conv(m, d["wg"] if d["cin"] >= 16 else d["w"], d["b"], d["ln"][0], d["ln"][1], 1e-6, B, side, side, d["cin"], d["cout"],
-                     out_dtype=BF if j == 3 else F32)
+            gemm_path = d["cin"] >= 16 and not P                                                   # wide stages: im2col + tcgen05 GEMM (bf16 operands)
+            conv = ops.conv3x3s2_ln_gelu_gemm if gemm_path else ops.conv3x3s2_ln_gelu
+            m = conv(m, d["wg"] if gemm_path else d["w"], d["b"], d["ln"][0], d["ln"][1], 1e-6, B, side, side, d["cin"], d["cout"],
+                     out_dtype=adt if j == 3 else F32)
             side //= 2
-        m = ops.gemm(m, self.ds_out.w, bias=self.ds_out.b, out_dtype=F32)                                # [B*HW, C]
-        px = ops.gemm(ops.cast(top, BF), self.pix_proj.w, bias=self.pix_proj.b, out_dtype=F32)           # [HW, C] shared by objects
+        m = ops.gemm(m, self.ds_out.W(P), bias=self.ds_out.b, out_dtype=F32)                                # [B*HW, C]
+        px = ops.gemm(top if P else ops.cast(top, BF), self.pix_proj.W(P), bias=self.pix_proj.b, out_dtype=F32)   # [HW, C] shared by objects
         x = ops.add(m, px)
         fs = cfg.feat_size
         for f in self.fuser:
             y = ops.dwconv(x, f["dw"], f["dwb"], B, fs, fs, 7)
-            yn = ops.norm(y, *f["ln"], eps=1e-6)
-            h = ops.gemm(yn, f["pw1"].w, bias=f["pw1"].b, act="gelu")
-            x = ops.gemm(h, f["pw2"].w, bias=f["pw2"].b, col_scale=f["gamma"], resid=x, out=x)
-        out = ops.gemm(ops.cast(x, BF), self.mem_out.w, bias=self.mem_out.b)                              # bf16 (sam2_video_predictor.py:967)
+            yn = ops.norm(y, *f["ln"], eps=1e-6, out_dtype=adt)
+            h = ops.gemm(yn, f["pw1"].W(P), bias=f["pw1"].b, act="gelu", out_dtype=adt)
+            x = ops.gemm(h, f["pw2"].W(P), bias=f["pw2"].b, col_scale=f["gamma"], resid=x, out=x, out_dtype=F32)
+        out = ops.gemm(x if P else ops.cast(x, BF), self.mem_out.W(P), bias=self.mem_out.b)                  # bf16 (sam2_video_predictor.py:967)
         return out.view(B, self.HW, cfg.mem_dim)
 
     # ------------------------------------------------------------------------------------------------ memory attention
     def memory_attention(self, top: torch.Tensor, B: int, memory: torch.Tensor, mem_pos: torch.Tensor, n_ptr_tokens: int) -> torch.Tensor:
         """MemoryAttention.forward memory_attention.py:119-169 / MemoryAttentionLayer :58-99 / RoPEAttention sam/transformer.py:285-327.
-        top fp32 [HW, C]; memory bf16 [B, Nk, mem_dim]; mem_pos fp32 [Nk, mem_dim] (shared by objects) -> fp32 [B*HW, C]."""
+        top fp32 [HW, C]; memory bf16 (fp32 when precise="all") [B, Nk, mem_dim]; mem_pos fp32 [Nk, mem_dim] (shared by objects) -> fp32 [B*HW, C]."""
         cfg, C, HW = self.cfg, self.cfg.d_model, self.HW
+        P = self.p_all
+        adt = F32 if P else BF
         fs = cfg.feat_size
         Nk = memory.shape[1]
         n_rope = Nk - n_ptr_tokens
         x = ops.add(top, self.pos_top, alpha=0.1, rows=B * HW)                                           # curr + 0.1*curr_pos, tiled over objects
-        mem2 = memory.reshape(B * Nk, cfg.mem_dim)
-        k_in = ops.add(mem2, mem_pos, out_dtype=BF)
+        mem2 = memory.reshape(B * Nk, cfg.mem_dim)                                                       # bf16, or fp32 in verification mode (_memory_bank)
+        k_in = ops.add(mem2, mem_pos, out_dtype=adt)
         for L in self.ma_layers:
-            t = ops.norm(x, *L["n1"], eps=1e-5)
-            qkv = ops.gemm(t, L["qkv"].w, bias=L["qkv"].b)                                                 # [B*HW, 3C]
+            t = ops.norm(x, *L["n1"], eps=1e-5, out_dtype=adt)
+            qkv = ops.gemm(t, L["qkv"].W(P), bias=L["qkv"].b, out_dtype=adt)                               # [B*HW, 3C]
             ops.rope2d_(qkv[:, :C], C, fs, fs)
             ops.rope2d_(qkv[:, C:2 * C], C, fs, fs)
             q, k, v = (qkv[:, j * C:(j + 1) * C].view(B, HW, 1, C) for j in range(3))
             o = ops.attention(q, k, v, scale=C ** -0.5)
-            x = ops.gemm(o.view(B * HW, C), L["sa_out"].w, bias=L["sa_out"].b, resid=x, out=x)
-            t = ops.norm(x, *L["n2"], eps=1e-5)
+            x = ops.gemm(o.view(B * HW, C), L["sa_out"].W(P), bias=L["sa_out"].b, resid=x, out=x, out_dtype=F32)
+            t = ops.norm(x, *L["n2"], eps=1e-5, out_dtype=adt)
             ca = L["ca"]
-            q = ops.gemm(t, ca["q"].w, bias=ca["q"].b)
+            q = ops.gemm(t, ca["q"].W(P), bias=ca["q"].b, out_dtype=adt)
             ops.rope2d_(q, C, fs, fs)
-            kk = ops.gemm(k_in, ca["k"].w, bias=ca["k"].b).view(B, Nk, C)
+            kk = ops.gemm(k_in, ca["k"].W(P), bias=ca["k"].b, out_dtype=adt).view(B, Nk, C)
             for b in range(B):
                 ops.rope2d_(kk[b, :n_rope], C, fs, fs)                                                    # rope_k_repeat: position = row % HW
-            vv = ops.gemm(mem2, ca["v"].w, bias=ca["v"].b)
+            vv = ops.gemm(mem2, ca["v"].W(P), bias=ca["v"].b, out_dtype=adt)
             o = ops.attention(q.view(B, HW, 1, C), kk.view(B, Nk, 1, C), vv.view(B, Nk, 1, C), scale=C ** -0.5)
-            x = ops.gemm(o.view(B * HW, C), ca["out"].w, bias=ca["out"].b, resid=x, out=x)
-            t = ops.norm(x, *L["n3"], eps=1e-5)
-            h = ops.gemm(t, L["fc1"].w, bias=L["fc1"].b, act="relu")
-            x = ops.gemm(h, L["fc2"].w, bias=L["fc2"].b, resid=x, out=x)
+            x = ops.gemm(o.view(B * HW, C), ca["out"].W(P), bias=ca["out"].b, resid=x, out=x, out_dtype=F32)
+            t = ops.norm(x, *L["n3"], eps=1e-5, out_dtype=adt)
+            h = ops.gemm(t, L["fc1"].W(P), bias=L["fc1"].b, act="relu", out_dtype=adt)
+            x = ops.gemm(h, L["fc2"].W(P), bias=L["fc2"].b, resid=x, out=x, out_dtype=F32)
         return ops.norm(x, *self.ma_norm, eps=1e-5, out_dtype=F32)
 
     def _memory_bank(self, t: int, cond: dict, non_cond: dict, num_frames: int, B: int):
@@ -398,7 +437,7 @@ class Sam2Engine:
         for tp, prev in sel:
             if prev is None:
                 continue
-            mems.append(prev.maskmem)
+            mems.append(ops.cast(prev.maskmem, F32) if self.p_all else prev.maskmem)   # bf16 storage (the reference rounds it, sam2_video_predictor.py:967)
             poss.append(self.mem_pos_slot[cfg.num_maskmem - tp - 1])
         ptrs = [o.obj_ptr for ti, o in cond.items() if ti <= t]
         for d in range(1, min(num_frames, cfg.max_obj_ptrs_in_encoder)):
@@ -411,7 +450,7 @@ class Sam2Engine:
         if ptrs:
             split = cfg.d_model // cfg.mem_dim
             op = torch.stack(ptrs, dim=1).reshape(B, len(ptrs) * split, cfg.mem_dim)   # [B, P*4, mem_dim]
-            mems.append(op.to(BF))
+            mems.append(op if self.p_all else op.to(BF))                        # pointers stay fp32 in the reference; bf16 here is the GEMM operand rounding
             poss.append(torch.zeros((op.shape[1], cfg.mem_dim), device=self.dev))
             n_ptr = op.shape[1]
         return torch.cat(mems, dim=1).contiguous(), torch.cat(poss, dim=0).contiguous(), n_ptr
