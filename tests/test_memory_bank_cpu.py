@@ -16,7 +16,7 @@ def test_bank_selection_matches_oracle(monkeypatch):
     tpos = torch.randn(ocfg.num_maskmem, 1, 1, md, generator=g)
     pos_mem = torch.randn(HW, md, generator=g)                         # maskmem_pos_enc of one frame, tokens x channels
     eng = object.__new__(Sam2Engine)                                   # no CUDA: only the attributes _memory_bank reads
-    eng.cfg, eng.dev = ecfg, torch.device("cpu")
+    eng.cfg, eng.dev, eng.p_all = ecfg, torch.device("cpu"), False
     eng.mem_pos_slot = (pos_mem[None] + tpos.reshape(ocfg.num_maskmem, 1, md)).contiguous()
     # per-frame outputs shared by both sides
     mem = {t: torch.randn(B, HW, md, generator=g).bfloat16() for t in range(T)}
