@@ -24,10 +24,33 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-T_ENC = T_SAM = 8
-N_NEW, SEG_STEP = 12, 5
-VIDEO_HW = (336, 336)
 L_QUERY = 20
+# BASELINE.json configs[1..4] (SURVEY.md §8 "Config shorthand" and §8d for the forced [SEG] counts / new-token counts). One "step" = `clips`
+# independent clips per GPU through the whole path.
+CONFIGS = {
+    2: dict(tag="C2", workload="BASELINE.json configs[1]: 1 clip T_enc=T_sam=8, CLIP 336px, IV2 224px, SAM2 1024px, Phi-3-mini 32L, 1 [SEG], 12 new tokens",
+            t_enc=8, t_sam=8, n_new=12, seg_steps=(5,), video_hw=(336, 336), clips=1),
+    3: dict(tag="C3", workload="BASELINE.json configs[2]: GCG multi-object, 4 clips per GPU (32 clips on 8 GPUs), each T=8 336px, 4 [SEG] objects, 80 new tokens",
+            t_enc=8, t_sam=8, n_new=80, seg_steps=(10, 30, 50, 70), video_hw=(336, 336), clips=4),
+    4: dict(tag="C4", workload="BASELINE.json configs[3]: Refer-DAVIS shape, 1 clip T_enc=T_sam=16, original 480x854, 1 object, 12 new tokens, L=3360 (sliding window cuts)",
+            t_enc=16, t_sam=16, n_new=12, seg_steps=(5,), video_hw=(480, 854), clips=1),
+    5: dict(tag="C5", workload="BASELINE.json configs[4]: MeViS shape, 1 clip per GPU, T_sam=32 (T_enc=16), original 720x1280, 4 objects, 20 new tokens, memory bank full",
+            t_enc=16, t_sam=32, n_new=20, seg_steps=(4, 8, 12, 16), video_hw=(720, 1280), clips=1),
+}
+CFG = CONFIGS[2]
+
+
+def set_config(n: int):
+    global CFG, T_ENC, T_SAM, N_NEW, VIDEO_HW
+    CFG = CONFIGS[n]
+    T_ENC, T_SAM, N_NEW, VIDEO_HW = CFG["t_enc"], CFG["t_sam"], CFG["n_new"], CFG["video_hw"]
+
+
+set_config(2)
+
+
+METRIC = {2: "grounded clips/sec (T=8, 336px) end-to-end", 3: "grounded clips/sec (T=8, 336px, 4 objects, batch of 4 clips per GPU) end-to-end",
+          4: "grounded clips/sec (T=16, 480p) end-to-end", 5: "grounded clips/sec (T=32, 720p, 4 objects) end-to-end"}
 
 
 def _peaks():
@@ -70,14 +93,15 @@ class ClockSampler:
 
 
 def clip_flops(L: int) -> float:
-    """Algorithmic FLOPs of one config-2 clip for the ideal engine: encode once, KV-cached decode."""
+    """Algorithmic FLOPs of one clip of the selected config for the ideal engine: encode once, KV-cached decode."""
+    n_obj = len(CFG["seg_steps"])
     enc = 0.382e12 * T_ENC + 2.25e12 * T_ENC / 4 + 0.022e12 * T_ENC
-    prefill = 2 * 3.62e9 * L + 2 * L * L * 98304
-    decode = N_NEW * (7.6e9 + 4 * L * 98304)
+    prefill = 2 * 3.62e9 * L + 2 * L * min(L, 2048) * 98304
+    decode = N_NEW * (7.6e9 + 4 * min(L, 2048) * 98304)
     sam = 1.620e12 * T_SAM
     for t in range(T_SAM):
         nk = 4096 * min(t, 7) + 4 * min(t, 16)
-        sam += 3.64e9 + 11.6e9 + (t > 0) * (4 * (2.1e9 + 17.2e9 + 1.07e9 + 8.6e9) + 4 * (65536 + 4194304) * nk)
+        sam += n_obj * (3.64e9 + 11.6e9 + (t > 0) * (4 * (2.1e9 + 17.2e9 + 1.07e9 + 8.6e9) + 4 * (65536 + 4194304) * nk))
     return enc + prefill + decode + sam
 
 
@@ -120,9 +144,11 @@ def run_engine(args):
     model = VideoGLaMMForCausalLM(sd, lmm_cfg, sam_cfg, device=dev, validate=False)
     del sd
     torch.cuda.empty_cache()
-    forced = {SEG_STEP: lmm_cfg.seg_token_idx}
-    host = synth_inputs(rank, pinned=True)
-    resident = [t.to(dev) for t in host]
+    forced = {st: lmm_cfg.seg_token_idx for st in CFG["seg_steps"]}
+    n_obj, CPS = len(forced), CFG["clips"]
+    host_clips = [synth_inputs(rank * CPS + j, pinned=True) for j in range(CPS)]       # CPS different clips per GPU and step
+    res_clips = [[t.to(dev) for t in h] for h in host_clips]
+    host, resident = host_clips[0], res_clips[0]
     L = host[3].shape[1] - T_ENC + 208 * T_ENC
 
     def step(inp):
@@ -130,26 +156,31 @@ def run_engine(args):
         out_ids, segs = model.inference([im], [ctx], [sam], ids, None, [VIDEO_HW], max_new_tokens=N_NEW, use_sam2_video_branch=True, forced_tokens=forced)
         return out_ids, segs
 
-    def gather_masks(out_ids, segs):
-        """§8(e): the only collective on the path — token ids + bit-packed final masks to rank 0 (videoglamm_b200.parallel)."""
+    def gather_batch(results):
+        """§8(e): the only collective step on the path — ONE gather per batch of the token ids + the device-packed mask bits to rank 0
+        (videoglamm_b200.parallel: a fixed-size header all_gather + a padded payload gather; nothing is pickled, masks stay bit-packed)."""
         if world > 1:
-            P.gather_results([(rank, out_ids, segs[0])], device=dev)
+            P.gather_results([(rank * len(results) + j, ids, pm) for j, (ids, pm) in enumerate(results)], device=dev, unpack=False)
 
     from videoglamm_b200.pipeline import ClipPipeline
     pipe = ClipPipeline(model)
 
-    def run_clips(inp, steps):
-        """K independent clips. Sequential mode calls model.inference clip by clip; pipelined mode (default) overlaps the LMM stage of
-        clip i+1 with the SAM2 stage of clip i on two streams — same public engine, same results, all K clips complete in the region."""
+    def run_clips(inps, steps):
+        """`steps` batches of CPS independent clips per GPU. Sequential mode calls model.inference clip by clip; pipelined mode (default) overlaps
+        the LMM stage of clip i+1 with the SAM2 stage of clip i on two streams — same public engine, same results; every clip completes (masks on
+        the host as bool arrays) and the batch is gathered to rank 0 inside the region."""
         if args.sequential:
-            for _ in range(steps):
-                out_ids, segs = step(inp)
-                gather_masks(out_ids, segs)
+            res = []
+            for k in range(steps * CPS):
+                out_ids, segs = step(inps[k % CPS])
+                res.append((out_ids, model.last_packed))
+            gather_batch(res)
             return
-        im, ctx, sam, ids = inp
-        clips = [dict(images=im, context_images=ctx, images_for_sam=sam, input_ids=ids, original_size=VIDEO_HW) for _ in range(steps)]
-        for out_ids, segs in pipe.run(clips, N_NEW, forced_tokens=forced):
-            gather_masks(out_ids, [segs])
+        clips = []
+        for k in range(steps * CPS):
+            im, ctx, sam, ids = inps[k % CPS]
+            clips.append(dict(images=im, context_images=ctx, images_for_sam=sam, input_ids=ids, original_size=VIDEO_HW))
+        gather_batch([(out_ids, pm) for out_ids, _, pm in pipe.run(clips, N_NEW, forced_tokens=forced)])
 
     def timed(inp, steps):
         if world > 1:
@@ -169,7 +200,7 @@ def run_engine(args):
 
     for _ in range(max(args.warmup, 3)):
         step(resident)
-    run_clips(resident, 2)                       # pipeline warm-up (per-thread stream state, graph pools)
+    run_clips(res_clips, 2)                      # pipeline warm-up (per-thread stream state, graph pools)
     torch.cuda.synchronize()
     lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat0.record()
@@ -181,9 +212,9 @@ def run_engine(args):
     if rank == 0:
         sampler.start()
     ops.launch_count_reset()
-    ms = timed(resident, args.steps)
+    ms = timed(res_clips, args.steps)
     launches = ops.launch_count()
-    ms_e2e = timed(host, args.steps)            # same call, HOST pinned inputs: H2D of every input + D2H of the masks inside the region
+    ms_e2e = timed(host_clips, args.steps)      # same call, HOST pinned inputs: H2D of every input + D2H of the masks inside the region
     clocks = sampler.stop() if rank == 0 else {}
     # dominant kernel = the tcgen05 GEMM: per-launch CUDA-event timing on one extra (untimed) step
     from videoglamm_b200 import graphs
@@ -198,21 +229,23 @@ def run_engine(args):
             print("gemm shape", row, file=sys.stderr)
     dec = time_decode_step(model, L) if rank == 0 else None
     mdec = time_mask_decoder(model) if rank == 0 else None
-    cpu = cpu_baseline_sample(L) if (rank == 0 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_sample(L) if (rank == 0 and not args.no_cpu_baseline and world == 1) else None
     if rank == 0:
         tf_peak, hbm_peak, src = _peaks()
-        n_clips = args.steps * world
+        n_clips = args.steps * world * CPS
         tp, tall = prof["tensor_big"], prof["tensor"]
         ach = tp["flops"] / (tp["ms"] * 1e-3) / 1e12 if tp["ms"] > 0 else 0.0
         ach_all = tall["flops"] / (tall["ms"] * 1e-3) / 1e12 if tall["ms"] > 0 else 0.0
-        h2d = sum(t.numel() * t.element_size() for t in host)
-        d2h = T_SAM * VIDEO_HW[0] * VIDEO_HW[1] + (host[3].numel() + N_NEW) * 8
+        h2d = CPS * sum(t.numel() * t.element_size() for t in host)
+        d2h = CPS * (T_SAM * n_obj * ((VIDEO_HW[0] * VIDEO_HW[1] + 7) // 8) + 8)     # bit-packed masks + the per-token id reads of the decode loop
+        ms_clip = ms / (args.steps * CPS)
         line = {
-            "metric": "grounded clips/sec (T=8, 336px) end-to-end", "value": n_clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
+            "metric": METRIC[args.config], "value": n_clips / (ms * 1e-3), "unit": "clips/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: 1 clip T_enc=T_sam=8, CLIP 336px, IV2 224px, SAM2 1024px, Phi-3-mini 32L, 1 [SEG], 12 new tokens",
-                       "llm_seq_len": L, "clips_per_step_per_gpu": 1, "parallelism": f"dp{world} (independent clips, masks gathered to rank 0)",
+            "config": {"workload": CFG["workload"], "precision": "bf16 operands / fp32 accumulation; SAM2 mask decoder in fp32-grade split-bf16 arithmetic (precise=heads)",
+                       "llm_seq_len": L, "clips_per_step_per_gpu": CPS, "objects_per_clip": n_obj,
+                       "parallelism": f"dp{world} (independent clips, bit-packed masks gathered to rank 0 once per batch)",
                        "l2": "no explicit flush: each step streams 10.8 GB of bf16 weights (>> 126 MB L2)",
                        "algorithmic_tflop_per_clip": clip_flops(L) / 1e12,
                        "schedule": "sequential clips" if args.sequential else "2-stage pipeline over clips (LMM of clip i+1 || SAM2 of clip i, two streams)",
@@ -222,12 +255,12 @@ def run_engine(args):
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip with >= 1 GFLOP: "
                          f"{tp['n']} launches carrying {tp['flops'] / max(tall['flops'], 1):.1%} of the GEMM FLOPs)", "achieved": ach, "peak": tf_peak,
                          "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": NCU_TRAFFIC["dram_bytes"], "traffic_detail": NCU_TRAFFIC, "peak_source": f"{src} bf16_tflops_sustained",
-                         "launches": tp["n"], "gemm_ms_per_clip": tp["ms"], "gemm_share_of_step": tp["ms"] / (ms / args.steps),
+                         "launches": tp["n"], "gemm_ms_per_clip": tp["ms"], "gemm_share_of_step": tp["ms"] / ms_clip,
                          "all_tensor_gemm_launches": {"launches": tall["n"], "ms_per_clip": tall["ms"], "achieved": ach_all, "frac": ach_all / tf_peak,
                                                       "note": "includes ~700 sub-GFLOP launches whose event-timed duration is launch latency"},
                          "note": "algorithmic 2MNK per launch / per-launch CUDA events on an extra eager (non-graph) step; traffic = ncu dram bytes of the "
                                  "largest-share shape (profiles/r01_ncu_targets_*.md)",
-                         "whole_clip_tflops": clip_flops(L) / (ms / args.steps * 1e-3) / 1e12},
+                         "whole_clip_tflops": clip_flops(L) / (ms_clip * 1e-3) / 1e12},
             "roofline_decode": {"bound": "hbm", "kernel": "one KV-cached Phi-3 decode step (graph replay: 4 weight-streaming GEMVs + RoPE/append + "
                                 "single-query attention per layer, lm_head, argmax)", "achieved": dec["gbs"], "peak": hbm_peak, "unit": "GB/s",
                                 "frac": dec["gbs"] / hbm_peak, "bytes_per_step": dec["bytes"], "ms_per_step": dec["ms"], "peak_source": f"{src} hbm_gbs"},
@@ -334,7 +367,7 @@ def cpu_baseline_sample(L: int) -> dict:
 
     with torch.no_grad():
         # CLIP layer (23 run), 8 frames x 577 tokens
-        x = torch.randn(8, 577, 1024, generator=g)
+        x = torch.randn(T_ENC, 577, 1024, generator=g)
         w = {k: rnd(*s) for k, s in dict(qkv=(3072, 1024), o=(1024, 1024), f1=(4096, 1024), f2=(1024, 4096)).items()}
 
         def vit_layer(x, w, heads, act):
@@ -345,7 +378,7 @@ def cpu_baseline_sample(L: int) -> dict:
             return x + F.linear(act(F.linear(F.layer_norm(x, (C,)), w["f1"])), w["f2"])
 
         clock("clip", lambda: vit_layer(x, w, 16, lambda z: z * torch.sigmoid(1.702 * z)), 23)
-        x2 = torch.randn(2, 1025, 1408, generator=g)
+        x2 = torch.randn(T_ENC // 4, 1025, 1408, generator=g)
         w2 = {k: rnd(*s) for k, s in dict(qkv=(4224, 1408), o=(1408, 1408), f1=(6144, 1408), f2=(1408, 6144)).items()}
         clock("iv2", lambda: vit_layer(x2, w2, 16, F.gelu), 39)
         # Phi-3 layer at L tokens; the reference-as-written runs N_NEW+2 full forwards (use_cache=False, VideoGLaMM.py:782-799)
@@ -371,18 +404,62 @@ def cpu_baseline_sample(L: int) -> dict:
             xh = torch.randn(1, side, side, dim, generator=g)
             clock(f"hiera_stage{si}", lambda: O.hiera_block(bsd, p, xh, specs[bi]), cnt * T_SAM)
             hier += t[f"hiera_stage{si}"]
+        # SAM2 heads / memory path at the true widths and 64x64 feature maps (tiny Hiera: its weights are not used by these stages)
+        n_obj = len(CFG["seg_steps"])
+        hcfg = O.Sam2Cfg(embed_dim=32, stages=(1, 2, 3, 1), global_att_blocks=(4,))
+        from oracle import weights as Wt
+        ssd = Wt.make_sam2_state_dict(hcfg, 1)
+        fs = hcfg.feat_size
+        pix, s0f, s1f = torch.randn(n_obj, 256, fs, fs, generator=g), torch.randn(n_obj, 32, 4 * fs, 4 * fs, generator=g), torch.randn(n_obj, 64, 2 * fs, 2 * fs, generator=g)
+        clock("sam_heads", lambda: O.forward_sam_heads(ssd, hcfg, pix, [s0f, s1f]), T_SAM)
+        high = torch.randn(n_obj, 1, hcfg.image_size, hcfg.image_size, generator=g)
+        clock("memory_encoder", lambda: O.encode_new_memory(ssd, hcfg, pix, high, is_mask_from_pts=False), T_SAM)
+        f_avg = round(sum(min(tt, 7) for tt in range(1, T_SAM)) / (T_SAM - 1))   # memory frames in an average bank (+ 16 pointers = 64 tokens)
+        nk_avg = 4096 * f_avg + 64
+        curr, cpos = torch.randn(fs * fs, n_obj, 256, generator=g), torch.randn(fs * fs, n_obj, 256, generator=g)
+        mem, mpos = torch.randn(nk_avg, n_obj, 64, generator=g), torch.randn(nk_avg, n_obj, 64, generator=g)
+        clock("memory_attention", lambda: O.memory_attention(ssd, hcfg, curr, cpos, mem, mpos, 64), T_SAM - 1)
     llm_forwards = N_NEW + 2
-    total = t["clip"] + t["iv2"] + t["phi3_layer_full_forward"] * llm_forwards + hier
+    sam_heads = t["sam_heads"] + t["memory_encoder"] + t["memory_attention"]
+    total = t["clip"] + t["iv2"] + t["phi3_layer_full_forward"] * llm_forwards + hier + sam_heads
     return {"value": 1.0 / total, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle (CPU fp32 port of the reference path) timed per full-width layer and scaled by multiplicity: CLIP 1 layer x8 frames (x23), "
-                      "IV2 1 block x2 chunks (x39), Phi-3 1 layer at L tokens (x32 layers x14 full forwards, use_cache=False as the reference), "
-                      "Hiera 1 block per stage (x2/6/36/4 x8 frames); SAM2 decoder/memory stages omitted (<3% of CPU time)",
+            "sample": f"oracle (CPU fp32 port of the reference path, {CFG['tag']}) timed per full-width stage and scaled by multiplicity: CLIP 1 layer x{T_ENC} frames "
+                      f"(x23), IV2 1 block x{T_ENC // 4} chunks (x39), Phi-3 1 layer at L={L} tokens (x32 layers x{llm_forwards} full forwards: use_cache=False as the "
+                      f"reference), Hiera 1 block per stage (x2/6/36/4 x{T_SAM} frames), SAM heads (prompt encoder + mask decoder + pointer MLP, {n_obj} objects) "
+                      f"x{T_SAM} frames, memory encoder x{T_SAM}, memory attention (4 layers, average bank of {nk_avg} keys) x{T_SAM - 1}; pre/post-processing excluded",
             "seconds_per_clip_extrapolated": total, "stage_seconds": t}
 
 
+def reference_inference_reduced() -> dict:
+    """ONE call of the UNMODIFIED reference's VideoGLaMMForCausalLM.inference (video branch) on the host cores, from the package staged under
+    baseline/_ref (oracle/build_ref.py:stage_reference; absent -> reported as such). Config: the reduced one of tests/golden (true IV2 / CLIP
+    widths and resolutions, reduced depths, tiny Phi-3 and Hiera, 3 SAM2 frames at 256 px, 2 objects, 5 new tokens) — a functional run of the
+    reference's own code path next to the per-stage full-width sample, not an estimate of the full config."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "VideoGLaMM", "model", "VideoGLaMM.py")):
+        return {"unavailable": "baseline/_ref not staged on this box"}
+    os.environ["VG_REFERENCE_ROOT"] = ref_root
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    try:
+        import numpy as np
+        import make_golden as MG
+        ref, *_ = MG.ref_videoglamm()
+        MG.ref_e2e_run(ref)                                  # warm-up
+        t0 = time.perf_counter()
+        ids, masks = MG.ref_e2e_run(ref)
+        dt = time.perf_counter() - t0
+        g = np.load(os.path.join(ROOT, "tests", "golden", "e2e_tiny.npz"))
+        return {"seconds_per_call": dt, "config": "tests/golden e2e_tiny (T_enc=4, T_sam=3 at 256px, 2 [SEG], 5 new tokens, reduced depths)",
+                "matches_committed_golden": bool(np.array_equal(ids, g["output_ids"])), "code": "unmodified reference, baseline/_ref"}
+    except Exception as e:  # the arm must still print its line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
-    """`--impl reference`: the reference's own CPU implementation of the path = the oracle port (the reference tree is not on the GPU box),
-    all host threads, same config/metric. Each step is the bounded sample above."""
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores, all host threads, same config/metric.
+    `value` comes from the bounded per-stage sample of the oracle port (every stage of the path, full width, scaled by multiplicity);
+    `ms_per_step` = 1000 / value (the extrapolated time of one step's clips); the wall time of the sample itself and one REAL call of the unmodified
+    reference's inference() at a reduced config are reported next to it."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -392,16 +469,21 @@ def run_reference(args):
         res = cpu_baseline_sample(L)
     vals = []
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(max(args.steps, 1)):
         res = cpu_baseline_sample(L)
         vals.append(res["value"])
     wall = time.perf_counter() - t0
     v = sum(vals) / len(vals)
-    line = {"impl": "reference", "metric": "grounded clips/sec (T=8, 336px) end-to-end", "value": v, "unit": "clips/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    real = reference_inference_reduced()
+    line = {"impl": "reference", "metric": METRIC[args.config], "value": v, "unit": "clips/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * CFG["clips"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1] (same as the engine arm); bounded per-layer sample extrapolated to one clip", "device": "host CPU"},
-            "cpu_baseline": {**res, "value": v}, "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "config": {"workload": CFG["workload"] + " (same as the engine arm)", "device": "host CPU", "clips_per_step_per_gpu": CFG["clips"],
+                       "sample_wall_ms_per_step": wall / max(args.steps, 1) * 1e3,
+                       "note": "value = 1 / (per-stage full-width sample x multiplicity): a bounded sample of the workload, not a full run (one full-size clip takes "
+                               "minutes on host cores)"},
+            "cpu_baseline": {**res, "value": v}, "reference_inference_reduced": real,
+            "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -413,7 +495,9 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sequential", action="store_true", help="one clip at a time (latency mode); default overlaps consecutive clips")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]: 2 (headline, default), 3, 4, 5")
     a = ap.parse_args()
+    set_config(a.config)
     if a.impl == "reference":
         run_reference(a)
     else:

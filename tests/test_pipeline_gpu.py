@@ -28,8 +28,10 @@ def test_pipeline_matches_sequential_inference():
                            max_new_tokens=5, use_sam2_video_branch=True, forced_tokens=forced) for c in clips]
     seq = [(ids.cpu().clone(), {t: {o: m.copy() for o, m in fr.items()} for t, fr in segs[0].items()}) for ids, segs in seq]
     out = ClipPipeline(model).run(clips, 5, forced_tokens=forced)
-    for (ids_a, seg_a), (ids_b, seg_b) in zip(seq, out):
+    for (ids_a, seg_a), (ids_b, seg_b, packed) in zip(seq, out):
         assert torch.equal(ids_a, ids_b.cpu())
+        back = packed.to_segments()                                   # the device-packed bits (multi-GPU gather payload) carry the same masks
+        assert all(np.array_equal(back[t][o], seg_b[t][o]) for t in seg_b for o in seg_b[t])
         assert sorted(seg_a) == sorted(seg_b)
         for t in seg_a:
             for o in seg_a[t]:

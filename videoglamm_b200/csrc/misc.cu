@@ -505,6 +505,34 @@ __global__ void bilinear_kernel(const float* x, void* y, int n, int ih, int iw, 
   reinterpret_cast<float*>(y)[i] = o;
 }
 
+// mode 4 of vg_bilinear: threshold (> 0) and bit-pack, one thread per output BYTE = 8 consecutive pixels of one plane (MSB first, like
+// numpy.packbits); each plane is padded to a whole number of bytes. Divides the mask bytes that leave the GPU by 8.
+__global__ void bilinear_pack_kernel(const float* x, uint8_t* y, int n, int ih, int iw, int oh, int ow) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long bpp = (static_cast<long long>(oh) * ow + 7) / 8;  // bytes per plane
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n * bpp) return;
+  const int img = static_cast<int>(i / bpp);
+  const long long byte = i - img * bpp;
+  const float ry = static_cast<float>(ih) / oh, rx = static_cast<float>(iw) / ow;
+  const float* p = x + static_cast<long long>(img) * ih * iw;
+  unsigned bits = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const long long px = byte * 8 + b;
+    if (px >= static_cast<long long>(oh) * ow) break;
+    const int ox = static_cast<int>(px % ow), oy = static_cast<int>(px / ow);
+    const float sy = fmaxf((oy + 0.5f) * ry - 0.5f, 0.f), sx = fmaxf((ox + 0.5f) * rx - 0.5f, 0.f);
+    const int y0 = static_cast<int>(sy), x0 = static_cast<int>(sx);
+    const int y1 = min(y0 + 1, ih - 1), x1 = min(x0 + 1, iw - 1);
+    const float ly = sy - y0, lx = sx - x0;
+    const float v = (1.f - ly) * ((1.f - lx) * p[y0 * iw + x0] + lx * p[y0 * iw + x1]) + ly * ((1.f - lx) * p[y1 * iw + x0] + lx * p[y1 * iw + x1]);
+    if (v > 0.f) bits |= 0x80u >> b;
+  }
+  y[i] = static_cast<uint8_t>(bits);
+}
+
 __global__ void rope2d_kernel(void* x, int xdt, long long ld, int nrows, int dim, int gw, int gh) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
@@ -862,6 +890,12 @@ extern "C" int vg_conv3x3s2_ln_gelu(const void* x, int x_dtype, const float* w, 
 
 extern "C" int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, int mode, float scale, float bias, void* stream) {
   if (!x || !y) return set_error(VG_EINVAL, "vg_bilinear: null");
+  if (mode == 4) {
+    const long long bytes = static_cast<long long>(n) * ((static_cast<long long>(oh) * ow + 7) / 8);
+    launch_k(bilinear_pack_kernel, dim3(blocks_for(bytes, 256)), dim3(256), 0, STREAM, x, static_cast<uint8_t*>(y), n, ih, iw, oh, ow);
+    count_launch();
+    return check_launch("bilinear_pack_kernel");
+  }
   launch_k(bilinear_kernel, dim3(blocks_for(static_cast<long long>(n) * oh * ow, 256)), dim3(256), 0, STREAM, x, y, n, ih, iw, oh, ow, mode, scale, bias);
   count_launch();
   return check_launch("bilinear_kernel");

@@ -135,7 +135,25 @@ class VideoGLaMMForCausalLM:
             stacked = (logits > 0).numpy()
             segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}
             return out_ids, [segs], logits
-        frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary=True)
-        stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)                 # ONE device->host copy per clip
-        segs = {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])}
+        frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary="packed")
+        segs, self.last_packed = self.masks_to_host(frames, int(H), int(W))
         return out_ids, [segs]
+
+    def masks_to_host(self, frames: list, H: int, W: int):
+        """Per-frame bit-packed device masks [n_obj, ceil(H*W/8)] -> ({frame: {obj: bool ndarray [H,W]}}, PackedMasks still on the device).
+        ONE device->host copy per clip, of H*W/8 bytes per mask, into pinned memory; the bool arrays are expanded on the host."""
+        from ..parallel import PackedMasks
+        packed = torch.stack(frames)                                                  # [T, n_obj, bpp] uint8
+        key = tuple(packed.shape)
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        host = self._pinned.get(key)
+        if host is None:
+            if len(self._pinned) > 16:
+                self._pinned.clear()
+            host = self._pinned[key] = torch.empty(key, dtype=torch.uint8, pin_memory=True)
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        T, n_obj = key[:2]
+        bits = np.unpackbits(host.numpy(), axis=-1, count=H * W).reshape(T, n_obj, H, W).view(np.bool_)
+        return {t: {o: bits[t, o] for o in range(n_obj)} for t in range(T)}, PackedMasks(packed, (T, n_obj, H, W))

@@ -342,11 +342,14 @@ def conv3x3s2_ln_gelu(x: torch.Tensor, w: torch.Tensor, bias, ln_w, ln_b, eps: f
 
 
 def bilinear(x: torch.Tensor, oh: int, ow: int, *, mode: int = 0, scale: float = 1.0, bias: float = 0.0) -> torch.Tensor:
-    """x [n, ih, iw] fp32 -> [n, oh, ow] fp32 (mode 0/1/2) or uint8 (mode 3: x > 0)"""
+    """x [n, ih, iw] fp32 -> [n, oh, ow] fp32 (mode 0/1/2), uint8 (mode 3: x > 0) or bit-packed uint8 [n, ceil(oh*ow/8)] (mode 4: x > 0, numpy.packbits order)"""
     _require_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3
     n, ih, iw = x.shape
-    y = torch.empty((n, oh, ow), device=x.device, dtype=torch.uint8 if mode == 3 else torch.float32)
+    if mode == 4:
+        y = torch.empty((n, (oh * ow + 7) // 8), device=x.device, dtype=torch.uint8)
+    else:
+        y = torch.empty((n, oh, ow), device=x.device, dtype=torch.uint8 if mode == 3 else torch.float32)
     L.check(L.lib().vg_bilinear(_ptr(x), _ptr(y), n, ih, iw, oh, ow, mode, C.c_float(scale), C.c_float(bias), _stream()), "vg_bilinear")
     return y
 

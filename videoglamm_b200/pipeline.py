@@ -22,7 +22,8 @@ class ClipPipeline:
     @torch.no_grad()
     def run(self, clips: list[dict], max_new_tokens: int, forced_tokens: dict | None = None) -> list[tuple]:
         """clips: [{"images", "context_images", "images_for_sam", "input_ids", "original_size"}] (host or device tensors).
-        Returns [(output_ids, segments)] in order; segments as in `inference` ({frame: {obj: bool ndarray}})."""
+        Returns [(output_ids, segments, packed)] in order; segments as in `inference` ({frame: {obj: bool ndarray}}), packed = the same masks
+        bit-packed and still on the device (parallel.PackedMasks; None for a clip without [SEG]) for the multi-GPU gather."""
         m = self.model
         dev = torch.device("cuda", self.model.device.index if self.model.device.index is not None else torch.cuda.current_device())
         q: queue.Queue = queue.Queue(maxsize=self.depth)
@@ -70,12 +71,12 @@ class ClipPipeline:
                             self.s_sam.wait_event(ev_copy)
                             sam_dev.record_stream(self.s_sam)
                         if emb.shape[0] == 0:
-                            results[i] = (out_ids, {})
+                            results[i] = (out_ids, {}, None)
                             continue
                         H, W = clips[i]["original_size"]
-                        frames = m.sam.run_video(sam_dev, emb[:, None, :], (int(H), int(W)), binary=True)
-                        stacked = torch.stack(frames).cpu().numpy().astype(np.bool_)
-                        results[i] = (out_ids, {t: {o: stacked[t, o] for o in range(emb.shape[0])} for t in range(stacked.shape[0])})
+                        frames = m.sam.run_video(sam_dev, emb[:, None, :], (int(H), int(W)), binary="packed")
+                        segs, packed = m.masks_to_host(frames, int(H), int(W))
+                        results[i] = (out_ids, segs, packed)
             except Exception as e:
                 errors.append(e)
                 while q.get() is not None:

@@ -20,6 +20,7 @@ from .graphs import GraphedStage
 from .config import Sam2Config
 
 NO_OBJ_SCORE = -1024.0
+_OUT_MODE = {False: 0, True: 3, "packed": 4}   # vg_bilinear output map of the final upsampling: fp32 logits / uint8 (x>0) / bit-packed (x>0)
 BF, F32 = torch.bfloat16, torch.float32
 
 
@@ -457,7 +458,7 @@ class Sam2Engine:
 
     # ------------------------------------------------------------------------------------------------ video session
     @torch.no_grad()
-    def run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False, collect: dict | None = None):
+    def run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False, collect: dict | None = None):
         """Graph-captured entry: the whole session's launch sequence is a function of (T, n_obj, video size) only. Returns a list of
         per-frame [n_obj, H, W] tensors (views of graph-owned memory, valid until the next call with the same shapes)."""
         if collect is not None:
@@ -467,10 +468,11 @@ class Sam2Engine:
                            images=images, text_embeds=text_embeds.to(F32))
         return list(out.unbind(0))
 
-    def _run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False, collect: dict | None = None):
+    def _run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False, collect: dict | None = None):
         """The VideoGLaMM video-branch session (VideoGLaMM.py:846-875 -> sam2_video_predictor.py init_state_from_tensor :109-180,
         add_new_text :416-495 on frame 0 per object, propagate_in_video :745-827 incl. preflight :675-729).
-        images [T,3,S,S] fp32 cuda; text_embeds [n_obj,1,C]. Returns per frame [n_obj,H,W]: fp32 logits (binary=False) or uint8 (x>0)."""
+        images [T,3,S,S] fp32 cuda; text_embeds [n_obj,1,C]. Returns per frame [n_obj,H,W]: fp32 logits (binary=False) or uint8 (x>0); binary="packed": per frame uint8 [n_obj, ceil(H*W/8)],
+        the (x>0) bits packed 8 per byte by the upsampling kernel (videoglamm_b200.parallel wire format)."""
         cfg = self.cfg
         T, B = images.shape[0], text_embeds.shape[0]
         HW, C = self.HW, cfg.d_model
@@ -506,12 +508,12 @@ class Sam2Engine:
                     non_cond[old].maskmem = None                                   # ring buffer: nothing older is ever read again
             if collect is not None:
                 collect.setdefault("low_res", {})[t] = pred
-            outs.append(ops.bilinear(pred, Hv, Wv, mode=3 if binary else 0))
+            outs.append(ops.bilinear(pred, Hv, Wv, mode=_OUT_MODE[binary]))
         return outs
 
     # ------------------------------------------------------------------------------------------------ framewise branch
     @torch.no_grad()
-    def run_framewise(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool = False):
+    def run_framewise(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False):
         """SAM2 part of VideoGLaMM_SAM2.inference_framewise (VideoGLaMM.py:598-768 with get_visual_embs_sam2 :205-241): every frame is
         decoded independently — image_embed = top-level feature + no_mem_embed, prompt = the text token only (no padding points),
         multimask_output=False with the stability fallback (mask_decoder.py:247-295), repeat_image over the objects,
@@ -531,7 +533,7 @@ class Sam2Engine:
                 masks, iou, _, _ = self.mask_decoder(pix, f["s0"], f["s1"], sparse)
                 sel = ops.multimask_select(masks, iou.contiguous())
                 low = masks[torch.arange(B, device=self.dev), sel].reshape(B, side, side).contiguous()
-                outs.append(ops.bilinear(low, Hv, Wv, mode=3 if binary else 0))
+                outs.append(ops.bilinear(low, Hv, Wv, mode=_OUT_MODE[binary]))
         return outs
 
     # ------------------------------------------------------------------------------------------------ predictor surface
