@@ -201,6 +201,7 @@ def run_engine(args):
     for _ in range(max(args.warmup, 3)):
         step(resident)
     run_clips(res_clips, 2)                      # pipeline warm-up (per-thread stream state, graph pools)
+    run_clips(host_clips, 2)                     # ... and of the host-input path (side-stream allocator pools, pinned result buffers)
     torch.cuda.synchronize()
     lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat0.record()
