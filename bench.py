@@ -265,7 +265,8 @@ def run_engine(args):
             "roofline_decode": {"bound": "hbm", "kernel": "one KV-cached Phi-3 decode step (graph replay: 4 weight-streaming GEMVs + RoPE/append + "
                                 "single-query attention per layer, lm_head, argmax)", "achieved": dec["gbs"], "peak": hbm_peak, "unit": "GB/s",
                                 "frac": dec["gbs"] / hbm_peak, "bytes_per_step": dec["bytes"], "ms_per_step": dec["ms"], "peak_source": f"{src} hbm_gbs"},
-            "mask_decoder": {"kernel_group": "PromptEncoder dense + TwoWayTransformer + upscaling + hypernetwork MLPs + IoU/object heads (graph replay, B=1 object)",
+            "mask_decoder": {"kernel_group": "vg_mask_decoder: PromptEncoder dense + TwoWayTransformer + upscaling + hypernetwork MLPs + IoU/object heads, fp32 "
+                             "(graph replay, B=1 object)",
                              "ms_per_frame": mdec["ms"], "launches": mdec["launches"], "algorithmic_bytes": mdec["bytes"], "achieved_gbs": mdec["gbs"],
                              "hbm_frac": mdec["gbs"] / hbm_peak, "algorithmic_gflop": mdec["gflop"], "achieved_tflops": mdec["tflops"],
                              "tensor_frac": mdec["tflops"] / tf_peak},
@@ -321,8 +322,8 @@ def time_mask_decoder(model, reps: int = 20) -> dict:
     g = torch.Generator(device="cpu").manual_seed(1)
     HW, C = sam.HW, cfg.d_model
     pix = torch.randn(HW, C, generator=g).to(dev)
-    s0 = torch.randn(16 * HW, C // 8, generator=g).to(dev).bfloat16()
-    s1 = torch.randn(4 * HW, C // 4, generator=g).to(dev).bfloat16()
+    s0 = torch.randn(16 * HW, C // 8, generator=g).to(dev)
+    s1 = torch.randn(4 * HW, C // 4, generator=g).to(dev)
     sparse = torch.randn(1, 3, C, generator=g).to(dev)
     stage = GraphedStage("mask_decoder_bench")
     run = lambda: stage(("md",), lambda pix, s0, s1, sparse: sam.mask_decoder(pix, s0, s1, sparse)[0], pix=pix, s0=s0, s1=s1, sparse=sparse)

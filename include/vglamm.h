@@ -205,6 +205,57 @@ int vg_split3(const float* x, long long ldx, void* out, long long ldo, long long
  * Product path: the two-way transformer's attentions (.../sam/transformer.py:233-260: 9x9, 9x4096, 4096x9 tokens). Verification mode: every
  * attention of the path (causal, sliding window and Hiera 2D windows supported; nk_dev / fused_rope_theta are not). */
 int vg_attention_f32(const VgAttention* a, void* stream);
+/* ------------------------------------------------------------------------------------------------ fused SAM2 mask decoder
+ * ONE launch for: src = image_embed + dense prompt (no_mask_embed), TwoWayTransformer (2 x {token self-attention, token->image attention, MLP 2048,
+ * image->token attention} + final token->image attention + LayerNorm), ConvTranspose2d(256->64,k2,s2) + feat_s1 + LayerNorm2d + GELU,
+ * ConvTranspose2d(64->32,k2,s2) + feat_s0 + GELU, the 4 hypernetwork MLPs, masks = hyper_in @ upscaled, IoU head (sigmoid) and object-score head —
+ * MaskDecoder.predict_masks .../sam2/modeling/sam/mask_decoder.py:167-245, TwoWayTransformer .../sam/transformer.py:63-115, 160-193, 233-260 —
+ * for all B objects of a frame (grid = (HW/32 row blocks, B); the blocks of one object synchronise through a counter in `workspace`).
+ * fp32 arithmetic throughout. Weight pointers are fp32 device arrays; "T" marks arrays stored TRANSPOSED ([in][out]) because the image-side
+ * contractions read them coalesced over the output column; the rest are nn.Linear layout ([out][in]). pek / peq are the load-time constant products
+ * dense_pe @ Wk^T (token->image k projections of layer 0, layer 1, final) and dense_pe @ Wq^T (image->token q projections of layer 0, 1), [HW][128].
+ */
+typedef struct VgLinear { const float* w; const float* b; } VgLinear;
+typedef struct VgMdAttn { VgLinear q, k, v, out; } VgMdAttn;
+typedef struct VgMdLayer {
+  VgMdAttn sa;                 /* token self-attention: all [256][256] */
+  VgMdAttn t2i;                /* q [128][256]; k T[256][128]; v T[256][128]; out [256][128] */
+  VgMdAttn i2t;                /* q T[256][128]; k [128][256]; v [128][256]; out T[128][256] */
+  VgLinear n1, n2, n3, n4;     /* LayerNorm weight / bias [256] */
+  VgLinear fc1, fc2;           /* [2048][256], [256][2048] */
+} VgMdLayer;
+typedef struct VgMaskDecoderWeights {
+  VgMdLayer layer[2];
+  VgMdAttn final_t2i;          /* like t2i */
+  VgLinear norm_final;
+  VgLinear up1;                /* T[256][4*64], column (dy*2+dx)*64 + co; bias [64] */
+  VgLinear up_ln;              /* LayerNorm2d(64) */
+  VgLinear up2;                /* T[64][4*32], column (dy*2+dx)*32 + co; bias [32] */
+  VgLinear hyper[4][3];        /* [256][256], [256][256], [32][256] per mask token */
+  VgLinear iou[3];             /* [256][256], [256][256], [4][256] */
+  VgLinear obj[3];             /* [256][256], [256][256], [1][256] */
+  const float* pek[3];
+  const float* peq[2];
+} VgMaskDecoderWeights;
+typedef struct VgMaskDecoder {
+  const float* pix;            /* fp32 [B][HW][256] image embedding rows per object ([HW][256] shared by all objects when pix_shared != 0) */
+  int pix_shared;
+  const float* dense_pe;       /* fp32 [HW][256] (get_dense_pe; only used through pek / peq, kept for validation) */
+  const float* no_mask;        /* fp32 [256] dense prompt embedding */
+  const float* s0;             /* fp32 [16*HW][32] high-res feature of the frame (conv_s0), shared by the objects */
+  const float* s1;             /* fp32 [4*HW][64]  (conv_s1) */
+  const float* tokens;         /* fp32 [B][Nt][256]: [obj_score, iou, 4 mask tokens] + sparse prompt embeddings */
+  int B, Nt, fs;               /* objects, tokens per object (<= 12), feature-map side (HW = fs*fs, a multiple of 32) */
+  int C, heads, mlp, depth;    /* must be 256, 8, 2048, 2 (the SAM2 decoder geometry this kernel is built for) */
+  const VgMaskDecoderWeights* weights;   /* HOST pointer to the table of device pointers */
+  float* masks;                /* out fp32 [B][4][(4*fs)^2] */
+  float* iou;                  /* out fp32 [B][4] (sigmoid) */
+  float* mask_tokens;          /* out fp32 [B][4][256] (hs[:, 2:6]) */
+  float* obj;                  /* out fp32 [B] object-score logits */
+  void* workspace; long long workspace_bytes;   /* >= vg_mask_decoder_workspace_bytes(B, fs) */
+} VgMaskDecoder;
+long long vg_mask_decoder_workspace_bytes(int B, int fs);
+int vg_mask_decoder(const VgMaskDecoder* d, void* stream);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

@@ -102,6 +102,35 @@ def test_mask_decoder(ctx, with_text):
     assert torch.equal(eh["low_res_masks"].cpu() > 0, oh["low_res_masks"][:, 0] > 0)
 
 
+@pytest.mark.parametrize("B,with_text", [(1, True), (2, False), (4, True)])
+def test_fused_mask_decoder_kernel(ctx, B, with_text):
+    """vg_mask_decoder (ONE launch: two-way transformer + upscaling + hypernetwork product, fp32) vs the oracle and vs the unfused fp32-grade path
+    (split-bf16 GEMMs + exact attention, ~120 launches) on identical inputs."""
+    ocfg, sd, eng, fpn = ctx["ocfg"], ctx["sd"], ctx["eng"], ctx["fpn"]
+    assert eng.fused_decoder
+    torch.manual_seed(10 + B)
+    text = torch.randn(B, 1, 256)
+    pix = (fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)).expand(B, -1, -1, -1) + 0.1 * torch.randn(B, 256, ocfg.feat_size, ocfg.feat_size)
+    sparse, dense = O.prompt_encode(sd, ocfg, B, text if with_text else None)
+    om = O.mask_decoder(sd, ocfg, pix, O.dense_pe(sd, ocfg), sparse, dense, [fpn[0].expand(B, -1, -1, -1), fpn[1].expand(B, -1, -1, -1)], True)
+    pix_tok = pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous()
+    s0, s1 = tok(fpn[0]).cuda().contiguous(), tok(fpn[1]).cuda().contiguous()
+    from videoglamm_b200 import ops
+    n0 = ops.launch_count()
+    fm = eng.mask_decoder(pix_tok, s0, s1, sparse.cuda())
+    assert ops.launch_count() - n0 == 1                               # one launch
+    side = 4 * ocfg.feat_size
+    errs = [rel(fm[0].view(B, 4, side, side), om[4]), rel(fm[1], om[5]), rel(fm[3], om[3]), rel(fm[2][:, 1:], om[2])]
+    print(f"PARITY fused mask decoder B={B} text={with_text}: masks {errs[0]:.2e}, iou {errs[1]:.2e}, obj {errs[2]:.2e}")
+    assert max(errs) < 1e-4, errs
+    eng.fused_decoder = False
+    try:
+        um = eng.mask_decoder(pix_tok, s0, s1, sparse.cuda())
+    finally:
+        eng.fused_decoder = True
+    assert rel(fm[0], um[0]) < 1e-4 and rel(fm[2], um[2]) < 1e-4 and rel(fm[1], um[1]) < 1e-4 and rel(fm[3], um[3]) < 1e-4
+
+
 def test_mask_decoder_bf16_mode_reported(ctx):
     """precise="none": the round-1 arithmetic (bf16 operands everywhere) stays available; its error is what the split-bf16 heads remove."""
     ocfg, sd, fpn = ctx["ocfg"], ctx["sd"], ctx["fpn"]

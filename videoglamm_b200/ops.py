@@ -453,3 +453,30 @@ def conv3x3s2_ln_gelu_gemm(x: torch.Tensor, w_gemm: torch.Tensor, bias, ln_w, ln
     L.check(L.lib().vg_layernorm_gelu(_ptr(g), C.c_longlong(g.stride(0)), _ptr(y), _dt(y.dtype), C.c_longlong(y.stride(0)), _ptr(ln_w), _ptr(ln_b), rows, cout,
                                       C.c_float(eps), _stream()), "vg_layernorm_gelu")
     return y
+
+
+def mask_decoder_fused(weights: "L.VgMaskDecoderWeights", pix: torch.Tensor, dense_pe: torch.Tensor, no_mask: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor,
+                       tokens: torch.Tensor, fs: int, pix_shared: bool = False):
+    """vg_mask_decoder: the whole SAM2 mask decoder for the B objects of one frame in ONE launch (include/vglamm.h). pix fp32 [B*HW, 256] (or [HW, 256]
+    shared), s0 fp32 [16*HW, 32], s1 fp32 [4*HW, 64], tokens fp32 [B, Nt, 256] -> (masks [B,4,(4fs)^2], iou [B,4], mask tokens [B,4,256], obj [B,1])."""
+    _require_cuda(pix, dense_pe, no_mask, s0, s1, tokens)
+    for t in (pix, dense_pe, no_mask, s0, s1, tokens):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+    B, Nt, Cc = tokens.shape
+    HW = fs * fs
+    assert Cc == 256 and s0.shape == (16 * HW, 32) and s1.shape == (4 * HW, 64) and pix.shape == ((HW if pix_shared else B * HW), 256)
+    dev = pix.device
+    masks = torch.empty((B, 4, 16 * HW), device=dev, dtype=torch.float32)
+    iou = torch.empty((B, 4), device=dev, dtype=torch.float32)
+    mt = torch.empty((B, 4, 256), device=dev, dtype=torch.float32)
+    obj = torch.empty((B, 1), device=dev, dtype=torch.float32)
+    nbytes = int(L.lib().vg_mask_decoder_workspace_bytes(B, fs))
+    ws = torch.empty((nbytes,), device=dev, dtype=torch.uint8)
+    d = L.VgMaskDecoder()
+    d.pix, d.pix_shared, d.dense_pe, d.no_mask, d.s0, d.s1, d.tokens = pix.data_ptr(), int(pix_shared), dense_pe.data_ptr(), no_mask.data_ptr(), s0.data_ptr(), s1.data_ptr(), tokens.data_ptr()
+    d.B, d.Nt, d.fs, d.C, d.heads, d.mlp, d.depth = B, Nt, fs, 256, 8, 2048, 2
+    d.weights = C.pointer(weights)
+    d.masks, d.iou, d.mask_tokens, d.obj = masks.data_ptr(), iou.data_ptr(), mt.data_ptr(), obj.data_ptr()
+    d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    L.check(L.lib().vg_mask_decoder(C.byref(d), _stream()), "vg_mask_decoder")
+    return masks, iou, mt, obj

@@ -57,6 +57,7 @@ class Sam2Engine:
         assert precise in ("none", "heads", "all"), precise
         self.precise = precise
         self.p_heads, self.p_all = precise != "none", precise == "all"
+        self.fused_decoder = self.p_heads and (self.cfg.d_model, self.cfg.dec_heads, self.cfg.dec_mlp, self.cfg.dec_depth) == (256, 8, 2048, 2)
         self.frames_per_encode = 8
         self.g_video = GraphedStage("sam2_video")
         self._sd = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
@@ -163,6 +164,8 @@ class Sam2Engine:
         self.iou_head = [self._lin(f"{md}.iou_prediction_head.layers.{j}", PH) for j in range(3)]
         self.obj_head = [self._lin(f"{md}.pred_obj_score_head.layers.{j}", PH) for j in range(3)]
         self.obj_ptr_proj = [self._lin(f"obj_ptr_proj.layers.{j}", PH) for j in range(3)]
+        if self.fused_decoder:
+            self._pack_fused_decoder()
         # memory encoder (memory_encoder.py)
         me = "memory_encoder"
         self.ds = []
@@ -189,6 +192,54 @@ class Sam2Engine:
             self.ma_layers.append(dict(qkv=qkv, sa_out=sa["out"], ca=ca, n1=self._ln(l + ".norm1"), n2=self._ln(l + ".norm2"), n3=self._ln(l + ".norm3"),
                                        fc1=self._lin(l + ".linear1"), fc2=self._lin(l + ".linear2")))
         self.ma_norm = self._ln("memory_attention.norm")
+
+    def _pack_fused_decoder(self):
+        """Table of fp32 device pointers for vg_mask_decoder (include/vglamm.h VgMaskDecoderWeights): nn.Linear layout for the token-side GEMVs,
+        transposed copies for the row-local image-side contractions, and the load-time constants dense_pe @ Wk^T / dense_pe @ Wq^T."""
+        from . import _lib as L
+        md = "sam_mask_decoder"
+        keep = self._fused_keep = []
+
+        def lin(key, transpose=False, w=None):
+            w = self._t(key + ".weight") if w is None else w
+            w = w.reshape(w.shape[0], -1)
+            w = (w.t() if transpose else w).contiguous()
+            b = self._t(key + ".bias").contiguous()
+            keep.extend([w, b])
+            return L.VgLinear(w.data_ptr(), b.data_ptr())
+
+        def attn(p, tq=False, tk=False, tv=False, tout=False):
+            return L.VgMdAttn(lin(p + ".q_proj", tq), lin(p + ".k_proj", tk), lin(p + ".v_proj", tv), lin(p + ".out_proj", tout))
+
+        def const(x):
+            x = x.contiguous()
+            keep.append(x)
+            return x.data_ptr()
+
+        W = L.VgMaskDecoderWeights()
+        for i in range(2):
+            l = f"{md}.transformer.layers.{i}"
+            W.layer[i] = L.VgMdLayer(attn(l + ".self_attn"), attn(l + ".cross_attn_token_to_image", tk=True, tv=True),
+                                     attn(l + ".cross_attn_image_to_token", tq=True, tout=True), lin(l + ".norm1"), lin(l + ".norm2"), lin(l + ".norm3"),
+                                     lin(l + ".norm4"), lin(l + ".mlp.layers.0"), lin(l + ".mlp.layers.1"))
+            W.pek[i] = const(self.dense_pe @ self._t(l + ".cross_attn_token_to_image.k_proj.weight").t())
+            W.peq[i] = const(self.dense_pe @ self._t(l + ".cross_attn_image_to_token.q_proj.weight").t())
+        f = md + ".transformer.final_attn_token_to_image"
+        W.final_t2i = attn(f, tk=True, tv=True)
+        W.pek[2] = const(self.dense_pe @ self._t(f + ".k_proj.weight").t())
+        W.norm_final = lin(md + ".transformer.norm_final_attn")
+        for name, key in (("up1", ".output_upscaling.0"), ("up2", ".output_upscaling.3")):
+            wt = self._t(md + key + ".weight")                                   # ConvTranspose2d [Cin, Cout, 2, 2] -> T[Cin][(dy,dx,co)]
+            setattr(W, name, lin(md + key, w=wt.permute(0, 2, 3, 1).reshape(wt.shape[0], -1)))
+        W.up_ln = lin(md + ".output_upscaling.1")
+        for i in range(4):
+            for j in range(3):
+                W.hyper[i][j] = lin(f"{md}.output_hypernetworks_mlps.{i}.layers.{j}")
+        for j in range(3):
+            W.iou[j] = lin(f"{md}.iou_prediction_head.layers.{j}")
+            W.obj[j] = lin(f"{md}.pred_obj_score_head.layers.{j}")
+        self.fused_w = W
+        self.no_mask_vec = self.no_mask_embed.reshape(-1).contiguous()
 
     def _sine_pos(self, H, W, num_pos_feats):
         """PositionEmbeddingSine (position_encoding.py:79-112): a constant table per feature size -> [H*W, C] fp32."""
@@ -296,6 +347,9 @@ class Sam2Engine:
         adt = F32 if P else BF
         act = (lambda t: t) if P else (lambda t: ops.cast(t, BF))     # GEMM-operand view of an fp32 activation
         B = sparse.shape[0]
+        if self.fused_decoder and debug is None and s0.dtype == F32 and pix.shape[0] == B * HW:
+            tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).contiguous()
+            return ops.mask_decoder_fused(self.fused_w, pix, self.dense_pe, self.no_mask_vec, s0, s1, tokens, cfg.feat_size)
         tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(-1, C).contiguous()
         Nt = tokens.shape[0] // B
         keys = ops.add(pix, self.no_mask_embed)                       # src = image_embeddings + dense (no_mask_embed)
