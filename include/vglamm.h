@@ -211,7 +211,8 @@ int vg_attention_f32(const VgAttention* a, void* stream);
  * ConvTranspose2d(64->32,k2,s2) + feat_s0 + GELU, the 4 hypernetwork MLPs, masks = hyper_in @ upscaled, IoU head (sigmoid) and object-score head —
  * MaskDecoder.predict_masks .../sam2/modeling/sam/mask_decoder.py:167-245, TwoWayTransformer .../sam/transformer.py:63-115, 160-193, 233-260 —
  * for all B objects of a frame (grid = (HW/32 row blocks, B); the blocks of one object synchronise through a counter in `workspace`).
- * fp32 arithmetic throughout. Weight pointers are fp32 device arrays; "T" marks arrays stored TRANSPOSED ([in][out]) because the image-side
+ * fp32-grade arithmetic throughout: the token chain, softmaxes, norms and GELUs in fp32; the row-local image-side contractions either in fp32 FMA
+ * (force_exact) or on the tensor cores as split-bf16 (hi/lo) products with fp32 accumulation (default; ~2^-17 relative). Weight pointers are fp32 device arrays; "T" marks arrays stored TRANSPOSED ([in][out]) because the image-side
  * contractions read them coalesced over the output column; the rest are nn.Linear layout ([out][in]). pek / peq are the load-time constant products
  * dense_pe @ Wk^T (token->image k projections of layer 0, layer 1, final) and dense_pe @ Wq^T (image->token q projections of layer 0, 1), [HW][128].
  */
@@ -236,6 +237,10 @@ typedef struct VgMaskDecoderWeights {
   VgLinear obj[3];             /* [256][256], [256][256], [1][256] */
   const float* pek[3];
   const float* peq[2];
+  /* tensor-core path of the row-local contractions: the same 12 image-side matrices in nn.Linear layout [out][in], split into bf16 hi = bf16(w) and
+   * lo = bf16(w - hi): index 4*layer + {0: t2i.k, 1: t2i.v, 2: i2t.q, 3: i2t.out}, 8: final k, 9: final v, 10: up1 [(dy,dx,co)][256], 11: up2 [(dy,dx,co)][64] */
+  const void* img_hi[12];
+  const void* img_lo[12];
 } VgMaskDecoderWeights;
 typedef struct VgMaskDecoder {
   const float* pix;            /* fp32 [B][HW][256] image embedding rows per object ([HW][256] shared by all objects when pix_shared != 0) */
@@ -253,9 +258,13 @@ typedef struct VgMaskDecoder {
   float* mask_tokens;          /* out fp32 [B][4][256] (hs[:, 2:6]) */
   float* obj;                  /* out fp32 [B] object-score logits */
   void* workspace; long long workspace_bytes;   /* >= vg_mask_decoder_workspace_bytes(B, fs) */
+  int force_exact;             /* 1: fp32-FMA row-local contractions (also selected by the environment variable VG_MD_EXACT=1); 0: bf16-split tensor-core path */
 } VgMaskDecoder;
 long long vg_mask_decoder_workspace_bytes(int B, int fs);
 int vg_mask_decoder(const VgMaskDecoder* d, void* stream);
+/* diagnostic: `dev_buf` = device buffer of 64 uint64 that following launches fill with the %globaltimer of block (0,0) at kernel start, after each
+ * grid barrier and at the end ([63] = number of barriers); NULL disables. */
+void vg_mask_decoder_set_timeline(void* dev_buf);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

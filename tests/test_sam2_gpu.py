@@ -102,8 +102,9 @@ def test_mask_decoder(ctx, with_text):
     assert torch.equal(eh["low_res_masks"].cpu() > 0, oh["low_res_masks"][:, 0] > 0)
 
 
+@pytest.mark.parametrize("exact", [False, True])
 @pytest.mark.parametrize("B,with_text", [(1, True), (2, False), (4, True)])
-def test_fused_mask_decoder_kernel(ctx, B, with_text):
+def test_fused_mask_decoder_kernel(ctx, B, with_text, exact):
     """vg_mask_decoder (ONE launch: two-way transformer + upscaling + hypernetwork product, fp32) vs the oracle and vs the unfused fp32-grade path
     (split-bf16 GEMMs + exact attention, ~120 launches) on identical inputs."""
     ocfg, sd, eng, fpn = ctx["ocfg"], ctx["sd"], ctx["eng"], ctx["fpn"]
@@ -117,11 +118,15 @@ def test_fused_mask_decoder_kernel(ctx, B, with_text):
     s0, s1 = tok(fpn[0]).cuda().contiguous(), tok(fpn[1]).cuda().contiguous()
     from videoglamm_b200 import ops
     n0 = ops.launch_count()
-    fm = eng.mask_decoder(pix_tok, s0, s1, sparse.cuda())
+    eng.fused_exact = exact                                           # False: split-bf16 tensor-core contractions (default); True: fp32 FMA
+    try:
+        fm = eng.mask_decoder(pix_tok, s0, s1, sparse.cuda())
+    finally:
+        eng.fused_exact = False
     assert ops.launch_count() - n0 == 1                               # one launch
     side = 4 * ocfg.feat_size
     errs = [rel(fm[0].view(B, 4, side, side), om[4]), rel(fm[1], om[5]), rel(fm[3], om[3]), rel(fm[2][:, 1:], om[2])]
-    print(f"PARITY fused mask decoder B={B} text={with_text}: masks {errs[0]:.2e}, iou {errs[1]:.2e}, obj {errs[2]:.2e}")
+    print(f"PARITY fused mask decoder B={B} text={with_text} exact={exact}: masks {errs[0]:.2e}, iou {errs[1]:.2e}, obj {errs[2]:.2e}")
     assert max(errs) < 1e-4, errs
     eng.fused_decoder = False
     try:

@@ -74,7 +74,7 @@ SYMBOLS = [
     "vg_add", "vg_pool2x2", "vg_upsample2x_add", "vg_convt2x2_epilogue", "vg_im2col", "vg_dwconv", "vg_conv3x3s2_ln_gelu", "vg_bilinear",
     "vg_rope2d", "vg_rope_neox", "vg_embedding", "vg_argmax", "vg_row_scatter", "vg_launch_count_add", "vg_rope_kv_append", "vg_multimask_select",
     "vg_connected_components", "vg_im2col3x3s2_cl", "vg_layernorm_gelu", "vg_split3", "vg_attention_f32",
-    "vg_mask_decoder", "vg_mask_decoder_workspace_bytes",
+    "vg_mask_decoder", "vg_mask_decoder_workspace_bytes", "vg_mask_decoder_set_timeline",
 ]
 
 
@@ -93,12 +93,13 @@ class VgMdLayer(C.Structure):
 
 class VgMaskDecoderWeights(C.Structure):
     _fields_ = [("layer", VgMdLayer * 2), ("final_t2i", VgMdAttn), ("norm_final", VgLinear), ("up1", VgLinear), ("up_ln", VgLinear), ("up2", VgLinear),
-                ("hyper", (VgLinear * 3) * 4), ("iou", VgLinear * 3), ("obj", VgLinear * 3), ("pek", C.c_void_p * 3), ("peq", C.c_void_p * 2)]
+                ("hyper", (VgLinear * 3) * 4), ("iou", VgLinear * 3), ("obj", VgLinear * 3), ("pek", C.c_void_p * 3), ("peq", C.c_void_p * 2),
+                ("img_hi", C.c_void_p * 12), ("img_lo", C.c_void_p * 12)]
 
 
 class VgMaskDecoder(C.Structure):
     _fields_ = [("pix", C.c_void_p), ("pix_shared", C.c_int), ("dense_pe", C.c_void_p), ("no_mask", C.c_void_p), ("s0", C.c_void_p), ("s1", C.c_void_p),
                 ("tokens", C.c_void_p), ("B", C.c_int), ("Nt", C.c_int), ("fs", C.c_int), ("C", C.c_int), ("heads", C.c_int), ("mlp", C.c_int),
                 ("depth", C.c_int), ("weights", C.POINTER(VgMaskDecoderWeights)), ("masks", C.c_void_p), ("iou", C.c_void_p), ("mask_tokens", C.c_void_p),
-                ("obj", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
+                ("obj", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("force_exact", C.c_int)]
 

@@ -14,6 +14,8 @@
 // Row-local contractions read TRANSPOSED weights [K][N] (coalesced over n); token-side GEMVs read nn.Linear-layout rows [N][K] (coalesced over k).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "pdl.cuh"
 #include "ptx.cuh"
@@ -22,6 +24,12 @@ namespace vg {
 
 constexpr int MD_C = 256, MD_CI = 128, MD_H = 8, MD_RB = 32, MD_NT = 12, MD_MLP = 2048, MD_LDK = 132, MD_THREADS = 256;
 constexpr int MD_TB = MD_NT * 768;  // token buffer (floats)
+constexpr int MD_LDX = 260;         // leading dimension of the resident image rows (4 mod 32 words: conflict-free row-parallel float4 reads)
+constexpr int MD_LDU = 68;          // ... of the up1 pixels [128][64]
+constexpr int MD_LDA = 264;         // bf16 leading dimension of the split (hi / lo) copies of the A operand rows [32][<= 256]
+constexpr int MD_WR = 20480;        // weight ring (floats): fp32 path 2 x [32][256] fp32; tensor path 2 stages x (hi, lo) x [256][40] bf16
+// image-side weight matrices of the tensor-core path (VgMaskDecoderWeights.img_hi / img_lo)
+enum { MD_W_T2I_K = 0, MD_W_T2I_V = 1, MD_W_I2T_Q = 2, MD_W_I2T_OUT = 3, MD_W_FIN_K = 8, MD_W_FIN_V = 9, MD_W_UP1 = 10, MD_W_UP2 = 11 };
 
 // per-object scratch layout (floats)
 struct MdOff {
@@ -51,6 +59,7 @@ struct MdParams {
   float *masks, *iou, *mask_tokens, *obj;
   float* ws; long long ws_obj_stride;
   unsigned* bar;
+  unsigned long long* timeline;   // diagnostic: globaltimer of block (0,0) at kernel start and after every grid barrier, then at the end
   VgMaskDecoderWeights w;
 };
 
@@ -77,10 +86,24 @@ __device__ __forceinline__ void md_barrier(unsigned* ctr, unsigned target) {
 
 // ---- token-side helpers -------------------------------------------------------------------------------------------------------------------
 // rows [0, NT) of a global [NT][ld] matrix -> shared [NT][K] (L2 reads: the producer was another block)
+// (float4 granularity, 4 independent loads in flight per thread: the L2 round trip is ~1 us, an unpipelined element loop costs 10+ us per stage)
 __device__ __forceinline__ void md_load_rows(float* dst, const float* src, int ld, int K, int NT) {
-  for (int i = threadIdx.x; i < NT * K; i += MD_THREADS) {
-    const int t = i / K, k = i - t * K;
-    dst[i] = __ldcg(src + t * ld + k);
+  const int k4 = K >> 2, total = NT * k4;
+  for (int i0 = threadIdx.x; i0 < total; i0 += 4 * MD_THREADS) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * MD_THREADS;
+      if (i < total) {
+        const int t = i / k4, k = i - t * k4;
+        v[u] = __ldcg(reinterpret_cast<const float4*>(src + t * ld) + k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * MD_THREADS;
+      if (i < total) reinterpret_cast<float4*>(dst)[i] = v[u];
+    }
   }
 }
 
@@ -110,18 +133,27 @@ __device__ __forceinline__ void md_load_rows_ln(float* dst, const float* src, in
 // Distributed linear: this block computes output columns n = blk + G * j of y[t][n] = act(bias[n] + x[t][:] . W[n][:]) (+ resid[t][n]); x in
 // shared memory [NT][ldx], W global row-major [N][K] (nn.Linear layout), one warp per column, lanes stride over k. accumulate: y += (K chunks).
 __device__ __forceinline__ void md_tok_linear(const float* xs, int ldx, int K, const float* W, int ldw, const float* bias, int N, float* y, int ldy, int NT,
-                                              bool relu, const float* resid, int ldr, bool accumulate, int blk, int G) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                              bool relu, const float* resid, int ldr, bool accumulate, int blk, int G, int woff = 0) {
+  // woff rotates the warp -> column assignment so that back-to-back calls with few columns per block (q / k / v projections) occupy different warps
+  const int warp = ((threadIdx.x >> 5) + (MD_THREADS / 32) - woff) % (MD_THREADS / 32), lane = threadIdx.x & 31;
   for (int n = blk + G * warp; n < N; n += G * (MD_THREADS / 32)) {
     float acc[MD_NT];
 #pragma unroll
     for (int t = 0; t < MD_NT; ++t) acc[t] = 0.f;
     const float* wr = W + static_cast<long long>(n) * ldw;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __ldg(wr + k);
+    for (int k0 = lane; k0 < K; k0 += 256) {   // 8 weight loads in flight per lane (the weights come from L2 / HBM)
+      float wv[8];
 #pragma unroll
-      for (int t = 0; t < MD_NT; ++t)
-        if (t < NT) acc[t] = fmaf(xs[t * ldx + k], wv, acc[t]);
+      for (int u = 0; u < 8; ++u) wv[u] = (k0 + 32 * u < K) ? __ldg(wr + k0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < K) {
+#pragma unroll
+          for (int t = 0; t < MD_NT; ++t)
+            if (t < NT) acc[t] = fmaf(xs[t * ldx + k], wv[u], acc[t]);
+        }
+      }
     }
 #pragma unroll
     for (int t = 0; t < MD_NT; ++t)
@@ -143,36 +175,108 @@ __device__ __forceinline__ void md_tok_linear(const float* xs, int ldx, int K, c
   }
 }
 
+// Large-K variant (MLP fc2, K = 2048): all 8 warps work on each of the block's columns, every warp a contiguous eighth of K; partial sums meet in
+// shared memory. y[t][n] = bias[n] + x[t][:] . W[n][:] + resid[t][n]
+__device__ __forceinline__ void md_tok_linear_coop(const float* xs, int ldx, int K, const float* W, int ldw, const float* bias, int N, float* y, int ldy, int NT,
+                                                   const float* resid, int ldr, int blk, int G, float* red /* [8][MD_NT] shared */) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kw = K / (MD_THREADS / 32);
+  for (int n = blk; n < N; n += G) {
+    float acc[MD_NT];
+#pragma unroll
+    for (int t = 0; t < MD_NT; ++t) acc[t] = 0.f;
+    const float* wr = W + static_cast<long long>(n) * ldw + warp * kw;
+    const float* xw = xs + warp * kw;
+    for (int k0 = lane; k0 < kw; k0 += 256) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = (k0 + 32 * u < kw) ? __ldg(wr + k0 + 32 * u) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 32 * u;
+        if (k < kw) {
+#pragma unroll
+          for (int t = 0; t < MD_NT; ++t)
+            if (t < NT) acc[t] = fmaf(xw[t * ldx + k], wv[u], acc[t]);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < MD_NT; ++t)
+      if (t < NT) acc[t] = warp_sum(acc[t]);
+    if (lane < NT) {
+      float v = 0.f;
+#pragma unroll
+      for (int t = 0; t < MD_NT; ++t)
+        if (t == lane) v = acc[t];
+      red[warp * MD_NT + lane] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NT) {
+      float v = bias[n];
+#pragma unroll
+      for (int w = 0; w < MD_THREADS / 32; ++w) v += red[w * MD_NT + threadIdx.x];
+      y[threadIdx.x * ldy + n] = v + __ldcg(resid + threadIdx.x * ldr + n);
+    }
+    __syncthreads();
+  }
+}
+
 // ---- image-side helpers -------------------------------------------------------------------------------------------------------------------
 // out[r][n] = bias[n] + sum_k A[r][k] Wt[k][n] (+ add[r * ld_add + n]) for the block's 32 rows; A shared [32][lda], Wt global TRANSPOSED [K][N],
-// out shared [32][ldo]. Thread tile: RPT rows x 4 columns, k unrolled by 4 (float4 loads of A along k and of Wt along n).
+// out shared [32][ldo]. Wt streams through a two-stage cp.async ring in shared memory (MD_KT weight rows = one contiguous chunk per stage) so
+// the L2 latency of the weights is hidden under the FMAs of the previous chunk. Thread tile: RPT rows x 4 columns, k unrolled by 4.
+constexpr int MD_KT = 32;
 template <int N>
 __device__ __forceinline__ void md_img_gemm(const float* A, int lda, int K, const float* __restrict__ Wt, const float* __restrict__ bias, const float* add,
-                                            long long ld_add, float* out, int ldo) {
-  constexpr int CG = N / 4, RG = MD_THREADS / CG, RPT = MD_RB / RG;
-  const int cg = threadIdx.x % CG, rg = threadIdx.x / CG;
+                                            long long ld_add, float* out, int ldo, float* wring) {
+  // warp w owns the N/8 output columns [w*N/8, (w+1)*N/8) for all 32 rows: lanes = (CGW column groups of 4) x (32/CGW row groups of RPT rows).
+  // Every weight element is then read from shared memory by exactly one warp (as a broadcast to the lanes sharing a column group), and the A rows
+  // (leading dimension = 4 mod 32 words) are conflict-free: the contraction is FMA-bound instead of shared-memory-bound.
+  constexpr int CGW = N / 32, RGW = 32 / CGW, RPT = MD_RB / RGW;
+  constexpr int STAGE = MD_KT * N;            // floats per stage
+  const int cg = (threadIdx.x >> 5) * CGW + (threadIdx.x & 31) % CGW, rg = (threadIdx.x & 31) / CGW;
   float acc[RPT][4];
 #pragma unroll
   for (int i = 0; i < RPT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const float* wp = Wt + 4 * cg;
-  for (int k = 0; k < K; k += 4) {
-    float4 w[4];
+  auto issue = [&](int kt) {
+    const float* src = Wt + static_cast<long long>(kt) * STAGE;
+    float* dst = wring + (kt & 1) * STAGE;
+    for (int i = threadIdx.x * 4; i < STAGE; i += MD_THREADS * 4) cp_async16(dst + i, src + i, true);
+    cp_async_commit();
+  };
+  const int nkt = K / MD_KT;
+  issue(0);
+  for (int kt = 0; kt < nkt; ++kt) {
+    if (kt + 1 < nkt) {
+      issue(kt + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* ws = wring + (kt & 1) * STAGE + 4 * cg;
+#pragma unroll 2
+    for (int k = 0; k < MD_KT; k += 4) {
+      float4 w[4];
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) w[kk] = __ldg(reinterpret_cast<const float4*>(wp + static_cast<long long>(k + kk) * N));
+      for (int kk = 0; kk < 4; ++kk) w[kk] = *reinterpret_cast<const float4*>(ws + (k + kk) * N);
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-      const float4 a = *reinterpret_cast<const float4*>(A + (rg * RPT + i) * lda + k);
-      const float av[4] = {a.x, a.y, a.z, a.w};
+      for (int i = 0; i < RPT; ++i) {
+        const float4 a = *reinterpret_cast<const float4*>(A + (rg * RPT + i) * lda + kt * MD_KT + k);
+        const float av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        acc[i][0] = fmaf(av[kk], w[kk].x, acc[i][0]);
-        acc[i][1] = fmaf(av[kk], w[kk].y, acc[i][1]);
-        acc[i][2] = fmaf(av[kk], w[kk].z, acc[i][2]);
-        acc[i][3] = fmaf(av[kk], w[kk].w, acc[i][3]);
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i][0] = fmaf(av[kk], w[kk].x, acc[i][0]);
+          acc[i][1] = fmaf(av[kk], w[kk].y, acc[i][1]);
+          acc[i][2] = fmaf(av[kk], w[kk].z, acc[i][2]);
+          acc[i][3] = fmaf(av[kk], w[kk].w, acc[i][3]);
+        }
       }
     }
+    __syncthreads();   // this stage is overwritten by the chunk issued in the next iteration
   }
   float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) bv = __ldg(reinterpret_cast<const float4*>(bias + 4 * cg));
@@ -185,6 +289,111 @@ __device__ __forceinline__ void md_img_gemm(const float* A, int lda, int K, cons
       o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
     }
     *reinterpret_cast<float4*>(out + r * ldo + 4 * cg) = o;
+  }
+}
+
+// Tensor-core variant of the row-local contraction: fp32-grade through the bf16 split  A W^T ~= A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T  (fp32
+// accumulation in the mma.sync accumulators; the dropped lo*lo term is 2^-17 relative). AH / AL: split copies of the 32 A rows in shared memory
+// [32][lda] bf16; WH / WL: pre-split weights in nn.Linear layout [N][K] bf16 (global), streamed in 32-wide k tiles through a two-stage cp.async
+// ring. Warp w owns output columns [w*N/8, (w+1)*N/8) for all 32 rows (2 m16 tiles).
+template <int N>
+__device__ __forceinline__ void md_img_gemm_mma(const __nv_bfloat16* AH, const __nv_bfloat16* AL, int lda, int K, const __nv_bfloat16* __restrict__ WH,
+                                                const __nv_bfloat16* __restrict__ WL, const float* __restrict__ bias, const float* add, long long ld_add,
+                                                float* out, int ldo, __nv_bfloat16* ring) {
+  constexpr int LDW = MD_KT + 8, TILE = N * LDW, NP = N / 128;  // NP: pairs of n8 tiles per warp (N/8 columns = N/64 n8 tiles)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+  const int a_row = (lane & 7) + ((lane >> 3) & 1) * 8, a_col = (lane >> 4) * 8;
+  const int b_row = (lane & 7) + (lane >> 4) * 8, b_col = ((lane >> 3) & 1) * 8;
+  float acc[2][2 * NP][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  // ring depth: as many (hi, lo) tile pairs as the MD_WR-float ring holds (4 for N = 128, 2 for N = 256): the weights come from L2 (~1 us round
+  // trip) and one tile is only ~0.2 us of tensor work, so the prefetch distance, not the arithmetic, sets the speed
+  constexpr int ST = (MD_WR * 4) / (2 * TILE * 2) >= 4 ? 4 : 2;
+  auto issue = [&](int kt) {
+    __nv_bfloat16* dst = ring + (kt % ST) * 2 * TILE;
+    for (int i = threadIdx.x; i < N * 4; i += MD_THREADS) {
+      const int row = i >> 2, ch = i & 3;
+      const long long src = static_cast<long long>(row) * K + kt * MD_KT + ch * 8;
+      cp_async16(dst + row * LDW + ch * 8, WH + src, true);
+      cp_async16(dst + TILE + row * LDW + ch * 8, WL + src, true);
+    }
+  };
+  const int nkt = K / MD_KT;
+#pragma unroll
+  for (int i = 0; i < ST - 1; ++i) {       // prologue: ST - 1 tiles in flight (empty groups keep the wait_group arithmetic uniform)
+    if (i < nkt) issue(i);
+    cp_async_commit();
+  }
+  for (int kt = 0; kt < nkt; ++kt) {
+    if (kt + ST - 1 < nkt) issue(kt + ST - 1);   // overwrites the stage consumed in iteration kt - 1 (all warps passed its trailing barrier)
+    cp_async_commit();
+    cp_async_wait<ST - 1>();
+    __syncthreads();
+    const __nv_bfloat16* th = ring + (kt % ST) * 2 * TILE;
+    const __nv_bfloat16* tl = th + TILE;
+#pragma unroll
+    for (int k16 = 0; k16 < MD_KT / 16; ++k16) {
+      uint32_t ah[2][4], al[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        ldmatrix_x4(ah[mt], AH + (mt * 16 + a_row) * lda + kt * MD_KT + k16 * 16 + a_col);
+        ldmatrix_x4(al[mt], AL + (mt * 16 + a_row) * lda + kt * MD_KT + k16 * 16 + a_col);
+      }
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const int n0 = warp * (N / 8) + j * 16;
+        uint32_t bh[4], bl[4];
+        ldmatrix_x4(bh, th + (n0 + b_row) * LDW + k16 * 16 + b_col);
+        ldmatrix_x4(bl, tl + (n0 + b_row) * LDW + k16 * 16 + b_col);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma_bf16_16816(acc[mt][2 * j], ah[mt], bh[0], bh[1]);
+          mma_bf16_16816(acc[mt][2 * j + 1], ah[mt], bh[2], bh[3]);
+          mma_bf16_16816(acc[mt][2 * j], al[mt], bh[0], bh[1]);
+          mma_bf16_16816(acc[mt][2 * j + 1], al[mt], bh[2], bh[3]);
+          mma_bf16_16816(acc[mt][2 * j], ah[mt], bl[0], bl[1]);
+          mma_bf16_16816(acc[mt][2 * j + 1], ah[mt], bl[2], bl[3]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2 * NP; ++nt) {
+      const int col = warp * (N / 8) + nt * 8 + 2 * t4;
+      const float b0 = bias ? __ldg(bias + col) : 0.f, b1 = bias ? __ldg(bias + col + 1) : 0.f;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = mt * 16 + g + hh * 8;
+        float2 o = make_float2(acc[mt][nt][2 * hh] + b0, acc[mt][nt][2 * hh + 1] + b1);
+        if (add) {
+          const float2 ad = __ldg(reinterpret_cast<const float2*>(add + r * ld_add + col));
+          o.x += ad.x;
+          o.y += ad.y;
+        }
+        *reinterpret_cast<float2*>(out + r * ldo + col) = o;
+      }
+    }
+}
+
+// split copies of 32 fp32 rows [32][K] (shared, leading dimension lds) -> AH = bf16(x), AL = bf16(x - AH), leading dimension lda
+__device__ __forceinline__ void md_split_rows(const float* src, int lds, int K, __nv_bfloat16* AH, __nv_bfloat16* AL, int lda) {
+  const int k2 = K >> 1;
+  for (int i = threadIdx.x; i < MD_RB * k2; i += MD_THREADS) {
+    const int r = i / k2, c = (i - r * k2) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(src + r * lds + c);
+    const __nv_bfloat16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y);
+    __nv_bfloat162 hi, lo;
+    hi.x = h0; hi.y = h1;
+    lo.x = __float2bfloat16(v.x - __bfloat162float(h0));
+    lo.y = __float2bfloat16(v.y - __bfloat162float(h1));
+    *reinterpret_cast<__nv_bfloat162*>(AH + r * lda + c) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(AL + r * lda + c) = lo;
   }
 }
 
@@ -266,7 +475,7 @@ __device__ __forceinline__ void md_rows_add_ln(float* X, const float* D, int ldd
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
-      v[i] = X[r * MD_C + c] + D[r * ldd + c];
+      v[i] = X[r * MD_LDX + c] + D[r * ldd + c];
       s += v[i];
     }
     const float mean = warp_sum(s) * (1.0f / MD_C);
@@ -277,22 +486,39 @@ __device__ __forceinline__ void md_rows_add_ln(float* X, const float* D, int ldd
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
-      X[r * MD_C + c] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
+      X[r * MD_LDX + c] = (v[i] - mean) * rstd * __ldg(w + c) + __ldg(b + c);
     }
   }
 }
 
+// EXACT = true: every row-local contraction in fp32 FMA (verification / fallback); false: on the tensor cores through the bf16 split.
+template <bool EXACT>
 __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdParams p) {
   pdl_wait();
   pdl_launch_dependents();
   extern __shared__ __align__(16) float md_smem[];
-  float* Xs = md_smem;                       // [32][256]  image rows ("keys" stream)
-  float* Ks = Xs + MD_RB * MD_C;             // [32][132]  K projection / image-side q / up1 pixels (aliased per stage)
+  float* Xs = md_smem;                       // [32][260]  image rows ("keys" stream)
+  float* Ks = Xs + MD_RB * MD_LDX;           // [32][132]  K projection / image-side q (aliased per stage)
   float* Vs = Ks + MD_RB * MD_LDK;           // [32][132]  V projection / image-side attention output
   float* TB = Vs + MD_RB * MD_LDK;           // token buffer [12][768] / out-projection tile [32][256] / conv tiles
+  float* WR = TB + MD_TB;                    // weight ring of the row-local contractions (MD_WR floats)
+  __nv_bfloat16* AH = reinterpret_cast<__nv_bfloat16*>(WR + MD_WR);   // split (hi, lo) bf16 copies of the current A operand rows [32][MD_LDA]
+  __nv_bfloat16* AL = AH + MD_RB * MD_LDA;
+  __nv_bfloat16* WRB = reinterpret_cast<__nv_bfloat16*>(WR);
+  // row-local contraction out = A W^T (+ bias, + add): fp32 FMA from the transposed fp32 weights, or tensor cores from the pre-split bf16 weights.
+  // `A` must be reflected in AH / AL (md_split_rows) before a tensor-core call.
+#define MD_GEMM(NN, A, LDA_F32, KK, LIN, WIDX, BIAS, ADD, LDADD, OUT, LDO)                                                                     \
+  do {                                                                                                                                       \
+    if (EXACT)                                                                                                                               \
+      md_img_gemm<NN>(A, LDA_F32, KK, (LIN).w, BIAS, ADD, LDADD, OUT, LDO, WR);                                                               \
+    else                                                                                                                                     \
+      md_img_gemm_mma<NN>(AH, AL, MD_LDA, KK, static_cast<const __nv_bfloat16*>(W.img_hi[WIDX]), static_cast<const __nv_bfloat16*>(W.img_lo[WIDX]), \
+                          BIAS, ADD, LDADD, OUT, LDO, WRB);                                                                                   \
+  } while (0)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int blk = blockIdx.x, b = blockIdx.y, G = p.G, NT = p.Nt, fs = p.fs;
   const MdOff off(G);
+  __shared__ float red[(MD_THREADS / 32) * MD_NT];
   float* ws = p.ws + b * p.ws_obj_stride;
   unsigned* bar = p.bar + b;
   unsigned nbar = 0;
@@ -301,13 +527,42 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
   const int row0 = blk * MD_RB;                                              // first image row of this block
   const float* pe_rows = p.pe;                                               // unused directly: the pe projections are folded (W.pek / W.peq)
   (void)pe_rows;
-#define MD_BAR() md_barrier(bar, (++nbar) * static_cast<unsigned>(G))
+#define MD_BAR()                                                  \
+  do {                                                            \
+    md_barrier(bar, (++nbar) * static_cast<unsigned>(G));         \
+    if (p.timeline && blk == 0 && b == 0 && tid == 0) {           \
+      unsigned long long t_;                                      \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));      \
+      p.timeline[nbar] = t_;                                      \
+    }                                                             \
+  } while (0)
+  if (p.timeline && blk == 0 && b == 0 && tid == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.timeline[0] = t_;
+  }
+  int nstamp = 0;
+  (void)nstamp;
+#define MD_STAMP()                                                \
+  do {                                                            \
+    if (p.timeline) {                                             \
+      __syncthreads();                                            \
+      if (blk == 0 && b == 0 && tid == 0 && nstamp < 30) {        \
+        unsigned long long t_;                                    \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));    \
+        p.timeline[32 + nstamp] = t_;                             \
+      }                                                           \
+      ++nstamp;                                                   \
+    }                                                             \
+  } while (0)
 
   // keys = image embedding + dense prompt embedding (no_mask_embed); mask_decoder.py:199-205
   {
     const float* px = p.pix + b * p.pix_obj_stride + static_cast<long long>(row0) * MD_C;
-    for (int i = tid; i < MD_RB * MD_C; i += MD_THREADS) Xs[i] = px[i] + __ldg(p.no_mask + (i & (MD_C - 1)));
+    for (int i = tid; i < MD_RB * MD_C; i += MD_THREADS) Xs[(i >> 8) * MD_LDX + (i & (MD_C - 1))] = px[i] + __ldg(p.no_mask + (i & (MD_C - 1)));
   }
+  __syncthreads();
+  if (!EXACT) md_split_rows(Xs, MD_LDX, MD_C, AH, AL, MD_LDA);
   __syncthreads();
 
   for (int layer = 0; layer < 2; ++layer) {
@@ -324,58 +579,70 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
     for (int i = tid; i < NT * MD_C; i += MD_THREADS) Tb[i] = layer == 0 ? Ta[i] : Ta[i] + tok_pe[i];
     __syncthreads();
     md_tok_linear(Tb, MD_C, MD_C, L.sa.q.w, MD_C, L.sa.q.b, MD_C, ws + off.QKV, 3 * MD_C, NT, false, nullptr, 0, false, blk, G);
-    md_tok_linear(Tb, MD_C, MD_C, L.sa.k.w, MD_C, L.sa.k.b, MD_C, ws + off.QKV + MD_C, 3 * MD_C, NT, false, nullptr, 0, false, blk, G);
-    md_tok_linear(Ta, MD_C, MD_C, L.sa.v.w, MD_C, L.sa.v.b, MD_C, ws + off.QKV + 2 * MD_C, 3 * MD_C, NT, false, nullptr, 0, false, blk, G);
+    md_tok_linear(Tb, MD_C, MD_C, L.sa.k.w, MD_C, L.sa.k.b, MD_C, ws + off.QKV + MD_C, 3 * MD_C, NT, false, nullptr, 0, false, blk, G, 2);
+    md_tok_linear(Ta, MD_C, MD_C, L.sa.v.w, MD_C, L.sa.v.b, MD_C, ws + off.QKV + 2 * MD_C, 3 * MD_C, NT, false, nullptr, 0, false, blk, G, 4);
     MD_BAR();
     // ---- T2: self-attention core (8 heads x 32, every block redundantly) + distributed out projection (+ residual except in layer 0)
+    MD_STAMP();
     md_load_rows(TB, ws + off.QKV, 3 * MD_C, 3 * MD_C, NT);
     __syncthreads();
+    MD_STAMP();
     float* Asa = Ks;                   // [NT][256] attention output (Ks is free until the K projection below)
-    for (int job = tid; job < NT * MD_H; job += MD_THREADS) {
-      const int t = job / MD_H, h = job - t * MD_H;
-      const float* q = TB + t * 3 * MD_C + h * 32;
-      float s[MD_NT], m = -INFINITY;
+    // scores: one thread per (query token, head, key token) -> S[(t*8+h)*12 + j]; softmax + weighted V: one thread per (t, h, feature)
+    float* Ssa = Vs;
+    for (int e = tid; e < NT * MD_H * NT; e += MD_THREADS) {
+      const int j = e % NT, th = e / NT, t = th / MD_H, h = th - t * MD_H;
+      const float4* q = reinterpret_cast<const float4*>(TB + t * 3 * MD_C + h * 32);
+      const float4* k = reinterpret_cast<const float4*>(TB + j * 3 * MD_C + MD_C + h * 32);
+      float a = 0.f;
 #pragma unroll
-      for (int j = 0; j < MD_NT; ++j) {
-        s[j] = -INFINITY;
-        if (j < NT) {
-          const float* k = TB + j * 3 * MD_C + MD_C + h * 32;
-          float a = 0.f;
-          for (int d = 0; d < 32; ++d) a = fmaf(q[d], k[d], a);
-          s[j] = a * 0.17677669529663687f;  // 32^-0.5
-          m = fmaxf(m, s[j]);
-        }
+      for (int d = 0; d < 8; ++d) {
+        const float4 qv = q[d], kv = k[d];
+        a = fmaf(qv.x, kv.x, a); a = fmaf(qv.y, kv.y, a); a = fmaf(qv.z, kv.z, a); a = fmaf(qv.w, kv.w, a);
       }
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < MD_NT; ++j) {
-        s[j] = j < NT ? expf(s[j] - m) : 0.f;
-        l += s[j];
-      }
-      const float inv = 1.0f / l;
-      for (int d = 0; d < 32; ++d) {
-        float o = 0.f;
-#pragma unroll
-        for (int j = 0; j < MD_NT; ++j)
-          if (j < NT) o = fmaf(s[j], TB[j * 3 * MD_C + 2 * MD_C + h * 32 + d], o);
-        Asa[t * MD_C + h * 32 + d] = o * inv;
-      }
+      Ssa[th * MD_NT + j] = a * 0.17677669529663687f;  // 32^-0.5
     }
     __syncthreads();
+    for (int th = tid; th < NT * MD_H; th += MD_THREADS) {             // softmax over the NT keys, once per (token, head)
+      float* sr = Ssa + th * MD_NT;
+      float m = -INFINITY, l = 0.f;
+      for (int j = 0; j < NT; ++j) m = fmaxf(m, sr[j]);
+      for (int j = 0; j < NT; ++j) {
+        sr[j] = expf(sr[j] - m);
+        l += sr[j];
+      }
+      const float inv = 1.0f / l;
+      for (int j = 0; j < NT; ++j) sr[j] *= inv;
+    }
+    __syncthreads();
+    for (int e = tid; e < NT * MD_C; e += MD_THREADS) {
+      const int t = e >> 8, c = e & 255, h = c >> 5;
+      const float* sr = Ssa + (t * MD_H + h) * MD_NT;
+      float o = 0.f;
+      for (int j = 0; j < NT; ++j) o = fmaf(sr[j], TB[j * 3 * MD_C + 2 * MD_C + c], o);
+      Asa[e] = o;
+    }
+    __syncthreads();
+    MD_STAMP();
     md_tok_linear(Asa, MD_C, MD_C, L.sa.out.w, MD_C, L.sa.out.b, MD_C, ws + off.QPRE, MD_C, NT, false, layer == 0 ? nullptr : ws + off.Q, MD_C, false, blk, G);
     MD_BAR();
     // ---- T3: norm1 (redundant per block) -> queries; token->image q projection of (queries + query_pe)
+    MD_STAMP();
     md_load_rows_ln(Ta, ws + off.QPRE, NT, L.n1.w, L.n1.b, 1e-5f);
     __syncthreads();
+    MD_STAMP();
     for (int i = tid; i < NT * MD_C; i += MD_THREADS) {
       if (blk == 0) ws[off.Q + i] = Ta[i];
       Tb[i] = Ta[i] + tok_pe[i];
     }
     __syncthreads();
     md_tok_linear(Tb, MD_C, MD_C, L.t2i.q.w, MD_C, L.t2i.q.b, MD_CI, ws + off.TQ, MD_CI, NT, false, nullptr, 0, false, blk, G);
+    MD_STAMP();
     // image side, row-local: K = (keys + pe) Wk + b (pe Wk folded: W.pek), V = keys Wv + b
-    md_img_gemm<MD_CI>(Xs, MD_C, MD_C, L.t2i.k.w, L.t2i.k.b, W.pek[layer] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
-    md_img_gemm<MD_CI>(Xs, MD_C, MD_C, L.t2i.v.w, L.t2i.v.b, nullptr, 0, Vs, MD_LDK);
+    MD_GEMM(MD_CI, Xs, MD_LDX, MD_C, L.t2i.k, 4 * layer + MD_W_T2I_K, L.t2i.k.b, W.pek[layer] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
+    MD_STAMP();
+    MD_GEMM(MD_CI, Xs, MD_LDX, MD_C, L.t2i.v, 4 * layer + MD_W_T2I_V, L.t2i.v.b, nullptr, 0, Vs, MD_LDK);
+    MD_STAMP();
     MD_BAR();
     // ---- I1: partial token->image attention over this block's rows
     md_load_rows(TB, ws + off.TQ, MD_CI, MD_CI, NT);
@@ -397,13 +664,10 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
       for (int i = tid; i < NT * MD_C; i += MD_THREADS) ws[off.Q + i] = Ta[i];
     md_tok_linear(Ta, MD_C, MD_C, L.fc1.w, MD_C, L.fc1.b, MD_MLP, ws + off.HID, MD_MLP, NT, true, nullptr, 0, false, blk, G);
     MD_BAR();
-    // ---- T6: MLP fc2 + residual (K = 2048 in chunks of 512 through the token buffer)
-    for (int kc = 0; kc < MD_MLP; kc += 512) {
-      __syncthreads();
-      md_load_rows(TB, ws + off.HID + kc, MD_MLP, 512, NT);
-      __syncthreads();
-      md_tok_linear(TB, 512, 512, L.fc2.w + kc, MD_MLP, L.fc2.b, MD_C, ws + off.QPRE, MD_C, NT, false, ws + off.Q, MD_C, kc != 0, blk, G);
-    }
+    // ---- T6: MLP fc2 + residual: the hidden rows [NT][2048] fill the token buffer + the (idle) weight ring; K split over the 8 warps
+    md_load_rows(TB, ws + off.HID, MD_MLP, MD_MLP, NT);
+    __syncthreads();
+    md_tok_linear_coop(TB, MD_MLP, MD_MLP, L.fc2.w, MD_MLP, L.fc2.b, MD_C, ws + off.QPRE, MD_C, NT, ws + off.Q, MD_C, blk, G, red);
     MD_BAR();
     // ---- T7: norm3 -> queries; image->token k = (queries + pe) Wk, v = queries Wv
     md_load_rows_ln(Ta, ws + off.QPRE, NT, L.n3.w, L.n3.b, 1e-5f);
@@ -414,9 +678,9 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
     }
     __syncthreads();
     md_tok_linear(Tb, MD_C, MD_C, L.i2t.k.w, MD_C, L.i2t.k.b, MD_CI, ws + off.TK, MD_CI, NT, false, nullptr, 0, false, blk, G);
-    md_tok_linear(Ta, MD_C, MD_C, L.i2t.v.w, MD_C, L.i2t.v.b, MD_CI, ws + off.TV, MD_CI, NT, false, nullptr, 0, false, blk, G);
+    md_tok_linear(Ta, MD_C, MD_C, L.i2t.v.w, MD_C, L.i2t.v.b, MD_CI, ws + off.TV, MD_CI, NT, false, nullptr, 0, false, blk, G, 4);
     // image side, row-local: q = (keys + pe) Wq + b
-    md_img_gemm<MD_CI>(Xs, MD_C, MD_C, L.i2t.q.w, L.i2t.q.b, W.peq[layer] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
+    MD_GEMM(MD_CI, Xs, MD_LDX, MD_C, L.i2t.q, 4 * layer + MD_W_I2T_Q, L.i2t.q.b, W.peq[layer] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
     MD_BAR();
     // ---- I2: image->token attention (softmax over the NT tokens per (row, head)), out projection, residual, norm4 — all row-local
     md_load_rows(TB, ws + off.TK, MD_CI, MD_CI, NT);
@@ -466,9 +730,15 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
         *reinterpret_cast<float4*>(Vs + r * MD_LDK + h * 16 + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
     }
     __syncthreads();
-    md_img_gemm<MD_C>(Vs, MD_LDK, MD_CI, L.i2t.out.w, L.i2t.out.b, nullptr, 0, TB, MD_C);   // [32][256] into the token buffer
+    if (!EXACT) {
+      md_split_rows(Vs, MD_LDK, MD_CI, AH, AL, MD_LDA);
+      __syncthreads();
+    }
+    MD_GEMM(MD_C, Vs, MD_LDK, MD_CI, L.i2t.out, 4 * layer + MD_W_I2T_OUT, L.i2t.out.b, nullptr, 0, TB, MD_C);   // [32][256] into the token buffer
     __syncthreads();
     md_rows_add_ln(Xs, TB, MD_C, L.n4.w, L.n4.b, 1e-5f);
+    __syncthreads();
+    if (!EXACT) md_split_rows(Xs, MD_LDX, MD_C, AH, AL, MD_LDA);   // the updated image rows feed the next K / V / q projections
     __syncthreads();
   }
 
@@ -480,8 +750,8 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
     for (int i = tid; i < NT * MD_C; i += MD_THREADS) Ta[i] += tok_pe[i];
     __syncthreads();
     md_tok_linear(Ta, MD_C, MD_C, W.final_t2i.q.w, MD_C, W.final_t2i.q.b, MD_CI, ws + off.TQ, MD_CI, NT, false, nullptr, 0, false, blk, G);
-    md_img_gemm<MD_CI>(Xs, MD_C, MD_C, W.final_t2i.k.w, W.final_t2i.k.b, W.pek[2] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
-    md_img_gemm<MD_CI>(Xs, MD_C, MD_C, W.final_t2i.v.w, W.final_t2i.v.b, nullptr, 0, Vs, MD_LDK);
+    MD_GEMM(MD_CI, Xs, MD_LDX, MD_C, W.final_t2i.k, MD_W_FIN_K, W.final_t2i.k.b, W.pek[2] + static_cast<long long>(row0) * MD_CI, MD_CI, Ks, MD_LDK);
+    MD_GEMM(MD_CI, Xs, MD_LDX, MD_C, W.final_t2i.v, MD_W_FIN_V, W.final_t2i.v.b, nullptr, 0, Vs, MD_LDK);
     MD_BAR();
     md_load_rows(TB, ws + off.TQ, MD_CI, MD_CI, NT);
     __syncthreads();
@@ -511,8 +781,11 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
         const int head = o >> 8, n = o & 255;
         const VgLinear lin = head < 4 ? W.hyper[head][stage] : (head == 4 ? W.iou[stage] : W.obj[stage]);
         const float* x = stage == 0 ? in + (head < 4 ? 2 + head : (head == 4 ? 1 : 0)) * MD_C : in + head * MD_C;
-        float a = 0.f;
-        for (int k = lane; k < MD_C; k += 32) a = fmaf(x[k], __ldg(lin.w + n * MD_C + k), a);
+        float a = 0.f, wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = __ldg(lin.w + n * MD_C + lane + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a = fmaf(x[lane + 32 * u], wv[u], a);
         a = warp_sum(a);
         if (lane == 0) outg[head * MD_C + n] = fmaxf(a + lin.b[n], 0.f);
       }
@@ -526,8 +799,11 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
       if (o < 128) { head = o >> 5; n = o & 31; } else if (o < 132) { head = 4; n = o - 128; } else { head = 5; n = 0; }
       const VgLinear lin = head < 4 ? W.hyper[head][2] : (head == 4 ? W.iou[2] : W.obj[2]);
       const float* x = H1s + head * MD_C;
-      float a = 0.f;
-      for (int k = lane; k < MD_C; k += 32) a = fmaf(x[k], __ldg(lin.w + n * MD_C + k), a);
+      float a = 0.f, wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(lin.w + n * MD_C + lane + 32 * u);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a = fmaf(x[lane + 32 * u], wv[u], a);
       a = warp_sum(a) + lin.b[n];
       if (lane == 0) {
         if (head < 4) ws[off.HYP + head * 32 + n] = a;
@@ -541,9 +817,9 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
   // masks[m] = hyper_in[m] . up2
   __shared__ float hyp[4 * 32];
   if (tid < 128) hyp[tid] = __ldcg(ws + off.HYP + tid);
-  md_img_gemm<MD_C>(Xs, MD_C, MD_C, W.up1.w, nullptr, nullptr, 0, TB, MD_C);   // [32][(dy,dx,co) = 4*64]
+  MD_GEMM(MD_C, Xs, MD_LDX, MD_C, W.up1, MD_W_UP1, nullptr, nullptr, 0, TB, MD_C);   // [32][(dy,dx,co) = 4*64]
   __syncthreads();
-  float* U1 = Ks;  // [128 up1 pixels][64] = 8192 floats over the Ks + Vs regions (32*132*2 = 8448)
+  float* U1 = Xs;  // [128 up1 pixels][68] = 8704 floats over the (now dead) image rows and the head of the K region (8320 + 8448 floats)
   for (int px = warp; px < 4 * MD_RB; px += MD_THREADS / 32) {
     const int r = px >> 2, sub = px & 3;
     const int grow = row0 + r, y = grow / fs, x = grow - y * fs;
@@ -561,14 +837,18 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int c = lane + 32 * i;
-      U1[px * 64 + c] = md_gelu((v[i] - mean) * rstd * __ldg(W.up_ln.w + c) + __ldg(W.up_ln.b + c));
+      U1[px * MD_LDU + c] = md_gelu((v[i] - mean) * rstd * __ldg(W.up_ln.w + c) + __ldg(W.up_ln.b + c));
     }
   }
   __syncthreads();
   const int side = 4 * fs;
   float* mout = p.masks + static_cast<long long>(b) * 4 * side * side;
   for (int pass = 0; pass < 4; ++pass) {  // 32 up1 pixels per pass -> [32][(dy,dx,co) = 4*32] -> 128 up2 pixels
-    md_img_gemm<MD_CI>(U1 + pass * 32 * 64, 64, 64, W.up2.w, nullptr, nullptr, 0, TB, MD_LDK);
+    if (!EXACT) {
+      md_split_rows(U1 + pass * 32 * MD_LDU, MD_LDU, 64, AH, AL, MD_LDA);
+      __syncthreads();
+    }
+    MD_GEMM(MD_CI, U1 + pass * 32 * MD_LDU, MD_LDU, 64, W.up2, MD_W_UP2, nullptr, nullptr, 0, TB, MD_LDK);
     __syncthreads();
     if (tid < 128) {
       const int pl = tid >> 2, sub2 = tid & 3;           // local up1 pixel, position inside its 2x2 up2 patch
@@ -595,12 +875,23 @@ __global__ void __launch_bounds__(MD_THREADS, 1) mask_decoder_kernel(const MdPar
     }
     __syncthreads();
   }
+  if (p.timeline && blk == 0 && b == 0 && tid == 0) {
+    unsigned long long t_;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+    p.timeline[nbar + 1] = t_;
+    p.timeline[63] = nbar;
+  }
 #undef MD_BAR
+#undef MD_GEMM
 }
 
 }  // namespace vg
 
 using namespace vg;
+
+static unsigned long long* g_md_timeline = nullptr;
+/* diagnostic (scripts/gpu_md_timeline.py): device buffer of 64 u64 that the next launches fill with block (0,0)'s globaltimer stamps; NULL disables */
+extern "C" void vg_mask_decoder_set_timeline(void* dev_buf) { g_md_timeline = static_cast<unsigned long long*>(dev_buf); }
 
 extern "C" long long vg_mask_decoder_workspace_bytes(int B, int fs) {
   const int G = fs * fs / MD_RB;
@@ -629,12 +920,15 @@ extern "C" int vg_mask_decoder(const VgMaskDecoder* d, void* stream) {
   p.ws = reinterpret_cast<float*>(static_cast<char*>(d->workspace) + 256 * 4);
   p.ws_obj_stride = off.total;
   p.w = *d->weights;
+  p.timeline = g_md_timeline;
   cudaError_t e = cudaMemsetAsync(p.bar, 0, 256 * 4, s);
   if (e != cudaSuccess) return set_error(VG_ECUDA, "vg_mask_decoder memset: %s", cudaGetErrorString(e));
-  const int smem = (MD_RB * MD_C + 2 * MD_RB * MD_LDK + MD_TB) * 4;
+  const int smem = (MD_RB * MD_LDX + 2 * MD_RB * MD_LDK + MD_TB + MD_WR) * 4 + 2 * MD_RB * MD_LDA * 2;
+  static const bool exact = [] { const char* v = getenv("VG_MD_EXACT"); return v && atoi(v) != 0; }();   // fp32-FMA contractions instead of the bf16 split
   static bool attr = false;
   if (!attr) {
-    e = cudaFuncSetAttribute(mask_decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = cudaFuncSetAttribute(mask_decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mask_decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_error(VG_ECUDA, "vg_mask_decoder smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -644,11 +938,14 @@ extern "C" int vg_mask_decoder(const VgMaskDecoder* d, void* stream) {
     int per_sm = 0, dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mask_decoder_kernel, MD_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mask_decoder_kernel<true>, MD_THREADS, smem);
     max_resident = per_sm * sms;
   }
   if (G > max_resident) return set_error(VG_ENOSUP, "vg_mask_decoder: %d row blocks per object exceed the %d co-resident blocks of this device", G, max_resident);
-  launch_k(mask_decoder_kernel, dim3(G, d->B), dim3(MD_THREADS), smem, s, p);
+  if (exact || d->force_exact)
+    launch_k(mask_decoder_kernel<true>, dim3(G, d->B), dim3(MD_THREADS), smem, s, p);
+  else
+    launch_k(mask_decoder_kernel<false>, dim3(G, d->B), dim3(MD_THREADS), smem, s, p);
   count_launch();
   return check_launch("mask_decoder_kernel");
 }

@@ -456,7 +456,7 @@ def conv3x3s2_ln_gelu_gemm(x: torch.Tensor, w_gemm: torch.Tensor, bias, ln_w, ln
 
 
 def mask_decoder_fused(weights: "L.VgMaskDecoderWeights", pix: torch.Tensor, dense_pe: torch.Tensor, no_mask: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor,
-                       tokens: torch.Tensor, fs: int, pix_shared: bool = False):
+                       tokens: torch.Tensor, fs: int, pix_shared: bool = False, exact: bool = False):
     """vg_mask_decoder: the whole SAM2 mask decoder for the B objects of one frame in ONE launch (include/vglamm.h). pix fp32 [B*HW, 256] (or [HW, 256]
     shared), s0 fp32 [16*HW, 32], s1 fp32 [4*HW, 64], tokens fp32 [B, Nt, 256] -> (masks [B,4,(4fs)^2], iou [B,4], mask tokens [B,4,256], obj [B,1])."""
     _require_cuda(pix, dense_pe, no_mask, s0, s1, tokens)
@@ -478,5 +478,6 @@ def mask_decoder_fused(weights: "L.VgMaskDecoderWeights", pix: torch.Tensor, den
     d.weights = C.pointer(weights)
     d.masks, d.iou, d.mask_tokens, d.obj = masks.data_ptr(), iou.data_ptr(), mt.data_ptr(), obj.data_ptr()
     d.workspace, d.workspace_bytes = ws.data_ptr(), nbytes
+    d.force_exact = int(exact)
     L.check(L.lib().vg_mask_decoder(C.byref(d), _stream()), "vg_mask_decoder")
     return masks, iou, mt, obj

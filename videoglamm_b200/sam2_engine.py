@@ -238,7 +238,27 @@ class Sam2Engine:
         for j in range(3):
             W.iou[j] = lin(f"{md}.iou_prediction_head.layers.{j}")
             W.obj[j] = lin(f"{md}.pred_obj_score_head.layers.{j}")
+        # tensor-core path: the 12 image-side matrices in nn.Linear layout, split into bf16 hi / lo (include/vglamm.h img_hi / img_lo)
+        def split(i, w):
+            w = w.reshape(w.shape[0], -1).contiguous()
+            hi = w.to(BF)
+            lo = (w - hi.float()).to(BF)
+            keep.extend([hi, lo])
+            W.img_hi[i], W.img_lo[i] = hi.data_ptr(), lo.data_ptr()
+
+        for i in range(2):
+            l = f"{md}.transformer.layers.{i}"
+            split(4 * i + 0, self._t(l + ".cross_attn_token_to_image.k_proj.weight"))
+            split(4 * i + 1, self._t(l + ".cross_attn_token_to_image.v_proj.weight"))
+            split(4 * i + 2, self._t(l + ".cross_attn_image_to_token.q_proj.weight"))
+            split(4 * i + 3, self._t(l + ".cross_attn_image_to_token.out_proj.weight"))
+        split(8, self._t(f + ".k_proj.weight"))
+        split(9, self._t(f + ".v_proj.weight"))
+        for i, key in ((10, ".output_upscaling.0"), (11, ".output_upscaling.3")):
+            wt = self._t(md + key + ".weight")                                   # [Cin, Cout, 2, 2] -> [(dy,dx,co)][Cin]
+            split(i, wt.permute(2, 3, 1, 0).reshape(-1, wt.shape[0]))
         self.fused_w = W
+        self.fused_exact = False            # True: fp32-FMA row-local contractions (vg_mask_decoder force_exact)
         self.no_mask_vec = self.no_mask_embed.reshape(-1).contiguous()
 
     def _sine_pos(self, H, W, num_pos_feats):
@@ -349,7 +369,7 @@ class Sam2Engine:
         B = sparse.shape[0]
         if self.fused_decoder and debug is None and s0.dtype == F32 and pix.shape[0] == B * HW:
             tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).contiguous()
-            return ops.mask_decoder_fused(self.fused_w, pix, self.dense_pe, self.no_mask_vec, s0, s1, tokens, cfg.feat_size)
+            return ops.mask_decoder_fused(self.fused_w, pix, self.dense_pe, self.no_mask_vec, s0, s1, tokens, cfg.feat_size, exact=self.fused_exact)
         tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(-1, C).contiguous()
         Nt = tokens.shape[0] // B
         keys = ops.add(pix, self.no_mask_embed)                       # src = image_embeddings + dense (no_mask_embed)
