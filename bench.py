@@ -255,7 +255,7 @@ def run_engine(args):
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip with >= 1 GFLOP: "
                          f"{tp['n']} launches carrying {tp['flops'] / max(tall['flops'], 1):.1%} of the GEMM FLOPs)", "achieved": ach, "peak": tf_peak,
-                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": NCU_TRAFFIC["dram_bytes"], "traffic_detail": NCU_TRAFFIC, "peak_source": f"{src} bf16_tflops_sustained",
+                         "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": ncu_traffic()["dram_bytes"], "traffic_detail": ncu_traffic(), "peak_source": f"{src} bf16_tflops_sustained",
                          "launches": tp["n"], "gemm_ms_per_clip": tp["ms"], "gemm_share_of_step": tp["ms"] / ms_clip,
                          "all_tensor_gemm_launches": {"launches": tall["n"], "ms_per_clip": tall["ms"], "achieved": ach_all, "frac": ach_all / tf_peak,
                                                       "note": "includes ~700 sub-GFLOP launches whose event-timed duration is launch latency"},
@@ -279,11 +279,21 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest-share tensor GEMM shape (Hiera stage-3 fc2, 32768 x 576 x 2304,
-# in-place fp32 residual) from the committed `ncu --set full` capture; algorithmic bytes of that launch: 151.0 (A) + 2.7 (W) + 75.5 (C read) +
-# 75.5 (C write) = 304.7 MB. Updated by hand when the capture is retaken (profiles/).
-NCU_TRAFFIC = {"kernel": "gemm_tcgen05_kernel<192> 32768x576x2304 +resid", "dram_bytes": 272.6e6, "algorithmic_bytes": 304.7e6,
-               "source": "profiles/r01_ncu_targets_final.md row 1 (229.2 MB read + 43.4 MB written; part of the in-place C update stays in L2)"}
+def ncu_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the largest-share tensor GEMM shape (Hiera stage-3 fc2, 32768 x 576 x 2304,
+    in-place fp32 residual), READ from the committed summary of the `ncu --set full` capture (profiles/r02_ncu_targets.csv, written by
+    scripts/ncu_summarize.py from the .ncu-rep that scripts/gpu_ncu_targets.py produced; launch id 1). Algorithmic bytes of that launch:
+    151.0 (A) + 2.7 (W) + 75.5 (C read) + 75.5 (C write) = 304.7 MB."""
+    import csv
+    for name in ("r02_ncu_targets.csv",):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            for row in csv.DictReader(open(path)):
+                if row["id"] == "1" and "gemm_tcgen05_kernel" in row["kernel"]:
+                    rd, wr = float(row["dram_read_MB"]), float(row["dram_write_MB"])
+                    return {"kernel": row["kernel"] + " 32768x576x2304 +resid", "dram_bytes": (rd + wr) * 1e6, "dram_read_bytes": rd * 1e6, "dram_write_bytes": wr * 1e6,
+                            "algorithmic_bytes": 304.7e6, "source": f"profiles/{name} launch id 1 ({row['us']} us under ncu, tensor pipe {row['tensor_pipe_pct']} %)"}
+    return {"kernel": "gemm_tcgen05_kernel 32768x576x2304 +resid", "dram_bytes": None, "algorithmic_bytes": 304.7e6, "source": "no committed ncu summary found"}
 
 
 def time_decode_step(model, L: int, reps: int = 8) -> dict:

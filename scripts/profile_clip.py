@@ -11,7 +11,7 @@ lmm_cfg, sam_cfg = make_lmm_config(), Sam2Config()
 sd = random_state_dict(videoglamm_param_shapes(lmm_cfg, sam_cfg), "cuda", seed=1234)
 model = VideoGLaMMForCausalLM(sd, lmm_cfg, sam_cfg, validate=False); del sd
 inp = [t.cuda() for t in bench.synth_inputs(0, pinned=False)]
-forced = {bench.SEG_STEP: lmm_cfg.seg_token_idx}
+forced = {st: lmm_cfg.seg_token_idx for st in bench.CFG["seg_steps"]}
 def step():
     return model.inference([inp[0]], [inp[1]], [inp[2]], inp[3], None, [bench.VIDEO_HW], max_new_tokens=bench.N_NEW, use_sam2_video_branch=True, forced_tokens=forced)
 n_warm = int(os.environ.get("WARM", 2))
