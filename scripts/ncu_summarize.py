@@ -25,7 +25,7 @@ def main(src, dst):
     for r in data:
         d = {"id": r[0], "kernel": r[ki].split("(")[0].replace("void ", ""), "grid": r[gi], "block": r[bi]}
         for k, i in idx.items():
-            if i is None or r[i] == "":
+            if i is None or r[i] in ("", "no data", "n/a"):
                 d[k] = ""
                 continue
             v = float(r[i].replace(",", ""))
