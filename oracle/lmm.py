@@ -170,6 +170,9 @@ def avg_pool_tokens(x, out_side):
 def visual_tokens(sd, cfg: LmmCfg, images, context_images):
     """encode_videos arch.py:121-151 + project(input_type='video') :164-191. images [T,3,224,224] (IV2), context_images
     [T,3,336,336] (CLIP) -> [T*(gc/2)^2 + T*(gv/2)^2, hidden] with the CONTEXT block first."""
+    if context_images is None:   # still image: encode_images arch.py:110-119 (CLIP tower, patch features) + project(input_type="image") :193-203 (no pooling)
+        ctx = clip_tower(sd, "model.image_vision_tower.vision_tower", cfg.clip, images)
+        return projector(sd, "model.image_mm_projector", ctx, cfg.proj_depth).reshape(-1, cfg.phi.hidden)
     T = images.shape[0]
     vid = iv2_tower(sd, "model.vision_tower", cfg.iv2, images.reshape(T // CHUNK, CHUNK, *images.shape[1:]))[:, 1:]
     ctx = clip_tower(sd, "model.image_vision_tower.vision_tower", cfg.clip, context_images)

@@ -113,3 +113,87 @@ def test_e2e_against_reference_golden():
     agree = (got == want_masks).float().mean().item()
     decided = logits.abs() > 0.05 * logits.abs().max()          # pixels whose sign bf16 noise cannot flip
     assert agree > 0.98 and torch.equal(got[decided], want_masks[decided]), agree
+
+
+def test_still_image_input_matches_oracle():
+    """context_images=None: the still-image branch (arch.py:110-119, 193-203; chat.py:458-487) through the public API vs the oracle."""
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    arch = dict(M.TINY_LMM)
+    ocfg, scfg = M.make_cfg(**arch, seg_token_idx=300), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**arch, seg_token_idx=300), Sam2Config(**O.TINY))
+    torch.manual_seed(8)
+    side = ocfg.clip.image_size
+    image, sam = torch.randn(1, 3, side, side), torch.randn(1, 3, 256, 256)
+    ids = torch.cat([torch.randint(3, 290, (5,)), torch.tensor([-200]), torch.randint(3, 290, (7,))])
+    forced = {1: 300}
+    for ctx in (None, [None]):
+        out_ids, segs = model.inference([image.cuda()], ctx, [sam.cuda()], ids[None].cuda(), None, [(48, 64)], max_new_tokens=4, use_sam2_video_branch=True,
+                                        forced_tokens=forced)
+        with torch.no_grad():
+            ids_ref, emb_ref, _ = M.generate(sd, ocfg, ids, image, None, 4, forced=forced)
+            ssd = {k[len("model.visual_model."):]: v for k, v in sd.items() if k.startswith("model.visual_model.")}
+            ref = O.run_video(ssd, scfg, sam, emb_ref[:, None, :], (48, 64))
+        assert torch.equal(out_ids[0].cpu(), ids_ref)
+        assert out_ids.shape[1] == ids.shape[0] + 4 and sorted(segs[0]) == [0]
+        assert (torch.from_numpy(segs[0][0][0]) == (ref[0][0, 0] > 0)).float().mean() > 0.98
+
+
+def test_from_pretrained_round_trip(tmp_path):
+    """An exported HF directory (config.json + pytorch_model.bin + generation_config.json, CLIP in its own HF directory, InternVideo2 .pt) loaded with
+    from_pretrained, taken through the calls chat.py makes (resize_token_embeddings, initialize_vision_modules, tower handles, .bfloat16().cuda()),
+    gives exactly the outputs of the engine built directly from the same state dict; the multi-id EOS list of generation_config.json stops generation."""
+    import json
+    from safetensors.torch import save_file
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    arch = dict(M.TINY_LMM)
+    seg = 300
+    ocfg, scfg = M.make_cfg(**arch, seg_token_idx=seg), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    cp, ip = "model.image_vision_tower.vision_tower.", "model.vision_tower."
+    ckpt, clip_dir = tmp_path / "ckpt", tmp_path / "clip"
+    ckpt.mkdir(); clip_dir.mkdir()
+    save_file({k[len(cp):]: v.contiguous() for k, v in sd.items() if k.startswith(cp)}, str(clip_dir / "model.safetensors"))
+    torch.save({k[len(ip):]: v for k, v in sd.items() if k.startswith(ip)}, str(tmp_path / "iv2.pt"))
+    torch.save({k: v for k, v in sd.items() if not k.startswith(cp) and not k.startswith(ip)}, str(ckpt / "pytorch_model.bin"))
+    p = ocfg.phi
+    json.dump(dict(vocab_size=p.vocab, hidden_size=p.hidden, num_hidden_layers=p.layers, num_attention_heads=p.heads, intermediate_size=p.inter,
+                   rope_theta=p.rope_theta, rms_norm_eps=p.eps, sliding_window=p.sliding_window, seg_token_idx=seg, out_dim=256, use_sam2=True,
+                   mm_vision_tower=str(tmp_path / "iv2.pt"), image_mm_vision_tower=str(clip_dir), eos_token_id=2,
+                   vg_arch_overrides={k: v for k, v in arch.items() if k != "phi"},
+                   vg_sam2_overrides={k: (list(v) if isinstance(v, tuple) else v) for k, v in O.TINY.items()}), open(ckpt / "config.json", "w"))
+    torch.manual_seed(3)
+    T = 4
+    images, ctx, sam = torch.randn(T, 3, 56, 56), torch.randn(T, 3, 56, 56), torch.randn(2, 3, 256, 256)
+    ids = torch.cat([torch.randint(3, 290, (5,)), torch.full((T,), -200), torch.randint(3, 290, (7,))])[None].cuda()
+    direct = VideoGLaMMForCausalLM(sd, make_lmm_config(**arch, seg_token_idx=seg), Sam2Config(**O.TINY))
+    forced = {1: seg}
+    want_ids, want_segs = direct.inference([images.cuda()], [ctx.cuda()], [sam.cuda()], ids, None, [(48, 64)], max_new_tokens=6, use_sam2_video_branch=True,
+                                           forced_tokens=forced)
+    natural = [int(t) for t in want_ids[0, ids.shape[1]:]]
+    json.dump(dict(eos_token_id=[2, natural[3]]), open(ckpt / "generation_config.json", "w"))       # the 4th generated token is an EOS of the generation config
+    m = VideoGLaMMForCausalLM.from_pretrained(str(ckpt), low_cpu_mem_usage=False, use_sam2_video_branch=True, torch_dtype=torch.bfloat16)
+    assert m.lmm is None                                                           # weights on the host until .cuda()
+    m.resize_token_embeddings(p.vocab)
+    m.config.eos_token_id = 2                                                      # chat.py:305 overwrites it with the tokenizer's single id
+    m.get_model().initialize_vision_modules(m.get_model().config)
+    m.get_model().get_vision_tower().to(dtype=torch.bfloat16, device=0)
+    m.get_model().get_image_vision_tower().to(dtype=torch.bfloat16, device=0)
+    m = m.bfloat16().cuda()
+    m.eval()
+    got_ids, got_segs = m.inference([images.cuda()], [ctx.cuda()], [sam.cuda()], ids, None, [(48, 64)], max_new_tokens=6, use_sam2_video_branch=True,
+                                    forced_tokens=forced)
+    n = got_ids.shape[1] - ids.shape[1]
+    assert n == 4 and torch.equal(got_ids[0], want_ids[0, : ids.shape[1] + 4])     # stopped at the generation_config EOS id
+    import numpy as np
+    for t in want_segs[0]:
+        assert np.array_equal(got_segs[0][t][0], want_segs[0][t][0])
+    with pytest.raises(FileNotFoundError):                                          # unresolvable tower path is named, not a generic missing-keys error
+        cfgj = json.load(open(ckpt / "config.json")); cfgj["image_mm_vision_tower"] = "openai/clip-vit-large-patch14-336"
+        json.dump(cfgj, open(ckpt / "config.json", "w"))
+        VideoGLaMMForCausalLM.from_pretrained(str(ckpt)).initialize_vision_modules(None)

@@ -52,3 +52,26 @@ def test_e2e_inference_live_reference_equals_golden_and_oracle():
     assert np.array_equal(out_ids, want_ids.numpy()) and np.array_equal(masks, want_masks.numpy())
     ids, logits = _e2e_oracle()
     assert torch.equal(ids, want_ids) and torch.equal(logits > 0, want_masks)
+
+
+def test_still_image_branch_live_reference_equals_oracle():
+    """context_images=None (chat.py:458-487): one CLIP-preprocessed 336 px image, 576 un-pooled tokens at the single <image> sentinel, one SAM2
+    frame. Token ids bit-exact and masks identical between the reference's inference() and the oracle composition."""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as MG
+    from oracle import lmm as M
+    ref, sd, ocfg, scfg = MG.ref_videoglamm()
+    torch.manual_seed(5)
+    image, sam = torch.randn(1, 3, 336, 336), torch.randn(1, 3, 256, 256)
+    ids = torch.cat([torch.tensor([1]), torch.randint(3, 290, (5,)), torch.tensor([-200]), torch.randint(3, 290, (6,))])
+    with torch.no_grad():
+        out_ids, segs = ref.inference([image], None, [sam], ids[None], None, [MG.E2E_HW], max_new_tokens=MG.E2E_NEW, use_sam2_video_branch=True)
+        o_ids, emb, _ = M.generate(sd, ocfg, ids, image, None, MG.E2E_NEW, forced=MG.E2E_FORCED)
+        ssd = {k[len("model.visual_model."):]: v for k, v in sd.items() if k.startswith("model.visual_model.")}
+        logits = O.run_video(ssd, scfg, sam, emb[:, None, :], MG.E2E_HW)
+    assert torch.equal(out_ids[0], o_ids)
+    for o in range(emb.shape[0]):
+        assert np.array_equal(segs[0][0][o], (logits[0][o, 0] > 0).numpy())

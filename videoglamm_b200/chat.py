@@ -34,23 +34,24 @@ def initialize_model_videogptplus(model_base, precision, local_rank, load_in_8bi
     if load_in_8bit or load_in_4bit:
         raise NotImplementedError("bitsandbytes quantisation is not part of the B200 engine (weights are bf16)")
     torch.cuda.set_device(int(local_rank) if local_rank is not None else 0)
-    cfg = json.load(open(os.path.join(model_base, "config.json")))
-    clip_path = cfg.get("image_mm_vision_tower") or cfg.get("image_vision_tower")
+    # the CLIP / InternVideo2 towers are resolved from config.image_mm_vision_tower (local HF directory or a hub id in the local HF cache) and
+    # config.mm_vision_tower inside from_pretrained; an unresolvable path raises there / in initialize_vision_modules, naming the path
     model = VideoGLaMMForCausalLM.from_pretrained(model_base, low_cpu_mem_usage=False, use_sam2_video_branch=use_sam2_video_branch,
-                                                  torch_dtype={"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision, torch.float32),
-                                                  clip_path=clip_path if clip_path and os.path.isdir(clip_path) else None)
+                                                  torch_dtype={"bf16": torch.bfloat16, "fp16": torch.float16}.get(precision, torch.float32))
     tokenizer = AutoTokenizer.from_pretrained(model_base, use_fast=False)
     tokenizer.pad_token = tokenizer.unk_token
     tokenizer.add_tokens("[SEG]")
     seg_token_idx = tokenizer.convert_tokens_to_ids("[SEG]")
-    if seg_token_idx != model.config.seg_token_idx:                    # the engine packed lm_head / embeddings for the exported vocabulary
-        raise ValueError(f"tokenizer places [SEG] at {seg_token_idx}, the checkpoint was exported with {model.config.seg_token_idx}")
-    model.config.eos_token_id = [tokenizer.eos_token_id] if tokenizer.eos_token_id is not None else []
+    model.resize_token_embeddings(len(tokenizer))                      # chat.py:300 (a no-op for exported checkpoints, which carry the resized matrices)
+    model.config.seg_token_idx = seg_token_idx                         # chat.py:303
+    model.config.eos_token_id = tokenizer.eos_token_id          # chat.py:305; the ids of generation_config.json keep stopping generation (_eos_ids)
     model.config.bos_token_id = tokenizer.bos_token_id
     model.config.pad_token_id = tokenizer.pad_token_id
     if tokenizer.pad_token_id is None:                                 # chat.py:310-313 (llama-3.1 tokenizers)
         tokenizer.pad_token = tokenizer.eos_token
         tokenizer.pad_token_id = tokenizer.eos_token_id
+    model.get_model().initialize_vision_modules(model.get_model().config)   # chat.py:315 (strict: the tower weights must be resolvable)
+    model = model.bfloat16().cuda()
     model.eval()
     num_frames = int(os.environ.get("NUM_FRAMES", 16))                 # model/videogpt_plus/constants.py
     enc_preprocessor = EncPreprocessor_VideoGPTPlus(num_frames=num_frames)

@@ -233,6 +233,15 @@ class LmmEngine:
         c = ops.pool2x2(c, T, gc, gc, is_max=False)
         return torch.cat([c, v], 0)
 
+    def image_tokens(self, image: torch.Tensor) -> torch.Tensor:
+        """Still-image input (context_images=None): encode_images arch.py:110-119 (the CLIP tower on the 336 px image, patch features) +
+        project(input_type="image") :193-203 (image_mm_projector, NO pooling) -> fp32 [n*576, hidden]."""
+        ctx = self.clip(image)[:, 1:]
+        return self._project(ctx, self.ctx_proj)
+
+    def visual_tokens_any(self, images: torch.Tensor, context_images: torch.Tensor | None) -> torch.Tensor:
+        return self.image_tokens(images) if context_images is None else self.visual_tokens(images, context_images)
+
     # ------------------------------------------------------------------------------------------------ Phi-3
     def _alloc_cache(self, max_len: int):
         ph = self.cfg.phi
@@ -271,7 +280,14 @@ class LmmEngine:
         self.dec_nk.add_(1)
         return x, nxt
 
-    def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False) -> torch.Tensor:
+    def logits_all(self, x_resid: torch.Tensor) -> torch.Tensor:
+        """Full-sequence logits from the un-normalised residual rows [n, hidden]: RMSNorm without weight, then the lm_head that carries the folded
+        final-norm weight (the same arithmetic as the decode path) -> fp32 [n, vocab]."""
+        P = self.P
+        h = ops.norm(x_resid, self.ones, eps=self.cfg.phi.eps, rms=True, out_dtype=F32 if P else BF)
+        return ops.gemm(h, self.lm_head.W(P), out_dtype=F32)
+
+    def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False, raw: bool = False) -> torch.Tensor:
         """HF Phi3Model.forward (called at language_model/phi3.py:72-81) on rows [pos0, pos0+n) given a cache holding rows [0,pos0).
         x fp32 [n, hidden] (modified in place as the residual stream) -> final-norm hidden fp32 [n, hidden]."""
         ph = self.cfg.phi
@@ -294,6 +310,8 @@ class LmmEngine:
             h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=adt)
             h = ops.gemm(h, L["gu"].W(P), glu=True, act="silu", out_dtype=adt)
             x = ops.gemm(h, L["down"].W(P), resid=x, out=x)
+        if raw:
+            return x                                        # un-normalised residual rows (logits_all / final norm by the caller)
         if last_only:
             return x[-1:].contiguous()                      # un-normalised residual row: the consumers fuse the final norm
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
@@ -324,7 +342,9 @@ class LmmEngine:
         returns (output_ids int64 [1, L_txt+N] incl. -200 sentinels, pred_embeddings fp32 [n_seg, out_dim]).
         The hidden state that PREDICTED each [SEG] (mask shifted by one, :803-806) is the final-norm hidden of the step that emitted it."""
         cfg = self.cfg
-        if self.P:
+        if context_images is None:      # still image (chat.py:458-487): CLIP-preprocessed image -> 576 un-pooled tokens at the single <image> sentinel
+            vis = self.image_tokens(images) if self.P else self.g_vis((tuple(images.shape), None), self.image_tokens, image=images)
+        elif self.P:
             vis = self.visual_tokens(images, context_images)
         else:
             vis = self.g_vis((tuple(images.shape), tuple(context_images.shape)), self.visual_tokens, images=images, context_images=context_images)

@@ -14,6 +14,7 @@ import torch
 class ClipPipeline:
     def __init__(self, model, depth: int = 2):
         self.model = model
+        model._ensure_engines()
         self.depth = depth
         self.s_lmm = torch.cuda.Stream(device=model.device)
         self.s_sam = torch.cuda.Stream(device=model.device)
