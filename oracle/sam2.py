@@ -526,7 +526,7 @@ def run_video(sd, cfg: Sam2Cfg, images, text_embeds, video_hw, collect=None):
     return outs
 
 
-def run_framewise(sd, cfg: Sam2Cfg, images, text_embeds, video_hw):
+def run_framewise(sd, cfg: Sam2Cfg, images, text_embeds, video_hw, n_zero_dense: int = 0):
     """SAM2 part of VideoGLaMM_SAM2.inference_framewise (VideoGLaMM.py:598-768) with get_visual_embs_sam2 (:205-241): per frame,
     image_embed = top feature + no_mem_embed; sam_prompt_encoder(points=None, boxes=None, masks=None, text_embeds) -> the text token only;
     sam_mask_decoder(multimask_output=False, repeat_image=True) (stability fallback on); postprocess_masks (:147-153)."""
@@ -536,6 +536,8 @@ def run_framewise(sd, cfg: Sam2Cfg, images, text_embeds, video_hw):
         fpn, _ = forward_image(sd, cfg, images[t:t + 1].float())
         image_embed = fpn[2] + sd["no_mem_embed"].reshape(1, -1, 1, 1)
         dense = sd["sam_prompt_encoder.no_mask_embed.weight"].reshape(1, -1, 1, 1).expand(B, -1, cfg.feat_size, cfg.feat_size)
+        if n_zero_dense:   # model_forward pads the objects to 4 with ZERO sparse and ZERO dense embeddings (VideoGLaMM.py:416-433): the last n rows
+            dense = torch.cat([dense[: B - n_zero_dense], torch.zeros_like(dense[B - n_zero_dense:])], 0)
         hi = [fpn[0].expand(B, -1, -1, -1), fpn[1].expand(B, -1, -1, -1)]
         low, _, _, _, _, _ = mask_decoder(sd, cfg, image_embed, dense_pe(sd, cfg), text_embeds, dense, hi, multimask_output=False, repeat_image=True)
         outs.append(F.interpolate(low.float(), video_hw, mode="bilinear", align_corners=False))

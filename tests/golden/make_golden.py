@@ -118,14 +118,15 @@ def e2e_inputs():
     return images, ctx, sam, ids
 
 
-def ref_videoglamm(workdir=None):
+def ref_videoglamm(workdir=None, sam2_overrides=None, sam2_cfg_kw=None):
     """The reference's full VideoGLaMMForCausalLM (video branch) on CPU: true IV2 width/grid and CLIP width/336 px (hard-coded in the
     reference's composition), reduced depths, tiny Phi-3 and tiny SAM2. Weights = oracle.weights seed 11."""
     import tempfile
-    ocfg, scfg = M.make_cfg(**E2E_LMM, seg_token_idx=E2E_SEG), O.Sam2Cfg(**O.TINY)
+    ocfg, scfg = M.make_cfg(**E2E_LMM, seg_token_idx=E2E_SEG), O.Sam2Cfg(**(sam2_cfg_kw or O.TINY))
     c = ocfg.clip
     os.environ["NUM_FRAMES"] = "4"
-    ref = H.build_videoglamm(workdir or tempfile.mkdtemp(), phi=E2E_LMM["phi"], iv2_depth=E2E_LMM["iv2"]["depth"], sam2_overrides=SAM2_TINY_OVERRIDES,
+    ref = H.build_videoglamm(workdir or tempfile.mkdtemp(), phi=E2E_LMM["phi"], iv2_depth=E2E_LMM["iv2"]["depth"],
+                             sam2_overrides=SAM2_TINY_OVERRIDES if sam2_overrides is None else sam2_overrides,
                              clip=dict(width=c.width, mlp=c.mlp, layers=c.layers, heads=c.heads, image_size=c.image_size, patch=c.patch), seg_token_idx=E2E_SEG)
     sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=11)
     r = ref.load_state_dict(sd, strict=False)

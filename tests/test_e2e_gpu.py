@@ -197,3 +197,43 @@ def test_from_pretrained_round_trip(tmp_path):
         cfgj = json.load(open(ckpt / "config.json")); cfgj["image_mm_vision_tower"] = "openai/clip-vit-large-patch14-336"
         json.dump(cfgj, open(ckpt / "config.json", "w"))
         VideoGLaMMForCausalLM.from_pretrained(str(ckpt)).initialize_vision_modules(None)
+
+
+@pytest.mark.parametrize("precise,tol", [("all", 2e-3), ("heads", 6e-2)])
+def test_model_forward_validation_and_loss_values(precise, tol):
+    """model_forward on the collate_fn dict (VideoGLaMM.py:325-558) through `model(**batch)` (forward dispatch :897-903): validation path
+    (inference=True: per-frame masks padded to 4 objects, zero sparse + zero dense padding rows) and the training path's loss values vs
+    oracle/model_forward.py (pinned against the reference's own model_forward in tests/test_oracle_vs_reference.py)."""
+    from oracle import lmm as M, model_forward as OMF, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    seg = 300
+    ocfg, scfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=seg), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=seg), Sam2Config(**O.TINY), precise=precise)
+    model.ce_loss_weight, model.dice_loss_weight, model.bce_loss_weight = 1.0, 0.5, 2.0
+    torch.manual_seed(9)
+    T = 4
+    images, ctx, sam = torch.randn(T, 3, 56, 56), torch.randn(T, 3, 56, 56), torch.randn(2, 3, 256, 256)
+    ids = torch.cat([torch.tensor([1]), torch.randint(3, 290, (5,)), torch.full((T,), -200), torch.randint(3, 290, (4,)), torch.tensor([seg]),
+                     torch.randint(3, 290, (3,)), torch.tensor([seg, 2, 0, 0])])[None]
+    labels = ids.clone()
+    labels[:, :12] = -100
+    am = torch.ones_like(ids, dtype=torch.bool)
+    am[:, -2:] = False                                                  # right padding
+    gt = (torch.rand(2, 2, 48, 64) > 0.5).float()
+    batch = dict(images_for_sam=[sam], images=[images], context_images=[ctx], input_ids=ids, labels=labels, attention_masks=am,
+                 offset=torch.LongTensor([0, 1]), masks_list=[gt], label_list=[torch.zeros(48, 64)], resize_list=[(256, 256)])
+    got_v = model(**batch, inference=True)
+    got_t = model(**batch, inference=False)
+    with torch.no_grad():
+        want_v = OMF.model_forward(sd, ocfg, scfg, [sam], [images], [ctx], ids, labels, am, batch["offset"], [gt], batch["label_list"], inference=True)
+        want_t = OMF.model_forward(sd, ocfg, scfg, [sam], [images], [ctx], ids, labels, am, batch["offset"], [gt], batch["label_list"], inference=False,
+                                   weights=(1.0, 0.5, 2.0))
+    assert len(got_v["pred_masks"][0]) == 2 and tuple(got_v["pred_masks"][0][0].shape) == (4, 48, 64)
+    for t in range(2):
+        a, b = got_v["pred_masks"][0][t].cpu(), want_v["pred_masks"][0][t]
+        e = ((a - b).norm() / b.norm()).item()
+        assert e < tol, (t, e)
+    for k in ("ce_loss", "mask_bce_loss", "mask_dice_loss", "loss"):
+        assert abs(float(got_t[k]) - float(want_t[k])) < tol * max(1.0, abs(float(want_t[k]))), (k, float(got_t[k]), float(want_t[k]))

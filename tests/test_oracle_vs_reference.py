@@ -75,3 +75,43 @@ def test_still_image_branch_live_reference_equals_oracle():
     assert torch.equal(out_ids[0], o_ids)
     for o in range(emb.shape[0]):
         assert np.array_equal(segs[0][0][o], (logits[0][o, 0] > 0).numpy())
+
+
+def test_model_forward_live_reference_equals_oracle():
+    """The reference's own model_forward (validation path inference=True AND the training path's loss values) on the collate_fn dict vs
+    oracle/model_forward.py: padded-to-4 per-frame masks and ce / bce / dice losses."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_golden as MG
+    from oracle import model_forward as OMF
+    # get_visual_embs_sam2 hard-codes the 1024 px feature sizes (VideoGLaMM.py:225): tiny Hiera WIDTH / DEPTH, full 1024 px image
+    kw = {k: v for k, v in O.TINY.items() if k != "image_size"}
+    ref, sd, ocfg, scfg = MG.ref_videoglamm(sam2_overrides=[o for o in MG.SAM2_TINY_OVERRIDES if "image_size" not in o], sam2_cfg_kw=kw)
+    ref.ce_loss_weight, ref.dice_loss_weight, ref.bce_loss_weight = 1.0, 0.5, 2.0
+    torch.manual_seed(9)
+    images, ctx, _, _ = MG.e2e_inputs()
+    sam = torch.randn(2, 3, 1024, 1024)
+    seg = MG.E2E_SEG
+    ids = torch.cat([torch.tensor([1]), torch.randint(3, 290, (5,)), torch.full((4,), -200), torch.randint(3, 290, (4,)), torch.tensor([seg]),
+                     torch.randint(3, 290, (3,)), torch.tensor([seg, 2])])[None]
+    labels = ids.clone()
+    labels[:, :12] = -100
+    am = torch.ones_like(ids, dtype=torch.bool)
+    gt = (torch.rand(2, 2, 48, 64) > 0.5).float()
+    batch = dict(images_for_sam=[sam], images=[images], context_images=[ctx], input_ids=ids, labels=labels, attention_masks=am,
+                 offset=torch.LongTensor([0, 1]), masks_list=[gt], label_list=[torch.zeros(48, 64)], resize_list=[(1024, 1024)])
+    with torch.no_grad():
+        want_v = ref.model_forward(**batch, inference=True)
+        ref.training = True      # top module only: phi3.py:104-107 returns the per-layer hidden-state tuple only in training mode (submodules stay in eval)
+        want_t = ref.model_forward(**batch, inference=False)
+        ref.training = False
+        got_v = OMF.model_forward(sd, ocfg, scfg, [sam], [images], [ctx], ids, labels, am, batch["offset"], [gt], batch["label_list"], inference=True)
+        got_t = OMF.model_forward(sd, ocfg, scfg, [sam], [images], [ctx], ids, labels, am, batch["offset"], [gt], batch["label_list"], inference=False,
+                                  weights=(1.0, 0.5, 2.0))
+    assert len(want_v["pred_masks"][0]) == 2 and want_v["pred_masks"][0][0].shape == (4, 48, 64)          # padded to 4 objects
+    for t in range(2):
+        a, b = got_v["pred_masks"][0][t], want_v["pred_masks"][0][t].float()
+        assert (a - b).abs().max() < 1e-3 * b.abs().max().clamp_min(1.0), (t, (a - b).abs().max())
+    for k in ("ce_loss", "mask_bce_loss", "mask_dice_loss", "loss"):
+        assert abs(float(got_t[k]) - float(want_t[k])) < 1e-4 * max(1.0, abs(float(want_t[k]))), (k, float(got_t[k]), float(want_t[k]))

@@ -356,7 +356,7 @@ class Sam2Engine:
         h = ops.gemm(h, layers[1].W(P), bias=layers[1].b, act="relu", out_dtype=adt)
         return ops.gemm(h, layers[2].W(P), bias=layers[2].b, act=final_act, out_dtype=F32)
 
-    def mask_decoder(self, pix: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, sparse: torch.Tensor, debug: dict | None = None):
+    def mask_decoder(self, pix: torch.Tensor, s0: torch.Tensor, s1: torch.Tensor, sparse: torch.Tensor, debug: dict | None = None, zero_dense: bool = False):
         """PromptEncoder dense part + MaskDecoder.predict_masks (sam/mask_decoder.py:167-245), TwoWayTransformer
         (sam/transformer.py:63-115, 160-193). pix fp32 [B*HW, C] image embedding (one row block per object), s0/s1 the
         high-res maps of the ONE image shared by the B objects, sparse fp32 [B, Ns, C].
@@ -369,10 +369,11 @@ class Sam2Engine:
         B = sparse.shape[0]
         if self.fused_decoder and debug is None and s0.dtype == F32 and pix.shape[0] == B * HW:
             tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).contiguous()
-            return ops.mask_decoder_fused(self.fused_w, pix, self.dense_pe, self.no_mask_vec, s0, s1, tokens, cfg.feat_size, exact=self.fused_exact)
+            no_mask = torch.zeros_like(self.no_mask_vec) if zero_dense else self.no_mask_vec   # zero dense embedding: the padded objects of model_forward
+            return ops.mask_decoder_fused(self.fused_w, pix, self.dense_pe, no_mask, s0, s1, tokens, cfg.feat_size, exact=self.fused_exact)
         tokens = torch.cat([self.out_tokens[None].expand(B, -1, -1), sparse], dim=1).reshape(-1, C).contiguous()
         Nt = tokens.shape[0] // B
-        keys = ops.add(pix, self.no_mask_embed)                       # src = image_embeddings + dense (no_mask_embed)
+        keys = pix.clone() if zero_dense else ops.add(pix, self.no_mask_embed)    # src = image_embeddings + dense (no_mask_embed)
         queries = tokens
         k_pe = v_k = None
         for i, L in enumerate(self.dec_layers):
@@ -587,7 +588,7 @@ class Sam2Engine:
 
     # ------------------------------------------------------------------------------------------------ framewise branch
     @torch.no_grad()
-    def run_framewise(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False):
+    def run_framewise(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False, zero_dense: bool = False):
         """SAM2 part of VideoGLaMM_SAM2.inference_framewise (VideoGLaMM.py:598-768 with get_visual_embs_sam2 :205-241): every frame is
         decoded independently — image_embed = top-level feature + no_mem_embed, prompt = the text token only (no padding points),
         multimask_output=False with the stability fallback (mask_decoder.py:247-295), repeat_image over the objects,
@@ -604,7 +605,7 @@ class Sam2Engine:
             for i in range(nb):
                 f = {k: v.view(nb, -1, v.shape[-1])[i] for k, v in fb.items()}
                 pix = ops.add(f["top"], self.no_mem_embed, rows=B * self.HW)
-                masks, iou, _, _ = self.mask_decoder(pix, f["s0"], f["s1"], sparse)
+                masks, iou, _, _ = self.mask_decoder(pix, f["s0"], f["s1"], sparse, zero_dense=zero_dense)
                 sel = ops.multimask_select(masks, iou.contiguous())
                 low = masks[torch.arange(B, device=self.dev), sel].reshape(B, side, side).contiguous()
                 outs.append(ops.bilinear(low, Hv, Wv, mode=_OUT_MODE[binary]))
