@@ -163,7 +163,7 @@ def run_engine(args):
             P.gather_results([(rank * len(results) + j, ids, pm) for j, (ids, pm) in enumerate(results)], device=dev, unpack=False)
 
     from videoglamm_b200.pipeline import ClipPipeline
-    pipe = ClipPipeline(model)
+    pipe = ClipPipeline(model, decode_batch=CPS)        # C3: the 4 clips of a step decode together (one weight pass per token for all of them)
 
     def run_clips(inps, steps):
         """`steps` batches of CPS independent clips per GPU. Sequential mode calls model.inference clip by clip; pipelined mode (default) overlaps

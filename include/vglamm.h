@@ -104,11 +104,12 @@ typedef struct VgAttention {
   int force_legacy;                             /* 1: skip the tcgen05 kernel and use the mma.sync kernel (tests / A-B timing) */
   const int* nk_dev;                            /* optional (Nq == 1 only): the number of keys is read from this DEVICE int at run time
                                                    (Nk is then only an upper bound) so a captured decode step can be replayed */
-  float fused_rope_theta;                       /* > 0 (Nq == 1, B == 1, D <= 128 only): the decode step's RoPE + KV-cache append is fused: q points
+  float fused_rope_theta;                       /* > 0 (Nq == 1, D <= 128 only; batch entry b uses the packed row at q + b*q_bs and its own caches at k/v + b*k_bs): the decode step's RoPE + KV-cache append is fused: q points
                                                    at the UN-rotated packed row [q | k_new | v_new] (3*H*D bf16) of the newest token at position
                                                    Nk-1; the kernel rotates q on the fly, rotates k_new, writes k_new / v_new into row Nk-1 of the
                                                    k / v cache views (which must be writable) and attends over keys [0, Nk). Replaces
                                                    vg_rope_kv_append + vg_attention (one launch less per layer and token). */
+  int nk_per_batch;                             /* 1: nk_dev is an array of B key counts, one per batch entry (batched decode of sequences of different lengths) */
 } VgAttention;
 int vg_attention(const VgAttention* a, void* stream);
 

@@ -43,6 +43,12 @@ def test_hiera_l_full_depth_one_frame_and_heads():
     s0, s1 = tok(fpn[0]).cuda().bfloat16().contiguous(), tok(fpn[1]).cuda().bfloat16().contiguous()
     eh = eng.forward_sam_heads(pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous(), s0, s1, text.cuda(), 2)
     assert rel(eh["low_res_masks"], oh["low_res_masks"][:, 0]) < 2e-2
+    # the fused mask-decoder kernel at full size (HW = 4096 -> 128 row blocks per object, 2 objects) on fp32 high-res maps: north_star's 1e-3 bar
+    ef = eng.forward_sam_heads(pix.permute(0, 2, 3, 1).reshape(-1, 256).cuda().contiguous(), tok(fpn[0]).cuda().contiguous(), tok(fpn[1]).cuda().contiguous(),
+                               text.cuda(), 2)
+    e_masks, e_ptr = rel(ef["low_res_masks"], oh["low_res_masks"][:, 0]), rel(ef["obj_ptr"], oh["obj_ptr"])
+    print(f"PARITY full-size fused mask decoder (HW=4096, B=2): low_res_masks {e_masks:.2e}, obj_ptr {e_ptr:.2e}")
+    assert e_masks < 1e-3 and e_ptr < 1e-3
     emf = eng.encode_memory(tok(fpn[2]).cuda().contiguous(), oh["low_res_masks"][:, 0].cuda().contiguous(), binarize=False)
     assert rel(emf, mf.permute(0, 2, 3, 1).reshape(2, -1, 64)) < 1.5e-2
     Nk = 3 * 4096 + 12
@@ -72,4 +78,25 @@ def test_full_width_towers_and_phi3_reduced_depth():
         ids_ref, emb_ref, _ = M.generate(sd, ocfg, ids, images, ctx, 4, forced={1: 32011})
     out_ids, emb = eng.generate(ids[None].cuda(), images.cuda(), ctx.cuda(), 4, forced={1: 32011})
     assert torch.equal(out_ids[0].cpu(), ids_ref)          # greedy ids bit-exact at full width (855-token sequence, KV-cached vs no-cache)
+    assert rel(emb, emb_ref) < 2e-2
+
+
+def test_phi3_prefill_and_decode_beyond_the_sliding_window():
+    """BASELINE.json configs[3]/[4] (C4 / C5): T_enc = 16 -> 3,328 visual tokens, L = 3,352 > sliding_window + 1: the band cuts in the prefill
+    (tcgen05 attention with band-edge masking) and in every decode step (single-query kernel over the last 2,048 keys). Full Phi-3 width,
+    one layer (the CPU oracle re-forwards the whole sequence per token); greedy ids bit-exact, [SEG] embedding close."""
+    kw = dict(clip=dict(layers=2), iv2=dict(depth=2), phi=dict(layers=1, sliding_window=2047))
+    ocfg, ecfg = M.make_cfg(**kw, seg_token_idx=32011), make_lmm_config(**kw, seg_token_idx=32011)
+    sd = Wt.make_lmm_state_dict(ocfg, 77)
+    sd = {k: v.bfloat16().float() if v.dim() >= 2 else v for k, v in sd.items()}
+    eng = LmmEngine(sd, ecfg)
+    torch.manual_seed(3)
+    T = 16
+    images, ctx = torch.randn(T, 3, 224, 224), torch.randn(T, 3, 336, 336)
+    ids = torch.cat([torch.randint(3, 32000, (9,)), torch.full((T,), -200), torch.randint(3, 32000, (15,))])
+    with torch.no_grad():
+        ids_ref, emb_ref, hidden = M.generate(sd, ocfg, ids, images, ctx, 3, forced={1: 32011})
+    assert hidden.shape[0] > 2048 + 1300
+    out_ids, emb = eng.generate(ids[None].cuda(), images.cuda(), ctx.cuda(), 3, forced={1: 32011})
+    assert torch.equal(out_ids[0].cpu(), ids_ref)
     assert rel(emb, emb_ref) < 2e-2

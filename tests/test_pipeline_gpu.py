@@ -83,3 +83,42 @@ def test_pipeline_cold_start_with_heterogeneous_shapes():
                 assert np.array_equal(segs_a[0][t][o], seg_b[t][o])
     st = model.sam.g_video.stats
     assert st["captures"] >= 2 and st["evictions"] >= 1 and st["replays"] >= 1, st
+
+
+def test_batched_decode_equals_per_clip_generation():
+    """LmmEngine.generate_batch (S sequences of different prompt lengths decode together: skinny GEMMs with M = S, per-sequence KV-cache slot, key count
+    and RoPE position in the single-query attention) returns exactly what S calls of generate return; EOS stops one sequence while the others go on.
+    Then the same through ClipPipeline(decode_batch=3)."""
+    from oracle import lmm as M, sam2 as O, weights as Wt
+    from videoglamm_b200.config import Sam2Config, make_lmm_config
+    from videoglamm_b200.model import VideoGLaMMForCausalLM
+    from videoglamm_b200.pipeline import ClipPipeline
+    seg = 300
+    ocfg, scfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=seg), O.Sam2Cfg(**O.TINY)
+    sd = Wt.make_videoglamm_state_dict(ocfg, scfg, seed=7)
+    model = VideoGLaMMForCausalLM(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=seg), Sam2Config(**O.TINY))
+    reqs, clips = [], []
+    for i, (T, nq) in enumerate([(4, 7), (8, 3), (4, 12), (4, 5), (8, 9)]):
+        g = torch.Generator().manual_seed(50 + i)
+        images, ctx = torch.randn(T, 3, 56, 56, generator=g), torch.randn(T, 3, 56, 56, generator=g)
+        ids = torch.cat([torch.randint(3, 290, (5,), generator=g), torch.full((T,), -200), torch.randint(3, 290, (nq,), generator=g)])[None]
+        reqs.append((ids.cuda(), images.cuda(), ctx.cuda()))
+        clips.append(dict(images=images, context_images=ctx, images_for_sam=torch.randn(2, 3, 256, 256, generator=g), input_ids=ids, original_size=(32, 48)))
+    forced = {2: seg, 9: seg}
+    single = [model.lmm.generate(*r, 14, forced=forced) for r in reqs]
+    eos = (int(single[1][0][0, -6]),)                                     # a token that sequence 1 emits mid-way becomes an EOS id
+    single = [model.lmm.generate(*r, 14, eos_ids=eos, forced=forced) for r in reqs]
+    assert len({o.shape[1] - r[0].shape[1] for (o, _), r in zip(single, reqs)}) > 1   # the sequences really stop at different lengths
+    for rep in range(3):                                                  # eager first sight, capture, replay
+        batch = model.lmm.generate_batch(reqs, 14, eos_ids=eos, forced=forced)
+        for (ia, ea), (ib, eb) in zip(single, batch):
+            assert torch.equal(ia, ib) and torch.equal(ea, eb)
+    seq = [model.inference([c["images"]], [c["context_images"]], [c["images_for_sam"]], c["input_ids"].cuda(), None, [c["original_size"]],
+                           max_new_tokens=14, use_sam2_video_branch=True, forced_tokens=forced) for c in clips]
+    seq = [(ids.cpu().clone(), {t: {o: m.copy() for o, m in fr.items()} for t, fr in segs[0].items()}) for ids, segs in seq]
+    out = ClipPipeline(model, decode_batch=3).run(clips, 14, forced_tokens=forced)
+    for (ids_a, seg_a), (ids_b, seg_b, _) in zip(seq, out):
+        assert torch.equal(ids_a, ids_b.cpu())
+        for t in seg_a:
+            for o in seg_a[t]:
+                assert np.array_equal(seg_a[t][o], seg_b[t][o])

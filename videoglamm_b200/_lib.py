@@ -64,7 +64,7 @@ class VgAttention(C.Structure):
         ("k_win", C.c_int), ("k_gridw", C.c_int), ("k_nwx", C.c_int), ("k_nwy", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("ws_has_counters", C.c_int), ("force_legacy", C.c_int),
         ("nk_dev", C.c_void_p),
-        ("fused_rope_theta", C.c_float),
+        ("fused_rope_theta", C.c_float), ("nk_per_batch", C.c_int),
     ]
 
 

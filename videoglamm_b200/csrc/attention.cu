@@ -24,6 +24,7 @@ struct AttnParams {
   float* ws;                         // split-K partials for single-query attention
   int nsplit;
   const int* nk_dev;                 // optional: number of keys read from device memory (graph-replayable decode)
+  int nk_per_batch;                  // nk_dev holds one key count per batch entry (batched decode: every sequence has its own length)
   int* counters;                     // optional [B*H] zeroed ints: the last split block of a (b,h) merges in-kernel (no merge launch)
   float rope_theta;                  // > 0: decode step with fused RoPE + KV append (q = packed un-rotated [q|k|v] row of position Nk-1)
 };
@@ -408,7 +409,7 @@ template <int DMAX>
 __global__ void __launch_bounds__(128) attn_decode_kernel(AttnParams p) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
-  if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
+  if (p.nk_dev != nullptr) p.Nk = p.nk_dev[p.nk_per_batch ? blockIdx.y : 0];
   constexpr int NW = 4, PPL = DMAX / 64;  // warps per block; bf16x2 feature pairs per lane in the PV phase
   __shared__ float s_q[DMAX];
   __shared__ float s_p[NW][32];
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(128) attn_decode2_kernel(AttnParams p) {
   constexpr int DMAX = 128, LDS = DMAX + 8;  // padded row (bf16 elements)
   pdl_launch_dependents();
   pdl_wait();  // q / the newest cache row come from the preceding kernels; nk_dev is advanced by the previous decode step
-  if (p.nk_dev != nullptr) p.Nk = *p.nk_dev;
+  if (p.nk_dev != nullptr) p.Nk = p.nk_dev[p.nk_per_batch ? blockIdx.y : 0];
   __shared__ __align__(16) __nv_bfloat16 s_k[DEC2_KEYS * LDS];
   __shared__ __align__(16) __nv_bfloat16 s_v[DEC2_KEYS * LDS];
   __shared__ __align__(16) float s_q[DMAX];
@@ -845,12 +846,13 @@ extern "C" int vg_attention(const VgAttention* a, void* stream) {
   p.q_win = a->q_win; p.q_gridw = a->q_gridw; p.q_nwx = a->q_nwx; p.q_nwy = a->q_nwy;
   p.k_win = a->k_win; p.k_gridw = a->k_gridw; p.k_nwx = a->k_nwx; p.k_nwy = a->k_nwy;
   p.ws = nullptr; p.nsplit = 1; p.nk_dev = static_cast<const int*>(a->nk_dev); p.counters = nullptr; p.rope_theta = 0.f;
+  p.nk_per_batch = a->nk_per_batch;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a->nk_dev != nullptr && a->Nq != 1) return set_error(VG_EINVAL, "vg_attention: nk_dev is only supported for single-query attention");
   if (a->Nq == 1 && a->q_win == 0 && a->k_win == 0 && (a->Nk >= 256 || a->nk_dev != nullptr)) {  // decode: causal is a no-op for the newest query
     const int dmax = a->D <= 128 ? 128 : 256;
     if (a->fused_rope_theta > 0.f) {
-      if (dmax != 128 || a->B != 1 || a->q_hs != a->D || (a->D % 2)) return set_error(VG_EINVAL, "vg_attention: fused RoPE/append needs B == 1, D <= 128, packed q row");
+      if (dmax != 128 || a->q_hs != a->D || (a->D % 2)) return set_error(VG_EINVAL, "vg_attention: fused RoPE/append needs D <= 128 and packed [q|k|v] rows");
       p.rope_theta = a->fused_rope_theta;
     }
     int nsplit = 1;

@@ -198,6 +198,9 @@ class LmmEngine:
         self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
         self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
+        self.g_decode_batch = GraphedStage("decode_batch")
+        self.kv_slots = None
+        self._batch_state = {}
         self.dec_tok = torch.zeros(1, device=self.dev, dtype=torch.int64)
         self.dec_pos = torch.zeros(1, device=self.dev, dtype=torch.int32)
         self.dec_nk = torch.zeros(1, device=self.dev, dtype=torch.int32)
@@ -243,17 +246,45 @@ class LmmEngine:
         return self.image_tokens(images) if context_images is None else self.visual_tokens(images, context_images)
 
     # ------------------------------------------------------------------------------------------------ Phi-3
-    def _alloc_cache(self, max_len: int):
+    def _alloc_cache(self, max_len: int, slots: int = 1):
+        """Per layer one [slots, max_len, 3*hidden] buffer (slot = one sequence of a decode batch); self.kv[l] is slot 0 (single-sequence paths)."""
         ph = self.cfg.phi
-        if self.kv is None or self.kv[0].shape[0] < max_len:
+        if self.kv is None or self.kv[0].shape[0] < max_len or self.kv_slots[0].shape[0] < slots:
             n = max(max_len, ph.max_len)                 # allocate once at the model's context length: graphs keep these pointers
-            self.kv = [torch.zeros((n, 3 * ph.hidden), device=self.dev, dtype=F32 if self.P else BF) for _ in range(ph.layers)]
-            self.g_prefill.entries.clear()
-            self.g_decode.entries.clear()
+            ns = max(slots, 1 if self.kv is None else self.kv_slots[0].shape[0])
+            self.kv_slots = [torch.zeros((ns, n, 3 * ph.hidden), device=self.dev, dtype=F32 if self.P else BF) for _ in range(ph.layers)]
+            self.kv = [t[0] for t in self.kv_slots]
+            for g in (self.g_prefill, self.g_decode, self.g_decode_batch):
+                g.clear()
 
-    def _prefill_last(self, x: torch.Tensor) -> torch.Tensor:
+    def _prefill_last(self, x: torch.Tensor, slot: int = 0) -> torch.Tensor:
         """Prefill rows [0, n); returns the final-norm hidden state of the LAST row only ([1, hidden] fp32) — all that decoding needs."""
-        return self._llm(x, 0, last_only=True)
+        return self._llm(x, 0, last_only=True, slot=slot)
+
+    def _decode_step_batch(self, S: int, kv_bound: int):
+        """One KV-cached decode step for S sequences at once (C3: the clips queued on a GPU decode together): every weight matrix is streamed ONCE for
+        the S tokens (skinny GEMMs with M = S), each sequence attends over its own cache slot with its own key count (dec_nk[s]), RoPE and the cache
+        append fused into the attention kernel. Device-side state per sequence: st["tok"], st["pos"], st["nk"]."""
+        ph = self.cfg.phi
+        H, hd, D = ph.heads, ph.head_dim, ph.hidden
+        st = self._batch_state[S]
+        x = ops.embedding(self.embed, st["tok"])                                             # [S, hidden] fp32
+        for l, L in enumerate(self.layers):
+            cache = self.kv_slots[l]
+            ops.gemm(x, L["qkv"].w, out=st["qkv"], a_rms_eps=ph.eps)
+            q = st["qkv"][:, :D].unflatten(1, (H, hd))[:, None]                              # [S, 1, H, hd], batch stride 3*hidden
+            k = cache[:S, :kv_bound, D:2 * D].unflatten(2, (H, hd))
+            v = cache[:S, :kv_bound, 2 * D:].unflatten(2, (H, hd))
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=st["nk"], decode_ws=st["ws"],
+                              fused_rope_theta=ph.rope_theta)
+            x = ops.gemm(o.view(S, D), L["o"].w, resid=x, out=x)
+            h = ops.gemm(x, L["gu"].w, glu=True, act="silu", a_rms_eps=ph.eps)
+            x = ops.gemm(h, L["down"].w, resid=x, out=x)
+        nxt = self._logits_argmax(x)
+        st["tok"].copy_(nxt)
+        st["pos"].add_(1)
+        st["nk"].add_(1)
+        return x, nxt
 
     def _decode_step(self, kv_bound: int):
         """One KV-cached decode step whose launch sequence does not depend on the position: token id, position and key count live in
@@ -287,7 +318,7 @@ class LmmEngine:
         h = ops.norm(x_resid, self.ones, eps=self.cfg.phi.eps, rms=True, out_dtype=F32 if P else BF)
         return ops.gemm(h, self.lm_head.W(P), out_dtype=F32)
 
-    def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False, raw: bool = False) -> torch.Tensor:
+    def _llm(self, x: torch.Tensor, pos0: int, last_only: bool = False, raw: bool = False, slot: int = 0) -> torch.Tensor:
         """HF Phi3Model.forward (called at language_model/phi3.py:72-81) on rows [pos0, pos0+n) given a cache holding rows [0,pos0).
         x fp32 [n, hidden] (modified in place as the residual stream) -> final-norm hidden fp32 [n, hidden]."""
         ph = self.cfg.phi
@@ -297,7 +328,7 @@ class LmmEngine:
         P = self.P
         adt = F32 if P else BF
         for l, L in enumerate(self.layers):
-            cache = self.kv[l]
+            cache = self.kv_slots[l][slot]
             h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=adt)
             rows = cache[pos0:end]
             ops.gemm(h, L["qkv"].W(P), out=rows)
@@ -334,6 +365,67 @@ class LmmEngine:
         text = torch.cat([ids_host[:start], ids_host[end + 1:]]).to(self.dev)
         emb = self._embed(text) if text.numel() else torch.zeros((0, self.embed.shape[1]), device=self.dev)
         return torch.cat([emb[:start], vis, emb[start:]], 0).contiguous()
+
+    @torch.no_grad()
+    def generate_batch(self, requests: list[tuple], max_new_tokens: int, eos_ids=(), forced: dict | None = None) -> list[tuple]:
+        """`generate` for S = len(requests) <= 8 independent clips at once: requests = [(input_ids, images, context_images)]. Towers and prefill run
+        per clip (tensor-bound, each fills the GPU alone); the HBM-bound decode loop runs ONCE for all S sequences (`_decode_step_batch`), with one
+        host synchronisation per step for the whole batch. Results are bit-identical to S calls of `generate`: [(output_ids, pred_embeddings)]."""
+        cfg, S = self.cfg, len(requests)
+        assert 1 <= S <= 8 and not self.P
+        if S == 1:
+            return [self.generate(*requests[0], max_new_tokens, eos_ids=eos_ids, forced=forced)]
+        ph = cfg.phi
+        xs = []
+        for ids, images, ctx in requests:
+            if ctx is None:
+                vis = self.g_vis((tuple(images.shape), None), self.image_tokens, image=images)
+            else:
+                vis = self.g_vis((tuple(images.shape), tuple(ctx.shape)), self.visual_tokens, images=images, context_images=ctx)
+            xs.append(self.embed_prompt(ids, vis))
+        L0 = [x.shape[0] for x in xs]
+        self._alloc_cache(max(L0) + max_new_tokens + 1, slots=S)
+        x_last = torch.cat([self.g_prefill((x.shape[0], s), lambda x, s=s: self._prefill_last(x, slot=s), x=x).clone() for s, x in enumerate(xs)], 0)   # [S, hidden]
+        if S not in self._batch_state:
+            self._batch_state[S] = dict(tok=torch.zeros(S, device=self.dev, dtype=torch.int64), pos=torch.zeros(S, device=self.dev, dtype=torch.int32),
+                                        nk=torch.zeros(S, device=self.dev, dtype=torch.int32), qkv=torch.zeros((S, 3 * ph.hidden), device=self.dev, dtype=BF),
+                                        ws=ops.decode_workspace(S, ph.heads, ph.head_dim, self.dev))
+        st = self._batch_state[S]
+        kv_bound = min(self.kv[0].shape[0], (max(L0) + max_new_tokens + 511) // 512 * 512)
+        new_ids = [[] for _ in range(S)]
+        seg_hidden = [[] for _ in range(S)]
+        done = [False] * S
+        nxt_dev = self._logits_argmax(x_last)
+        for step in range(max_new_tokens):
+            nxt = nxt_dev.tolist()                              # ONE host sync per step for the whole batch
+            if forced and step in forced:
+                nxt = [forced[step]] * S
+            for s in range(S):
+                if done[s]:
+                    continue
+                new_ids[s].append(nxt[s])
+                if nxt[s] == cfg.seg_token_idx:
+                    seg_hidden[s].append(ops.norm(x_last[s:s + 1], self.final_norm, eps=ph.eps, rms=True, out_dtype=F32))
+                if nxt[s] in eos_ids:
+                    done[s] = True
+            if all(done) or step == max_new_tokens - 1:
+                break
+            if step == 0:
+                st["pos"].copy_(torch.tensor(L0, dtype=torch.int32), non_blocking=True)
+                st["nk"].copy_(torch.tensor([l + 1 for l in L0], dtype=torch.int32), non_blocking=True)
+            if step == 0 or (forced and step in forced):
+                st["tok"].copy_(torch.tensor(nxt, dtype=torch.int64), non_blocking=True)
+            x_last, nxt_dev = self.g_decode_batch((S, kv_bound), lambda: self._decode_step_batch(S, kv_bound), mutable_state=(st["tok"], st["pos"], st["nk"]))
+        out = []
+        for s, (ids, _, _) in enumerate(requests):
+            out_ids = torch.cat([ids.reshape(1, -1), torch.tensor([new_ids[s]], device=ids.device, dtype=torch.int64)], dim=1)
+            if seg_hidden[s]:
+                hs = ops.cast(torch.cat(seg_hidden[s], 0), BF)
+                emb = ops.gemm(ops.gemm(hs, self.fc[0].w, bias=self.fc[0].b, act="relu"), self.fc[1].w, bias=self.fc[1].b, out_dtype=F32)
+            else:
+                emb = torch.zeros((0, cfg.out_dim), device=self.dev)
+            out.append((out_ids, emb))
+        return out
 
     @torch.no_grad()
     def generate(self, input_ids: torch.Tensor, images: torch.Tensor, context_images: torch.Tensor, max_new_tokens: int, eos_ids=(),

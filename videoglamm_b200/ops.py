@@ -214,10 +214,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, scale: float
         L.check(L.lib().vg_attention_f32(C.byref(a), _stream()), "vg_attention_f32")
         return out
     if nk_dev is not None:
-        assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1
+        assert nk_dev.dtype == torch.int32 and nk_dev.is_cuda and Nq == 1 and nk_dev.numel() in (1, B)
         a.nk_dev = nk_dev.data_ptr()
+        a.nk_per_batch = int(nk_dev.numel() == B and B > 1)
     if fused_rope_theta:
-        assert Nq == 1 and B == 1 and q.stride(2) == D, "fused RoPE/append: q must be the packed [q|k|v] row of the newest token"
+        assert Nq == 1 and q.stride(2) == D, "fused RoPE/append: q must be the packed [q|k|v] row of the newest token (one row per batch entry)"
         a.fused_rope_theta = float(fused_rope_theta)
     if q_win is None and not causal and Nq > 1 and Nk >= 2048 and B * H * ((Nq + 63) // 64) < 148:
         # few query tiles, many keys (SAM2 memory attention): split-K scratch for up to 8 partials

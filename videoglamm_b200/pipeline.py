@@ -12,10 +12,13 @@ import torch
 
 
 class ClipPipeline:
-    def __init__(self, model, depth: int = 2):
+    def __init__(self, model, depth: int = 2, decode_batch: int = 1):
+        """decode_batch > 1: the LMM stage takes that many consecutive clips at a time and runs their HBM-bound decode loops as ONE batched loop
+        (LmmEngine.generate_batch: every weight matrix is streamed once per step for all of them) — BASELINE.json configs[2], 4 clips per GPU."""
         self.model = model
         model._ensure_engines()
-        self.depth = depth
+        self.depth = max(depth, decode_batch)
+        self.decode_batch = max(1, min(int(decode_batch), 8))
         self.s_lmm = torch.cuda.Stream(device=model.device)
         self.s_sam = torch.cuda.Stream(device=model.device)
         self.s_copy = torch.cuda.Stream(device=model.device)   # host -> device prefetch of the SAM2 frames (100 MB per clip at 1024 px)
@@ -35,24 +38,29 @@ class ClipPipeline:
             try:
                 torch.cuda.set_device(dev)
                 with torch.cuda.stream(self.s_lmm):
-                    for i, c in enumerate(clips):
-                        # the SAM2 frames of this clip are not needed before its LMM stage is over: copy them on their own stream now, so
-                        # the transfer runs under this clip's LMM kernels instead of in front of its SAM2 stage
-                        sam_dev, ev_copy = c["images_for_sam"], None
-                        if not sam_dev.is_cuda:
-                            with torch.cuda.stream(self.s_copy):
-                                sam_dev = sam_dev.to(dev, non_blocking=True)
-                                ev_copy = torch.cuda.Event()
-                                ev_copy.record(self.s_copy)
-                        ids = c["input_ids"].to(dev, non_blocking=True)
-                        out_ids, emb = m.lmm.generate(ids, c["images"].to(dev, torch.float32, non_blocking=True),
-                                                      c["context_images"].to(dev, torch.float32, non_blocking=True), max_new_tokens,
-                                                      eos_ids=m._eos_ids(), forced=forced_tokens)
-                        emb = emb.clone()
-                        emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
-                        ev = torch.cuda.Event()
-                        ev.record(self.s_lmm)
-                        q.put((i, out_ids, emb, ev, sam_dev, ev_copy))
+                    S = self.decode_batch
+                    for i0 in range(0, len(clips), S):
+                        group, reqs, sams = clips[i0:i0 + S], [], []
+                        for c in group:
+                            # the SAM2 frames of a clip are not needed before its LMM stage is over: copy them on their own stream now, so
+                            # the transfer runs under the LMM kernels instead of in front of the SAM2 stage
+                            sam_dev, ev_copy = c["images_for_sam"], None
+                            if not sam_dev.is_cuda:
+                                with torch.cuda.stream(self.s_copy):
+                                    sam_dev = sam_dev.to(dev, non_blocking=True)
+                                    ev_copy = torch.cuda.Event()
+                                    ev_copy.record(self.s_copy)
+                            sams.append((sam_dev, ev_copy))
+                            ctx = c.get("context_images")
+                            reqs.append((c["input_ids"].to(dev, non_blocking=True), c["images"].to(dev, torch.float32, non_blocking=True),
+                                         None if ctx is None else ctx.to(dev, torch.float32, non_blocking=True)))
+                        outs = m.lmm.generate_batch(reqs, max_new_tokens, eos_ids=m._eos_ids(), forced=forced_tokens)
+                        for j, ((out_ids, emb), (sam_dev, ev_copy)) in enumerate(zip(outs, sams)):
+                            emb = emb.clone()
+                            emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
+                            ev = torch.cuda.Event()
+                            ev.record(self.s_lmm)
+                            q.put((i0 + j, out_ids, emb, ev, sam_dev, ev_copy))
             except Exception as e:  # surface, don't swallow (the reference's eval loops silently skip failures)
                 errors.append(e)
             finally:
