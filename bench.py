@@ -116,6 +116,13 @@ def synth_inputs(seed: int, pinned: bool):
     return images, context, sam, ids
 
 
+def synth_raw_frames(seed: int):
+    """The raw uint8 video frames [T_sam, H, W, 3] at the original resolution (uniform [0,255]) for the end-to-end arm: the engine
+    pre-processes them on the GPU (PIL-exact resize, normalise, squash), so H*W*3 bytes per frame cross PCIe instead of 12.6 MB of fp32."""
+    g = torch.Generator().manual_seed(91234 + seed)
+    return torch.randint(0, 256, (T_SAM, VIDEO_HW[0], VIDEO_HW[1], 3), generator=g, dtype=torch.uint8).pin_memory()
+
+
 def run_engine(args):
     import torch.distributed as dist
     from videoglamm_b200 import build, ops, parallel as P
@@ -148,6 +155,7 @@ def run_engine(args):
     n_obj, CPS = len(forced), CFG["clips"]
     host_clips = [synth_inputs(rank * CPS + j, pinned=True) for j in range(CPS)]       # CPS different clips per GPU and step
     res_clips = [[t.to(dev) for t in h] for h in host_clips]
+    raw_clips = [[h[0], h[1], synth_raw_frames(rank * CPS + j), h[3]] for j, h in enumerate(host_clips)]   # e2e arm: raw uint8 SAM2 frames
     host, resident = host_clips[0], res_clips[0]
     L = host[3].shape[1] - T_ENC + 208 * T_ENC
 
@@ -201,7 +209,8 @@ def run_engine(args):
     for _ in range(max(args.warmup, 3)):
         step(resident)
     run_clips(res_clips, 2)                      # pipeline warm-up (per-thread stream state, graph pools)
-    run_clips(host_clips, 2)                     # ... and of the host-input path (side-stream allocator pools, pinned result buffers)
+    run_clips(host_clips, 2)                     # ... and of the host-input paths (side-stream allocator pools, pinned result buffers)
+    run_clips(raw_clips, 2)
     torch.cuda.synchronize()
     lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat0.record()
@@ -215,7 +224,8 @@ def run_engine(args):
     ops.launch_count_reset()
     ms = timed(res_clips, args.steps)
     launches = ops.launch_count()
-    ms_e2e = timed(host_clips, args.steps)      # same call, HOST pinned inputs: H2D of every input + D2H of the masks inside the region
+    ms_e2e = timed(raw_clips, args.steps)       # same call, HOST pinned inputs incl. the RAW uint8 SAM2 frames (GPU pre-processing): H2D + D2H inside the region
+    ms_e2e_fp32 = timed(host_clips, args.steps)  # ... and with the CPU-preprocessed fp32 SAM2 tensors the reference uploads (100 MB per 8-frame clip)
     clocks = sampler.stop() if rank == 0 else {}
     # dominant kernel = the tcgen05 GEMM: per-launch CUDA-event timing on one extra (untimed) step
     from videoglamm_b200 import graphs
@@ -237,7 +247,8 @@ def run_engine(args):
         tp, tall = prof["tensor_big"], prof["tensor"]
         ach = tp["flops"] / (tp["ms"] * 1e-3) / 1e12 if tp["ms"] > 0 else 0.0
         ach_all = tall["flops"] / (tall["ms"] * 1e-3) / 1e12 if tall["ms"] > 0 else 0.0
-        h2d = CPS * sum(t.numel() * t.element_size() for t in host)
+        h2d = CPS * sum(t.numel() * t.element_size() for t in raw_clips[0])
+        h2d_fp32 = CPS * sum(t.numel() * t.element_size() for t in host)
         d2h = CPS * (T_SAM * n_obj * ((VIDEO_HW[0] * VIDEO_HW[1] + 7) // 8) + 8)     # bit-packed masks + the per-token id reads of the decode loop
         ms_clip = ms / (args.steps * CPS)
         line = {
@@ -251,7 +262,11 @@ def run_engine(args):
                        "algorithmic_tflop_per_clip": clip_flops(L) / 1e12,
                        "schedule": "sequential clips" if args.sequential else "2-stage pipeline over clips (LMM of clip i+1 || SAM2 of clip i, two streams)",
                        "latency_ms_single_clip": latency_ms},
-            "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "inputs": "pinned host tensors: IV2 / CLIP frames fp32 (CPU-preprocessed as the reference does), SAM2 frames RAW uint8 [T,H,W,3] pre-processed on "
+                              "the GPU (vg_resize_u8_pil + vg_sam_normalize_squash), prompt ids; outputs: bit-packed masks expanded to bool arrays on the host",
+                    "with_fp32_sam_inputs": {"value": n_clips / (ms_e2e_fp32 * 1e-3), "h2d_bytes_per_step": h2d_fp32,
+                                             "note": "the reference's input format: SAM2 frames pre-processed on the CPU, uploaded as fp32 [T,3,1024,1024]"}},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip with >= 1 GFLOP: "
                          f"{tp['n']} launches carrying {tp['flops'] / max(tall['flops'], 1):.1%} of the GEMM FLOPs)", "achieved": ach, "peak": tf_peak,

@@ -266,6 +266,17 @@ int vg_mask_decoder(const VgMaskDecoder* d, void* stream);
 /* diagnostic: `dev_buf` = device buffer of 64 uint64 that following launches fill with the %globaltimer of block (0,0) at kernel start, after each
  * grid barrier and at the end ([63] = number of barriers); NULL disables. */
 void vg_mask_decoder_set_timeline(void* dev_buf);
+/* ------------------------------------------------------------------------------------------------ GPU pre-processing of the SAM2 frames
+ * vg_resize_u8_pil: PIL.Image.resize(BILINEAR) on uint8 HWC frames, BIT-EXACT (what torchvision's resize(to_pil_image(x)) does inside
+ * ResizeLongestSide.apply_image, VideoGLaMM/model/segment_anything/utils/transforms.py:26-36): horizontal pass src [n][h][w][c] -> tmp [n][h][ow][c],
+ * vertical pass -> dst [n][oh][ow][c], both with PIL's fixed-point coefficients. kh / kv: int32 [ow][ksize_h] / [oh][ksize_v] coefficients (22 fractional
+ * bits), bh / bv: int32 [ow][2] / [oh][2] = (first input index, tap count) — PIL's precompute_coeffs + normalize_coeffs_8bpc, evaluated by the caller
+ * (videoglamm_b200/preprocess.py:pil_bilinear_coeffs). All pointers device memory.
+ * vg_sam_normalize_squash: src uint8 [n][h][w][3] -> dst fp32 [n][3][S][S] = F.interpolate((x - mean) / std, (S, S), mode="bilinear") —
+ * sam_preprocess(model_type="sam2"), VideoGLaMM/utils/sam_transforms.py:54-58. mean3 / std3 are HOST pointers to 3 floats. */
+int vg_resize_u8_pil(const unsigned char* src, unsigned char* tmp, unsigned char* dst, int n, int h, int w, int c, int oh, int ow, const int* kh, const int* bh,
+                     int ksize_h, const int* kv, const int* bv, int ksize_v, void* stream);
+int vg_sam_normalize_squash(const unsigned char* src, float* dst, int n, int h, int w, int S, const float* mean3, const float* std3, void* stream);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

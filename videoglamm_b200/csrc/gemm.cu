@@ -582,7 +582,7 @@ static void launch_gemv(const VgGemm* g, const GemmParams& p, cudaStream_t s) {
   // few columns and long rows: split K over 4 warps so enough bytes are in flight to cover HBM latency
   const bool split = n_out < 6144 && g->K >= 2048;
   const unsigned blocks = split ? (static_cast<unsigned>(n_out) * 4 + 7) / 8 : (static_cast<unsigned>(n_out) + 7) / 8;
-  const int u = MR > 2 ? 2 : gemv_variant();
+  const int u = MR > 4 ? 2 : gemv_variant();   // 16-byte weight loads in flight per lane (registers: 4 U, x2 with GLU, next to 3 MR accumulators)
 #define VG_GEMV_LAUNCH(WPC, UU) launch_k(gemv_kernel<MR, WPC, UU, AF32>, dim3(blocks), dim3(256), 0, s, g->A, g->lda, B, g->ldb, p, g->a_rms_eps)
   if (split) {
     if (u >= 8) VG_GEMV_LAUNCH(4, 8); else if (u >= 4) VG_GEMV_LAUNCH(4, 4); else VG_GEMV_LAUNCH(4, 2);

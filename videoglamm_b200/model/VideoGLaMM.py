@@ -288,6 +288,9 @@ class VideoGLaMMForCausalLM:
         ctx = None if (context_images is None or context_images[0] is None) else context_images[0]
         # host-resident SAM2 frames (100 MB per 8-frame clip at 1024 px): start the transfer now on a side stream, it completes under the LMM stage
         sam_in, copy_done = images_for_sam[0], None
+        raw_u8 = sam_in.dtype == torch.uint8          # raw frames [T,H,W,3]: pre-processed on the GPU (H*W*3 bytes per frame over PCIe instead of 12.6 MB)
+        if raw_u8:
+            assert sam_in.dim() == 4 and sam_in.shape[3] == 3, "uint8 images_for_sam must be raw frames [T,H,W,3]"
         if not sam_in.is_cuda:
             if not hasattr(self, "_copy_stream"):
                 self._copy_stream = torch.cuda.Stream(device=dev)
@@ -305,6 +308,8 @@ class VideoGLaMMForCausalLM:
         if copy_done is not None:
             torch.cuda.current_stream(dev).wait_event(copy_done)
             sam_in.record_stream(torch.cuda.current_stream(dev))
+        if raw_u8:
+            sam_in = self.sam_preprocessor_gpu().preprocess_video(sam_in)[0]
         if return_logits:   # parity tests: the fp32 video-resolution logits the masks are thresholded from (VideoGLaMM.py:870-875), as a third value
             logits = torch.stack(run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary=False)).cpu()
             stacked = (logits > 0).numpy()
@@ -313,6 +318,12 @@ class VideoGLaMMForCausalLM:
         frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary="packed")
         segs, self.last_packed = self.masks_to_host(frames, int(H), int(W))
         return out_ids, [segs]
+
+    def sam_preprocessor_gpu(self):
+        if not hasattr(self, "_sam_pre_gpu"):
+            from ..preprocess import SAM_v2_PreprocessGPU
+            self._sam_pre_gpu = SAM_v2_PreprocessGPU(self.device, self.sam_cfg.image_size if self.sam_cfg.image_size == 1024 else 1024)
+        return self._sam_pre_gpu
 
     def masks_to_host(self, frames: list, H: int, W: int):
         """Per-frame bit-packed device masks [n_obj, ceil(H*W/8)] -> ({frame: {obj: bool ndarray [H,W]}}, PackedMasks still on the device).

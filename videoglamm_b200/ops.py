@@ -482,3 +482,29 @@ def mask_decoder_fused(weights: "L.VgMaskDecoderWeights", pix: torch.Tensor, den
     d.force_exact = int(exact)
     L.check(L.lib().vg_mask_decoder(C.byref(d), _stream()), "vg_mask_decoder")
     return masks, iou, mt, obj
+
+
+def resize_u8_pil(frames: torch.Tensor, oh: int, ow: int, tables: tuple) -> torch.Tensor:
+    """uint8 [n,h,w,c] cuda -> uint8 [n,oh,ow,c]: PIL.Image.resize(BILINEAR), bit-exact. tables = (kh, bh, kv, bv) int32 cuda tensors
+    (preprocess.pil_bilinear_coeffs for (w -> ow) and (h -> oh))."""
+    _require_cuda(frames, *tables)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4
+    n, h, w, c = frames.shape
+    kh, bh, kv, bv = tables
+    assert kh.dtype == bh.dtype == kv.dtype == bv.dtype == torch.int32 and kh.shape[0] == ow and kv.shape[0] == oh
+    tmp = torch.empty((n, h, ow, c), device=frames.device, dtype=torch.uint8)
+    out = torch.empty((n, oh, ow, c), device=frames.device, dtype=torch.uint8)
+    L.check(L.lib().vg_resize_u8_pil(_ptr(frames), _ptr(tmp), _ptr(out), n, h, w, c, oh, ow, _ptr(kh), _ptr(bh), kh.shape[1], _ptr(kv), _ptr(bv), kv.shape[1],
+                                     _stream()), "vg_resize_u8_pil")
+    return out
+
+
+def sam_normalize_squash(frames: torch.Tensor, S: int, mean: tuple, std: tuple) -> torch.Tensor:
+    """uint8 [n,h,w,3] cuda -> fp32 [n,3,S,S] = F.interpolate((x - mean) / std, (S, S), mode="bilinear")."""
+    _require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4 and frames.shape[3] == 3
+    n, h, w, _ = frames.shape
+    out = torch.empty((n, 3, S, S), device=frames.device, dtype=torch.float32)
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    L.check(L.lib().vg_sam_normalize_squash(_ptr(frames), _ptr(out), n, h, w, S, m3, s3, _stream()), "vg_sam_normalize_squash")
+    return out

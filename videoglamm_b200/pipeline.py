@@ -83,6 +83,8 @@ class ClipPipeline:
                             results[i] = (out_ids, {}, None)
                             continue
                         H, W = clips[i]["original_size"]
+                        if sam_dev.dtype == torch.uint8:       # raw frames [T,H,W,3]: GPU pre-processing (resize / normalise / squash)
+                            sam_dev = m.sam_preprocessor_gpu().preprocess_video(sam_dev)[0]
                         frames = m.sam.run_video(sam_dev, emb[:, None, :], (int(H), int(W)), binary="packed")
                         segs, packed = m.masks_to_host(frames, int(H), int(W))
                         results[i] = (out_ids, segs, packed)

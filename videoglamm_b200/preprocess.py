@@ -76,6 +76,83 @@ class SAM_v2_Preprocess:
         return sam_preprocess(x)
 
 
+def pil_bilinear_coeffs(in_size: int, out_size: int) -> tuple[np.ndarray, np.ndarray]:
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c) for the BILINEAR filter (support 1, scaled by the
+    down-sampling factor): int32 coefficients [out, ksize] with 22 fractional bits and bounds [out, 2] = (first input index, tap count).
+    Evaluated in float64 exactly as Pillow does, so vg_resize_u8_pil reproduces Image.resize bit for bit (tests/test_preprocess_cpu.py)."""
+    import math
+    scale = in_size / out_size
+    fs = max(scale, 1.0)
+    support = 1.0 * fs
+    ksize = int(math.ceil(support)) * 2 + 1
+    kk = np.zeros((out_size, ksize), dtype=np.float64)
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    inv = 1.0 / fs
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        a = np.abs((np.arange(xmax) + xmin - center + 0.5) * inv)
+        w = np.where(a < 1.0, 1.0 - a, 0.0)
+        ww = w.sum()
+        kk[xx, :xmax] = w / ww if ww != 0 else w
+        bounds[xx] = (xmin, xmax)
+    ki = np.where(kk < 0, (-0.5 + kk * (1 << 22)).astype(np.int64), (0.5 + kk * (1 << 22)).astype(np.int64)).astype(np.int32)
+    return ki, bounds
+
+
+def pil_bilinear_resize_numpy(img: np.ndarray, oh: int, ow: int) -> np.ndarray:
+    """Host restatement of Pillow's 8-bit two-pass bilinear resampling (the arithmetic vg_resize_u8_pil executes); used by the CPU tests."""
+    H, W, C = img.shape
+    kh, bh = pil_bilinear_coeffs(W, ow)
+    tmp = np.zeros((H, ow, C), np.uint8)
+    for x in range(ow):
+        lo, n = bh[x]
+        acc = (1 << 21) + (img[:, lo:lo + n, :].astype(np.int64) * kh[x, :n][None, :, None]).sum(1)
+        tmp[:, x] = np.clip(acc >> 22, 0, 255)
+    kv, bv = pil_bilinear_coeffs(H, oh)
+    out = np.zeros((oh, ow, C), np.uint8)
+    for y in range(oh):
+        lo, n = bv[y]
+        acc = (1 << 21) + (tmp[lo:lo + n].astype(np.int64) * kv[y, :n][:, None, None]).sum(0)
+        out[y] = np.clip(acc >> 22, 0, 255)
+    return out
+
+
+class SAM_v2_PreprocessGPU:
+    """sam_preprocess(model_type="sam2") for a whole clip ON THE GPU: the raw uint8 frames [T,H,W,3] are uploaded (H*W*3 bytes per
+    frame instead of 12.6 MB of fp32) and resized (PIL-bilinear, bit-exact), normalised and squashed to 1024x1024 by two libvglamm kernels.
+    Coefficient tables are cached per frame size."""
+
+    def __init__(self, device="cuda", img_size: int = 1024):
+        self.device, self.img_size, self._tables = torch.device(device), img_size, {}
+
+    def tables(self, h: int, w: int):
+        key = (h, w)
+        if key not in self._tables:
+            if len(self._tables) > 32:
+                self._tables.clear()
+            newh, neww = get_preprocess_shape(h, w, self.img_size)
+            kh, bh = pil_bilinear_coeffs(w, neww)
+            kv, bv = pil_bilinear_coeffs(h, newh)
+            self._tables[key] = ((newh, neww), tuple(torch.from_numpy(np.ascontiguousarray(a)).to(self.device) for a in (kh, bh, kv, bv)))
+        return self._tables[key]
+
+    def preprocess_video(self, frames) -> tuple[torch.Tensor, tuple]:
+        """frames: uint8 [T,H,W,3] (numpy, or a torch tensor on the host / device) -> (fp32 [T,3,1024,1024] on the device, resize_shape)."""
+        from . import ops
+        t = torch.from_numpy(np.ascontiguousarray(frames)) if isinstance(frames, np.ndarray) else frames
+        assert t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3
+        t = t.to(self.device, non_blocking=True).contiguous()
+        (newh, neww), tabs = self.tables(t.shape[1], t.shape[2])
+        r = ops.resize_u8_pil(t, newh, neww, tabs)
+        return ops.sam_normalize_squash(r, self.img_size, tuple(SAM_MEAN.flatten().tolist()), tuple(SAM_STD.flatten().tolist())), (newh, neww)
+
+    def preprocess(self, x: np.ndarray):
+        out, shape = self.preprocess_video(x[None])
+        return out[0], shape
+
+
 def tokenizer_image_token(prompt: str, tokenizer, image_token_index: int = IMAGE_TOKEN_INDEX, return_tensors=None):
     """model/videogpt_plus/mm_utils.py:17-37: tokenise the text between <image> markers, join with the -200 sentinel, keep one BOS."""
     chunks = [tokenizer(c).input_ids for c in prompt.split(DEFAULT_IMAGE_TOKEN)]
