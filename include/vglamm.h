@@ -129,6 +129,9 @@ int vg_norm(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, lon
  */
 int vg_add(const void* a, int a_dtype, long long lda, int a_rows, const void* b, int b_dtype, long long ldb, int b_rows, float alpha,
            void* out, int out_dtype, long long ldo, int rows, int cols, void* stream);
+/* out[i] = resid[i] + sum_p parts[p*n + i], fp32 (resid may be NULL or alias out): sums the K-split partial products of a skinny projection
+ * (batched LLM decode: o_proj / down_proj are run as `nparts` batched GEMMs over K slices so that every SM streams weights). */
+int vg_sum_parts(const float* parts, long long n, int nparts, const float* resid, float* out, void* stream);
 /* 2x2 max (is_max=1; Hiera q-pool, hieradet.py:21-33) or mean (is_max=0; arch.py:88-96 adaptive pooling by 2) over a
  * channels-last [n][h][w][c] grid; row stride of the input in elements (reads a column slice of a wider tensor). */
 int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int n, int h, int w, int c, int is_max,

@@ -109,10 +109,28 @@ def test_batched_decode_equals_per_clip_generation():
     eos = (int(single[1][0][0, -6]),)                                     # a token that sequence 1 emits mid-way becomes an EOS id
     single = [model.lmm.generate(*r, 14, eos_ids=eos, forced=forced) for r in reqs]
     assert len({o.shape[1] - r[0].shape[1] for (o, _), r in zip(single, reqs)}) > 1   # the sequences really stop at different lengths
+    # (a) fused-RMS skinny GEMVs (the single-sequence arithmetic, M = S rows): free-running greedy decoding is bit-identical to per-clip generation
+    model.lmm.batch_tc = False
     for rep in range(3):                                                  # eager first sight, capture, replay
         batch = model.lmm.generate_batch(reqs, 14, eos_ids=eos, forced=forced)
         for (ia, ea), (ib, eb) in zip(single, batch):
             assert torch.equal(ia, ib) and torch.equal(ea, eb)
+    # (b) default: the weight passes go through the TMA-fed tensor-core GEMM on bf16-normalised operands (the prefill's arithmetic). Near-tied
+    # logits may legitimately resolve differently from the fp32-operand GEMV, so every step is teacher-forced to the single-sequence tokens and
+    # the hidden states that predicted the [SEG] tokens are compared
+    model.lmm.batch_tc = True
+    model.lmm.g_decode_batch.clear()
+    n_new = min(o.shape[1] - r[0].shape[1] for (o, _), r in zip(single, reqs))
+    common = {st: int(single[0][0][0, reqs[0][0].shape[1] + st]) for st in range(n_new)}
+    common.update(forced)
+    ref_forced = [model.lmm.generate(*r, n_new, forced=common) for r in reqs]
+    for rep in range(3):
+        batch = model.lmm.generate_batch(reqs, n_new, forced=common)
+        for (ia, ea), (ib, eb) in zip(ref_forced, batch):
+            assert torch.equal(ia, ib)
+            assert ea.shape == eb.shape and ((ea - eb).norm() / ea.norm().clamp_min(1e-9)).item() < 2e-2
+    model.lmm.batch_tc = False
+    model.lmm.g_decode_batch.clear()
     seq = [model.inference([c["images"]], [c["context_images"]], [c["images_for_sam"]], c["input_ids"].cuda(), None, [c["original_size"]],
                            max_new_tokens=14, use_sam2_video_branch=True, forced_tokens=forced) for c in clips]
     seq = [(ids.cpu().clone(), {t: {o: m.copy() for o, m in fr.items()} for t, fr in segs[0].items()}) for ids, segs in seq]

@@ -19,18 +19,20 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 
-// EPI2: two staging boxes per epilogue warp (the bulk store of chunk i is still reading its box while chunk i+1 is computed), paid for with
-// one pipeline stage where shared memory is short. Used for the small-K GEMMs, which are bound by the epilogue: with ONE box every chunk waited
-// for the previous store to finish reading (measured: ~2.5-3 output elements/clk/SM whatever the activation, 2-3x the MMA time at K = 576).
-template <int BN, bool EPI2 = false>
+// WIDE: 16 epilogue warps instead of 8 (4 per scheduler; 112 registers each through setmaxnreg), one staging box per warp (64 KB), paid for with
+// one pipeline stage where shared memory is short. For the small-K GEMMs, whose epilogue (tcgen05.ld -> bias -> activation -> pack -> st.shared ->
+// TMA store) is a latency/ILP-bound instruction stream at two warps per scheduler (profiles/r01_gemm_epilogue.md).
+template <int BN, bool WIDE = false>
 struct GemmCfg {
+  static constexpr int EPI_WARPS = WIDE ? 16 : 8;
+  static constexpr int THREADS = (4 + EPI_WARPS) * 32;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BN * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;  // two accumulator stages; allocations are powers of two (128/256/512)
-  static constexpr int STG_PER_WARP = EPI2 ? 2 * 4096 : 4096;  // per epilogue warp: 32-row TMA-store boxes (<= 128 B per row)
-  static constexpr int STAGING_BYTES = 8 * STG_PER_WARP;
+  static constexpr int STG_PER_WARP = 4096;  // per epilogue warp: one 32-row TMA-store box (<= 128 B per row)
+  static constexpr int STAGING_BYTES = EPI_WARPS * STG_PER_WARP;
   static constexpr int VEC_BYTES = 2 /*acc stages*/ * BN * 4;  // bias of the tile being drained
   static constexpr int STAGES_WANT = BN == 256 ? 4 : (BN == 192 ? 4 : (BN >= 96 ? 6 : 8));
   static constexpr int STAGES_FIT = (227 * 1024 - STAGING_BYTES - VEC_BYTES - 256) / STAGE_BYTES;
@@ -124,11 +126,11 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   }
 }
 
-template <int BN, bool EPI2>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool WIDE>
+__global__ void __launch_bounds__(GemmCfg<BN, WIDE>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const GemmParams p) {
-  using Cfg = GemmCfg<BN, EPI2>;
+  using Cfg = GemmCfg<BN, WIDE>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023) != 0) __trap();  // SWIZZLE_128B tiles need a 1024-byte aligned base
   uint8_t* sA = smem;
@@ -156,7 +158,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 256);
+      mbar_init(&tempty_bar[a], Cfg::EPI_WARPS * 32);
     }
     mbar_fence_init();
   }
@@ -244,19 +246,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    if (WIDE)
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");  // 128*56 + 512*104 = 60416 <= 640*96 (the block's own allocation; 112 deadlocked)
+    else
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ------------------------------------------------ epilogue: TMEM -> regs -> (smem -> TMA store | global) ; 8 warps
     // Each warp owns a TMEM lane quadrant (warp % 4) and every other 32-column chunk. Results leave through a per-warp swizzled
     // shared-memory box and ONE bulk tensor store (or reduce-add, when the residual aliases the output) issued by lane 0:
     // thread-per-row st.global touched 32 lines per instruction and capped the epilogue at ~18 GB/s per SM (profiles/r01_gemm_epilogue.md).
     const int ew = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;                 // column group of this warp: chunks half, half + CG, ...
+    constexpr int CG = Cfg::EPI_WARPS / 4;
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out = p.glu ? p.N / 2 : p.N;
     const bool unit_alpha = p.alpha == 1.0f;
     uint8_t* stg_base = staging + (warp - 4) * Cfg::STG_PER_WARP;
-    int box = 0;  // which of this warp's staging boxes the next chunk uses (EPI2)
     const int esz = p.out_f32 ? 4 : 2;
     const int nvals_c = p.glu ? 16 : 32;
     const int row_bytes = nvals_c * esz;                         // 128 / 64 / 32: equals the TMA swizzle span
@@ -271,11 +276,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float* s_bias = s_vec + acc * BN;
       if (p.bias != nullptr) {
         const int et = threadIdx.x - 128;
-        for (int j = et; j < BN; j += 256) {
+        for (int j = et; j < BN; j += Cfg::EPI_WARPS * 32) {
           const int col = n_blk * BN + j;
           s_bias[j] = col < p.N ? __ldg(p.bias + b * p.strideBias + col) : 0.f;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // epilogue warps only
+        if (WIDE)
+          asm volatile("bar.sync 1, 512;" ::: "memory");  // epilogue warps only
+        else
+          asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -283,7 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = half; c < BN / 32; c += CG) {
         const int col0 = n_blk * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t raw[32];
@@ -349,13 +357,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         if (p.use_tma_store) {
           // the previous bulk store of this warp must have finished READING the staging box before it is overwritten
-          uint8_t* stg = stg_base + (EPI2 ? box * 4096 : 0);
-          if (EPI2) {
-            box ^= 1;
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the store issued two chunks ago has read this box
-          } else {
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          }
+          uint8_t* stg = stg_base;
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
           uint8_t* srow = stg + lane * row_bytes;
           if (p.out_f32) {
@@ -775,12 +778,12 @@ static GemmParams to_params(const VgGemm* g) {
   return p;
 }
 
-template <int BN, bool EPI2>
+template <int BN, bool WIDE>
 static int launch_gemm_cfg(const VgGemm* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, EPI2>;
+  using Cfg = GemmCfg<BN, WIDE>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return set_error(VG_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -812,17 +815,17 @@ static int launch_gemm_cfg(const VgGemm* g, cudaStream_t stream) {
   }
   const long long total = static_cast<long long>(p.tiles_m) * p.tiles_n * g->batch;
   const int grid = static_cast<int>(total < num_sms() ? total : num_sms());
-  launch_k(gemm_tcgen05_kernel<BN, EPI2>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p);
+  launch_k(gemm_tcgen05_kernel<BN, WIDE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmC, p);
   count_launch();
   return check_launch("gemm_tcgen05_kernel");
 }
 
-// Small-K problems are bound by the epilogue (store latency per 32-column chunk), large-K ones by the main loop: pick the staging / pipeline
-// split accordingly. VG_GEMM_EPI2=1 enables the two-box configuration (A/B timing; off by default, see profiles/r01_gemm_epilogue.md).
+// Small-K problems are bound by the epilogue, large-K ones by the main loop: pick the epilogue width / pipeline depth accordingly.
+// VG_GEMM_WIDE=0 forces the 8-warp epilogue everywhere (A/B timing).
 template <int BN>
 static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
-  static const int epi2 = [] { const char* e = getenv("VG_GEMM_EPI2"); return e ? atoi(e) : 0; }();  // measured: no gain (profiles/r01_gemm_epilogue.md)
-  if (epi2 && g->K <= 1024) return launch_gemm_cfg<BN, true>(g, stream);
+  static const int wide = [] { const char* e = getenv("VG_GEMM_WIDE"); return e ? atoi(e) : 0; }();  // opt-in until measured on the GPU
+  if (wide && g->K <= 1024 && static_cast<long long>(g->M) * g->N >= (1LL << 22)) return launch_gemm_cfg<BN, true>(g, stream);
   return launch_gemm_cfg<BN, false>(g, stream);
 }
 

@@ -179,6 +179,17 @@ __global__ void add_kernel(const void* a, int adt, long long lda, int a_rows, co
   st(out, odt, r * ldo + c, v);
 }
 
+// out[i] = resid[i] + sum_p parts[p][i] (fp32): reduction of the K-split partial products of the batched-decode projections
+__global__ void sum_parts_kernel(const float* __restrict__ parts, long long n, int nparts, const float* resid, float* out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= n) return;
+  float v = resid ? resid[i] : 0.f;
+  for (int p = 0; p < nparts; ++p) v += parts[p * n + i];
+  out[i] = v;
+}
+
 __global__ void pool2x2_kernel(const void* x, int xdt, long long ldx, void* y, int ydt, long long ldy, int n, int h, int w, int c, int is_max) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
@@ -818,6 +829,13 @@ extern "C" int vg_add(const void* a, int a_dtype, long long lda, int a_rows, con
                                                                                         out_dtype, ldo, rows, cols);
   count_launch();
   return check_launch("add_kernel");
+}
+
+extern "C" int vg_sum_parts(const float* parts, long long n, int nparts, const float* resid, float* out, void* stream) {
+  if (!parts || !out || n <= 0 || nparts <= 0) return set_error(VG_EINVAL, "vg_sum_parts: bad argument");
+  launch_k(sum_parts_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, STREAM, parts, n, nparts, resid, out);
+  count_launch();
+  return check_launch("sum_parts_kernel");
 }
 
 extern "C" int vg_pool2x2(const void* x, int x_dtype, long long ldx, void* y, int y_dtype, long long ldy, int n, int h, int w, int c, int is_max,

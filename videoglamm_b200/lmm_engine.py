@@ -10,6 +10,7 @@ Reference call sites cited per method (paths relative to VideoGLaMM/).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -199,6 +200,7 @@ class LmmEngine:
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
         self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
         self.g_decode_batch = GraphedStage("decode_batch")
+        self.batch_tc = os.environ.get("VG_BATCH_DECODE_TC", "1") != "0" and ph.hidden % 64 == 0
         self.kv_slots = None
         self._batch_state = {}
         self.dec_tok = torch.zeros(1, device=self.dev, dtype=torch.int64)
@@ -261,6 +263,14 @@ class LmmEngine:
         """Prefill rows [0, n); returns the final-norm hidden state of the LAST row only ([1, hidden] fp32) — all that decoding needs."""
         return self._llm(x, 0, last_only=True, slot=slot)
 
+    @staticmethod
+    def _ksplit(K: int) -> int:
+        """K slices for the skinny o_proj / down_proj of the batched decode: the largest of 4, 3, 2 whose slice is a multiple of 64 and >= 512."""
+        for p in (4, 3, 2):
+            if K % p == 0 and (K // p) % 64 == 0 and K // p >= 512:
+                return p
+        return 1
+
     def _decode_step_batch(self, S: int, kv_bound: int):
         """One KV-cached decode step for S sequences at once (C3: the clips queued on a GPU decode together): every weight matrix is streamed ONCE for
         the S tokens (skinny GEMMs with M = S), each sequence attends over its own cache slot with its own key count (dec_nk[s]), RoPE and the cache
@@ -269,8 +279,23 @@ class LmmEngine:
         H, hd, D = ph.heads, ph.head_dim, ph.hidden
         st = self._batch_state[S]
         x = ops.embedding(self.embed, st["tok"])                                             # [S, hidden] fp32
+        # M = S rows: the weight-streaming work goes through the TMA-fed tcgen05 GEMM (force_block_n=64 -> N/64 tiles, every SM streams a ring of
+        # weight tiles; the A tile is 4 real rows + TMA zero fill), o_proj / down_proj as K-split batched GEMMs so that they too fill the machine
         for l, L in enumerate(self.layers):
             cache = self.kv_slots[l]
+            if self.batch_tc:
+                h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
+                ops.gemm(h, L["qkv"].w, out=st["qkv"], force_block_n=64)
+                q = st["qkv"][:, :D].unflatten(1, (H, hd))[:, None]
+                k = cache[:S, :kv_bound, D:2 * D].unflatten(2, (H, hd))
+                v = cache[:S, :kv_bound, 2 * D:].unflatten(2, (H, hd))
+                o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=st["nk"], decode_ws=st["ws"],
+                                  fused_rope_theta=ph.rope_theta)
+                x = ops.gemm_ksplit(o.view(S, D), L["o"].w, self._ksplit(D), resid=x, out=x)
+                h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
+                h = ops.gemm(h, L["gu"].w, glu=True, act="silu", force_block_n=64)
+                x = ops.gemm_ksplit(h, L["down"].w, self._ksplit(ph.inter), resid=x, out=x)
+                continue
             ops.gemm(x, L["qkv"].w, out=st["qkv"], a_rms_eps=ph.eps)
             q = st["qkv"][:, :D].unflatten(1, (H, hd))[:, None]                              # [S, 1, H, hd], batch stride 3*hidden
             k = cache[:S, :kv_bound, D:2 * D].unflatten(2, (H, hd))
@@ -352,6 +377,9 @@ class LmmEngine:
         if self.P:
             h = ops.norm(x_last, self.ones, eps=self.cfg.phi.eps, rms=True, out_dtype=F32)
             return ops.argmax(ops.gemm(h, self.lm_head.w3, out_dtype=F32))
+        if x_last.shape[0] > 1 and self.batch_tc:      # batched decode: stream lm_head through the TMA-fed tensor-core GEMM (see _decode_step_batch)
+            h = ops.norm(x_last, self.ones, eps=self.cfg.phi.eps, rms=True)
+            return ops.argmax(ops.gemm(h, self.lm_head.w, out_dtype=F32, force_block_n=64))
         return ops.argmax(ops.gemm(x_last, self.lm_head.w, out_dtype=F32, a_rms_eps=self.cfg.phi.eps))
 
     def _embed(self, ids: torch.Tensor) -> torch.Tensor:
