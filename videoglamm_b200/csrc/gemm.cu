@@ -824,8 +824,11 @@ static int launch_gemm_cfg(const VgGemm* g, cudaStream_t stream) {
 // VG_GEMM_WIDE=0 forces the 8-warp epilogue everywhere (A/B timing).
 template <int BN>
 static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
-  static const int wide = [] { const char* e = getenv("VG_GEMM_WIDE"); return e ? atoi(e) : 0; }();  // opt-in until measured on the GPU
-  if (wide && g->K <= 1024 && static_cast<long long>(g->M) * g->N >= (1LL << 22)) return launch_gemm_cfg<BN, true>(g, stream);
+  // measured (profiles/r02_gemm_epilogue.md): 16 epilogue warps gain 10-15 % on the small-K GEMMs whose epilogue evaluates an activation
+  // (Hiera fc1: 111 -> 96 us, stage-2 fc1: 199 -> 181 us) and nothing (-3 %) on bias-only epilogues -> default on for the former only
+  static const int wide = [] { const char* e = getenv("VG_GEMM_WIDE"); return e ? atoi(e) : 2; }();  // 0 never, 1 every small-K GEMM, 2 (default) activated epilogues
+  if (wide && g->K <= 1024 && static_cast<long long>(g->M) * g->N >= (1LL << 22) && (wide == 1 || g->act != VG_ACT_NONE))
+    return launch_gemm_cfg<BN, true>(g, stream);
   return launch_gemm_cfg<BN, false>(g, stream);
 }
 
