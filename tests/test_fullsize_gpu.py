@@ -7,6 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import lmm as M, sam2 as O, weights as Wt  # noqa: E402
+from videoglamm_b200 import ops  # noqa: E402
 from videoglamm_b200.config import Sam2Config, make_lmm_config  # noqa: E402
 from videoglamm_b200.lmm_engine import LmmEngine  # noqa: E402
 from videoglamm_b200.sam2_engine import Sam2Engine  # noqa: E402
@@ -79,6 +80,21 @@ def test_full_width_towers_and_phi3_reduced_depth():
     out_ids, emb = eng.generate(ids[None].cuda(), images.cuda(), ctx.cuda(), 4, forced={1: 32011})
     assert torch.equal(out_ids[0].cpu(), ids_ref)          # greedy ids bit-exact at full width (855-token sequence, KV-cached vs no-cache)
     assert rel(emb, emb_ref) < 2e-2
+    # batched decode at full width: S = 3 sequences (different prompt lengths) through the multi-row weight-streaming kernel
+    # (csrc/gemv_ring.cu gemv_ring_mma_kernel: qkv / gate_up / lm_head with fused RMSNorm on fp32 rows, o_proj / down_proj on bf16 rows),
+    # teacher-forced to the oracle's tokens: ids reproduced, [SEG] hidden state within the same bar as the single-sequence path
+    forced_all = {st: int(ids_ref[ids.numel() + st]) for st in range(4)}
+    reqs = [(ids[None].cuda(), images.cuda(), ctx.cuda()),
+            (torch.cat([ids[:9], ids[9:9 + T], ids[9 + T:][:5]])[None].cuda(), images.cuda(), ctx.cuda()),
+            (ids[None].cuda(), images.cuda(), ctx.cuda())]
+    n0 = ops.launch_count()
+    outs = eng.generate_batch(reqs, 4, forced=forced_all)
+    assert ops.launch_count() > n0
+    for k in (0, 2):
+        assert torch.equal(outs[k][0][0].cpu(), ids_ref)
+        assert rel(outs[k][1], emb_ref) < 2e-2
+    single = eng.generate(*reqs[1], 4, forced=forced_all)
+    assert torch.equal(outs[1][0], single[0]) and rel(outs[1][1], single[1]) < 5e-3
 
 
 def test_phi3_prefill_and_decode_beyond_the_sliding_window():

@@ -356,7 +356,9 @@ def test_norm_block_per_row_path(rows, cols):
     assert rel(ops.norm(x, w, eps=1e-5, rms=True, out_dtype=torch.float32), x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * w) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,K,glu", [(1, 9216, 3072, False), (1, 16384, 3072, True), (1, 3072, 8192, False), (3, 1024, 512, False), (1, 32064, 3072, False)])
+@pytest.mark.parametrize("M,N,K,glu", [(1, 9216, 3072, False), (1, 16384, 3072, True), (1, 3072, 8192, False), (3, 1024, 512, False), (1, 32064, 3072, False),
+                                       (2, 9216, 3072, False), (4, 16384, 3072, True), (3, 16384, 3072, True), (4, 32064, 3072, False), (2, 1200, 1024, False),
+                                       (8, 9216, 3072, False), (7, 16384, 3072, True), (5, 2056, 1024, False)])
 def test_skinny_gemm_fused_rmsnorm(M, N, K, glu):
     """fp32 A rows RMS-normalised inside the weight-streaming kernel (norm weight folded into W by the caller)."""
     x = torch.randn(M, K, device=DEV) * 3
@@ -368,6 +370,31 @@ def test_skinny_gemm_fused_rmsnorm(M, N, K, glu):
         ref = (F.silu(r[:, :, 0]) * r[:, :, 1]).reshape(M, -1)
     y = ops.gemm(x, w, glu=glu, act="silu" if glu else None, out_dtype=torch.float32, a_rms_eps=1e-5)
     assert rel(y, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M", [2, 3, 4, 6, 8])
+def test_multi_row_ring_gemv_batched_decode_shapes(M):
+    """M = 2..8 rows through the multi-row TMA-ring kernel (csrc/gemv_ring.cu: every weight row streamed once for all rows, mma.sync), at the batched decode's
+    o_proj / down_proj shapes: bf16 A, fp32 residual updated in place, row strides larger than the row length; and row m of the M-row result agrees
+    with the single-row kernel on row m alone."""
+    for N, K in ((3072, 3072), (3072, 8192)):
+        abuf = torch.randn(M, K + 64, device=DEV).bfloat16()
+        a = abuf[:, :K]
+        w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+        x = torch.randn(M, N, device=DEV)
+        ref = x + a.float() @ w.float().T
+        singles = torch.cat([ops.gemm(a[m:m + 1].contiguous(), w, resid=x[m:m + 1].contiguous(), out_dtype=torch.float32) for m in range(M)])
+        y = ops.gemm(a, w, resid=x, out=x)
+        assert y.data_ptr() == x.data_ptr() and rel(x, ref) < 1e-5 and rel(x, singles) < 1e-5
+    # bf16 output into a column slice (the qkv scratch rows), bias + activation
+    K, N = 3072, 2048
+    xin = torch.randn(M, K, device=DEV)
+    w = (torch.randn(N, K, device=DEV) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    buf = torch.zeros(M, N + 128, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(xin, w, bias=bias, act="gelu", out=buf[:, :N], a_rms_eps=1e-6)
+    xn = xin * torch.rsqrt(xin.pow(2).mean(-1, keepdim=True) + 1e-6)
+    assert rel(buf[:, :N], F.gelu(xn @ w.float().T + bias)) < 4e-3 and float(buf[:, N:].abs().max()) == 0.0
 
 
 def test_rope_kv_append_and_fused_merge_decode_attention():

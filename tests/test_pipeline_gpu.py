@@ -115,10 +115,10 @@ def test_batched_decode_equals_per_clip_generation():
         batch = model.lmm.generate_batch(reqs, 14, eos_ids=eos, forced=forced)
         for (ia, ea), (ib, eb) in zip(single, batch):
             assert torch.equal(ia, ib) and torch.equal(ea, eb)
-    # (b) default: the weight passes go through the TMA-fed tensor-core GEMM on bf16-normalised operands (the prefill's arithmetic). Near-tied
-    # logits may legitimately resolve differently from the fp32-operand GEMV, so every step is teacher-forced to the single-sequence tokens and
-    # the hidden states that predicted the [SEG] tokens are compared
-    model.lmm.batch_tc = True
+    # (b) the alternative path (VG_BATCH_TC_MIN): the weight passes go through the TMA-fed tcgen05 GEMM on bf16-normalised operands (the prefill's
+    # arithmetic). Near-tied logits may legitimately resolve differently from the fp32-operand GEMV, so every step is teacher-forced to the
+    # single-sequence tokens and the hidden states that predicted the [SEG] tokens are compared
+    model.lmm.batch_tc, model.lmm.batch_tc_min = True, 2
     model.lmm.g_decode_batch.clear()
     n_new = min(o.shape[1] - r[0].shape[1] for (o, _), r in zip(single, reqs))
     common = {st: int(single[0][0][0, reqs[0][0].shape[1] + st]) for st in range(n_new)}

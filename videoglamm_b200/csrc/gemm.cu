@@ -835,7 +835,8 @@ static int launch_gemm(const VgGemm* g, cudaStream_t stream) {
 }  // namespace vg
 
 namespace vg {
-int gemv_ring_try(const VgGemm* g, cudaStream_t s);  // gemv_ring.cu
+int gemv_ring_try(const VgGemm* g, cudaStream_t s);
+int gemv_ring_mr_try(const VgGemm* g, cudaStream_t s);  // gemv_ring.cu
 }
 using namespace vg;
 
@@ -854,6 +855,9 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
     if (af32 && ((g->lda % 4) || (reinterpret_cast<uintptr_t>(g->A) & 15))) return set_error(VG_EINVAL, "vg_gemm: fp32 A must be 16B aligned");
     if (g->M == 1) {
       const int rrc = gemv_ring_try(g, s);  // persistent TMA-ring kernel (decode-sized problems); VG_ENOSUP -> generic skinny kernel
+      if (rrc != VG_ENOSUP) return rrc;
+    } else {
+      const int rrc = gemv_ring_mr_try(g, s);  // 2..8 rows (batched decode): the same streaming ring feeding mma.sync
       if (rrc != VG_ENOSUP) return rrc;
     }
     if (g->M == 1) { if (af32) launch_gemv<1, true>(g, p, s); else launch_gemv<1, false>(g, p, s); }

@@ -200,7 +200,11 @@ class LmmEngine:
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
         self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
         self.g_decode_batch = GraphedStage("decode_batch")
+        # batched decode: S <= 8 sequences stream the weights through the multi-row TMA-ring kernel (csrc/gemv_ring.cu: mma.sync on fp32 activations
+        # split hi + lo, fused RMSNorm: the single-sequence step's arithmetic up to summation order). S >= batch_tc_min (none by default) goes through
+        # the tcgen05 GEMM with one-wave tile counts instead (measured 4.6 / 5.3 ms per step at S = 4 / 8 against 3.1 / 4.1 ms for the ring)
         self.batch_tc = os.environ.get("VG_BATCH_DECODE_TC", "1") != "0" and ph.hidden % 64 == 0
+        self.batch_tc_min = int(os.environ.get("VG_BATCH_TC_MIN", "9"))
         self.kv_slots = None
         self._batch_state = {}
         self.dec_tok = torch.zeros(1, device=self.dev, dtype=torch.int64)
@@ -264,9 +268,9 @@ class LmmEngine:
         return self._llm(x, 0, last_only=True, slot=slot)
 
     @staticmethod
-    def _ksplit(K: int) -> int:
-        """K slices for the skinny o_proj / down_proj of the batched decode: the largest of 4, 3, 2 whose slice is a multiple of 64 and >= 512."""
-        for p in (4, 3, 2):
+    def _ksplit(K: int, want: int) -> int:
+        """K slices for the skinny o_proj / down_proj of the batched decode: `want` if its slices are multiples of 64 and >= 512, else fewer."""
+        for p in range(want, 1, -1):
             if K % p == 0 and (K // p) % 64 == 0 and K // p >= 512:
                 return p
         return 1
@@ -283,7 +287,7 @@ class LmmEngine:
         # weight tiles; the A tile is 4 real rows + TMA zero fill), o_proj / down_proj as K-split batched GEMMs so that they too fill the machine
         for l, L in enumerate(self.layers):
             cache = self.kv_slots[l]
-            if self.batch_tc:
+            if self.batch_tc and S >= self.batch_tc_min:
                 h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
                 ops.gemm(h, L["qkv"].w, out=st["qkv"], force_block_n=64)
                 q = st["qkv"][:, :D].unflatten(1, (H, hd))[:, None]
@@ -291,10 +295,12 @@ class LmmEngine:
                 v = cache[:S, :kv_bound, 2 * D:].unflatten(2, (H, hd))
                 o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0, nk_dev=st["nk"], decode_ws=st["ws"],
                                   fused_rope_theta=ph.rope_theta)
-                x = ops.gemm_ksplit(o.view(S, D), L["o"].w, self._ksplit(D), resid=x, out=x)
+                # tile counts are chosen to fill ONE wave of the 148 SMs (each tile streams its slice of the weights): Phi-3-mini: qkv 9216/64 = 144,
+                # o 3 K-slices x 3072/64 = 144, gate_up 16384/128 = 128, down 4 K-slices x 3072/96 = 128
+                x = ops.gemm_ksplit(o.view(S, D), L["o"].w, self._ksplit(D, 3), resid=x, out=x)
                 h = ops.norm(x, self.ones, eps=ph.eps, rms=True)
-                h = ops.gemm(h, L["gu"].w, glu=True, act="silu", force_block_n=64)
-                x = ops.gemm_ksplit(h, L["down"].w, self._ksplit(ph.inter), resid=x, out=x)
+                h = ops.gemm(h, L["gu"].w, glu=True, act="silu", force_block_n=128 if 2 * ph.inter >= 128 * 96 else 64)
+                x = ops.gemm_ksplit(h, L["down"].w, self._ksplit(ph.inter, 4), resid=x, out=x, block_n=96 if D % 96 == 0 else 64)
                 continue
             ops.gemm(x, L["qkv"].w, out=st["qkv"], a_rms_eps=ph.eps)
             q = st["qkv"][:, :D].unflatten(1, (H, hd))[:, None]                              # [S, 1, H, hd], batch stride 3*hidden
@@ -377,7 +383,7 @@ class LmmEngine:
         if self.P:
             h = ops.norm(x_last, self.ones, eps=self.cfg.phi.eps, rms=True, out_dtype=F32)
             return ops.argmax(ops.gemm(h, self.lm_head.w3, out_dtype=F32))
-        if x_last.shape[0] > 1 and self.batch_tc:      # batched decode: stream lm_head through the TMA-fed tensor-core GEMM (see _decode_step_batch)
+        if x_last.shape[0] >= self.batch_tc_min and self.batch_tc:      # batched decode: stream lm_head through the TMA-fed tensor-core GEMM (see _decode_step_batch)
             h = ops.norm(x_last, self.ones, eps=self.cfg.phi.eps, rms=True)
             return ops.argmax(ops.gemm(h, self.lm_head.w, out_dtype=F32, force_block_n=64))
         return ops.argmax(ops.gemm(x_last, self.lm_head.w, out_dtype=F32, a_rms_eps=self.cfg.phi.eps))
@@ -398,7 +404,8 @@ class LmmEngine:
     def generate_batch(self, requests: list[tuple], max_new_tokens: int, eos_ids=(), forced: dict | None = None) -> list[tuple]:
         """`generate` for S = len(requests) <= 8 independent clips at once: requests = [(input_ids, images, context_images)]. Towers and prefill run
         per clip (tensor-bound, each fills the GPU alone); the HBM-bound decode loop runs ONCE for all S sequences (`_decode_step_batch`), with one
-        host synchronisation per step for the whole batch. Results are bit-identical to S calls of `generate`: [(output_ids, pred_embeddings)]."""
+        host synchronisation per step for the whole batch. Same arithmetic as S calls of `generate` up to the fp32 summation order of the
+        weight-streaming kernels (bit-identical where both take the generic skinny kernel): [(output_ids, pred_embeddings)]."""
         cfg, S = self.cfg, len(requests)
         assert 1 <= S <= 8 and not self.P
         if S == 1:

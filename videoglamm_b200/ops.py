@@ -510,7 +510,8 @@ def sam_normalize_squash(frames: torch.Tensor, S: int, mean: tuple, std: tuple) 
     return out
 
 
-def gemm_ksplit(a: torch.Tensor, w: torch.Tensor, nparts: int, *, resid: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+def gemm_ksplit(a: torch.Tensor, w: torch.Tensor, nparts: int, *, resid: torch.Tensor | None = None, out: torch.Tensor | None = None,
+                block_n: int = 64) -> torch.Tensor:
     """Skinny projection out = a @ w^T (+ resid) with FEW output columns (a bf16 [M <= 8, K], w bf16 [N, K]) as `nparts` batched tensor-core GEMMs over
     K slices + a partial-sum kernel: N/64 tiles alone would leave most SMs idle while the weights stream (HBM-bound), N/64 * nparts tiles fill them."""
     M, K = a.shape
@@ -518,7 +519,7 @@ def gemm_ksplit(a: torch.Tensor, w: torch.Tensor, nparts: int, *, resid: torch.T
     assert K % nparts == 0 and (K // nparts) % 8 == 0 and a.is_contiguous() and w.is_contiguous()
     kp = K // nparts
     parts = torch.empty((nparts, M, N), device=a.device, dtype=torch.float32)
-    gemm(a.view(M, nparts, kp).permute(1, 0, 2), w.view(N, nparts, kp).permute(1, 0, 2), out=parts, force_block_n=64)
+    gemm(a.view(M, nparts, kp).permute(1, 0, 2), w.view(N, nparts, kp).permute(1, 0, 2), out=parts, force_block_n=block_n)
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=torch.float32)
     assert out.dtype == torch.float32 and out.is_contiguous() and (resid is None or (resid.dtype == torch.float32 and resid.is_contiguous()))
