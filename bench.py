@@ -12,6 +12,7 @@ Prints ONE JSON line (contract in the task statement / DESIGN.md §Measurement).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -76,6 +77,10 @@ class ClockSampler:
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+
+    def mark(self):
+        """Rows before this point (nvidia-smi start-up, idle GPU) are not part of the timed region."""
+        self.rows = []
 
     def _read(self):
         for line in self.proc.stdout:
@@ -171,9 +176,13 @@ def run_engine(args):
             P.gather_results([(rank * len(results) + j, ids, pm) for j, (ids, pm) in enumerate(results)], device=dev, unpack=False)
 
     from videoglamm_b200.pipeline import ClipPipeline
-    pipe = ClipPipeline(model, decode_batch=CPS)        # C3: the 4 clips of a step decode together (one weight pass per token for all of them)
+    # the HBM-bound decode loops of up to DB queued clips run as ONE batched loop (one weight pass per token for all of them): the 4 clips of a
+    # C3 step; for the 1-clip-per-step configs, DB consecutive clips of the stream (throughput serving; --decode-batch 1 turns it off)
+    DB = max(CPS, min(int(args.decode_batch), 8))
+    pipe = ClipPipeline(model, decode_batch=DB)
+    pipe1 = ClipPipeline(model, decode_batch=CPS) if DB != CPS else None
 
-    def run_clips(inps, steps):
+    def run_clips(inps, steps, pipe=pipe):
         """`steps` batches of CPS independent clips per GPU. Sequential mode calls model.inference clip by clip; pipelined mode (default) overlaps
         the LMM stage of clip i+1 with the SAM2 stage of clip i on two streams — same public engine, same results; every clip completes (masks on
         the host as bool arrays) and the batch is gathered to rank 0 inside the region."""
@@ -190,13 +199,13 @@ def run_engine(args):
             clips.append(dict(images=im, context_images=ctx, images_for_sam=sam, input_ids=ids, original_size=VIDEO_HW))
         gather_batch([(out_ids, pm) for out_ids, _, pm in pipe.run(clips, N_NEW, forced_tokens=forced)])
 
-    def timed(inp, steps):
+    def timed(inp, steps, pipe=pipe):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run_clips(inp, steps)
+        run_clips(inp, steps, pipe)
         e1.record()
         if world > 1:
             dist.barrier()
@@ -208,10 +217,19 @@ def run_engine(args):
 
     for _ in range(max(args.warmup, 3)):
         step(resident)
-    run_clips(res_clips, 2)                      # pipeline warm-up (per-thread stream state, graph pools)
-    run_clips(host_clips, 2)                     # ... and of the host-input paths (side-stream allocator pools, pinned result buffers)
-    run_clips(raw_clips, 2)
+    # pipeline warm-up (per-thread stream state, graph pools): two full decode groups + the remainder group the timed run will end with, so that
+    # every graph key of the timed region (prefill per cache slot, batched decode per group size) has been seen and captured
+    warm_steps = -(-(2 * DB + (args.steps * CPS) % DB) // CPS)
+    run_clips(res_clips, warm_steps)
+    run_clips(host_clips, warm_steps)            # ... and of the host-input paths (side-stream allocator pools, pinned result buffers)
+    run_clips(raw_clips, warm_steps)
+    if pipe1 is not None:
+        run_clips(res_clips, 2, pipe1)
     torch.cuda.synchronize()
+    # serving hygiene: the engine's long-lived Python objects (weights, graphs, tensor maps) move to the permanent generation, so that a
+    # generation-2 garbage collection cannot stall both stage threads for 0.1-0.3 s in the middle of a timed region (seen in the stage traces)
+    gc.collect()
+    gc.freeze()
     lat0, lat1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lat0.record()
     step(resident)
@@ -221,11 +239,33 @@ def run_engine(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()                     # nvidia-smi start-up (fork + NVML init across every GPU of the box stalls our launches for
+        while not sampler.rows and time.time() - t_wait < 8.0:   # 0.1-0.3 s) stays out of the timed region: wait for its first sample
+            time.sleep(0.05)
+        sampler.mark()
     ops.launch_count_reset()
+    def graph_stats():
+        return {k: dict(v.stats) for eng in (model.lmm, model.sam) for k, v in vars(eng).items() if hasattr(v, "stats") and hasattr(v, "entries")}
+    def dump_trace(name):
+        """diagnostics (VG_PIPE_TRACE=1): start -> end of every stage call of a timed region, ms from the first mark"""
+        if not pipe.trace:
+            return
+        t_first, marks = pipe.trace[0][2], {}
+        for tag, i, ev in pipe.trace:
+            marks[(tag, i)] = t_first.elapsed_time(ev)
+        row = [f"{tag[:-1]}{i}:{t:.0f}-{marks[(tag[:-1] + '1', i)]:.0f}" for (tag, i), t in sorted(marks.items(), key=lambda kv: kv[1]) if tag.endswith("0")]
+        print(f"trace {name}", " ".join(row), graph_stats(), file=sys.stderr)
+        pipe.trace = []
+    if os.environ.get("VG_PIPE_TRACE"):
+        pipe.trace = []
     ms = timed(res_clips, args.steps)
     launches = ops.launch_count()
+    dump_trace("resident")
     ms_e2e = timed(raw_clips, args.steps)       # same call, HOST pinned inputs incl. the RAW uint8 SAM2 frames (GPU pre-processing): H2D + D2H inside the region
+    dump_trace("e2e")
+    pipe.trace = None
     ms_e2e_fp32 = timed(host_clips, args.steps)  # ... and with the CPU-preprocessed fp32 SAM2 tensors the reference uploads (100 MB per 8-frame clip)
+    ms_db1 = timed(res_clips, args.steps, pipe1) if pipe1 is not None else None   # the same stream of clips, every clip decoded alone
     clocks = sampler.stop() if rank == 0 else {}
     # dominant kernel = the tcgen05 GEMM: per-launch CUDA-event timing on one extra (untimed) step
     from videoglamm_b200 import graphs
@@ -260,7 +300,10 @@ def run_engine(args):
                        "parallelism": f"dp{world} (independent clips, bit-packed masks gathered to rank 0 once per batch)",
                        "l2": "no explicit flush: each step streams 10.8 GB of bf16 weights (>> 126 MB L2)",
                        "algorithmic_tflop_per_clip": clip_flops(L) / 1e12,
-                       "schedule": "sequential clips" if args.sequential else "2-stage pipeline over clips (LMM of clip i+1 || SAM2 of clip i, two streams)",
+                       "schedule": "sequential clips" if args.sequential else
+                                   f"2-stage pipeline over clips (LMM of clips i+1.. || SAM2 of clip i, two streams); decode loops of {DB} queued clips batched",
+                       "decode_batch": DB,
+                       **({"value_decode_batch_1": n_clips / (ms_db1 * 1e-3)} if ms_db1 else {}),
                        "latency_ms_single_clip": latency_ms},
             "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "inputs": "pinned host tensors: IV2 / CLIP frames fp32 (CPU-preprocessed as the reference does), SAM2 frames RAW uint8 [T,H,W,3] pre-processed on "
@@ -521,6 +564,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--decode-batch", type=int, default=4, help="decode loops of this many queued clips run as one batched loop (>= clips per step)")
     ap.add_argument("--sequential", action="store_true", help="one clip at a time (latency mode); default overlaps consecutive clips")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]: 2 (headline, default), 3, 4, 5")
     a = ap.parse_args()

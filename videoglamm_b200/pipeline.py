@@ -22,6 +22,13 @@ class ClipPipeline:
         self.s_lmm = torch.cuda.Stream(device=model.device)
         self.s_sam = torch.cuda.Stream(device=model.device)
         self.s_copy = torch.cuda.Stream(device=model.device)   # host -> device prefetch of the SAM2 frames (100 MB per clip at 1024 px)
+        self.trace = None                                      # set to a list to collect (tag, index, cuda event) marks of both stages (diagnostics)
+
+    def _mark(self, tag: str, i: int, stream):
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self.trace.append((tag, i, ev))
 
     @torch.no_grad()
     def run(self, clips: list[dict], max_new_tokens: int, forced_tokens: dict | None = None) -> list[tuple]:
@@ -54,7 +61,9 @@ class ClipPipeline:
                             ctx = c.get("context_images")
                             reqs.append((c["input_ids"].to(dev, non_blocking=True), c["images"].to(dev, torch.float32, non_blocking=True),
                                          None if ctx is None else ctx.to(dev, torch.float32, non_blocking=True)))
+                        self._mark("lmm0", i0, self.s_lmm)
                         outs = m.lmm.generate_batch(reqs, max_new_tokens, eos_ids=m._eos_ids(), forced=forced_tokens)
+                        self._mark("lmm1", i0, self.s_lmm)
                         for j, ((out_ids, emb), (sam_dev, ev_copy)) in enumerate(zip(outs, sams)):
                             emb = emb.clone()
                             emb.record_stream(self.s_sam)      # consumed on the other stream: keep the allocator from recycling it early
@@ -83,10 +92,12 @@ class ClipPipeline:
                             results[i] = (out_ids, {}, None)
                             continue
                         H, W = clips[i]["original_size"]
+                        self._mark("sam0", i, self.s_sam)
                         if sam_dev.dtype == torch.uint8:       # raw frames [T,H,W,3]: GPU pre-processing (resize / normalise / squash)
                             sam_dev = m.sam_preprocessor_gpu().preprocess_video(sam_dev)[0]
                         frames = m.sam.run_video(sam_dev, emb[:, None, :], (int(H), int(W)), binary="packed")
                         segs, packed = m.masks_to_host(frames, int(H), int(W))
+                        self._mark("sam1", i, self.s_sam)
                         results[i] = (out_ids, segs, packed)
             except Exception as e:
                 errors.append(e)
