@@ -120,6 +120,17 @@ def test_attention(B, H, Nq, Nk, D, causal, window):
     assert rel(o, sdpa_ref(q, k, v, D ** -0.5, causal, window)) < 6e-3  # P is rounded to bf16 before PV
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk,D,causal,window", [(8, 8, 2048, 640, 72, False, 0), (4, 32, 1024, 1024, 96, True, 0), (4, 32, 1000, 1300, 96, True, 300),
+                                                      (16, 8, 1100, 333, 64, False, 0)])
+def test_attention_two_query_tiles_per_block(B, H, Nq, Nk, D, causal, window):
+    """>= 1024 query tiles x heads x batch and D <= 128: flash_attn_tc2_kernel (two query tiles per block share the K/V ring; causal / banded
+    pairs with different key ranges, a ragged last pair, key counts that are not a multiple of the tile)."""
+    torch.manual_seed(B + Nq)
+    q, k, v = [torch.randn(B, n, H, D, device=DEV).bfloat16() for n in (Nq, Nk, Nk)]
+    o = ops.attention(q, k, v, causal=causal, window=window)
+    assert rel(o, sdpa_ref(q, k, v, D ** -0.5, causal, window)) < 4e-3
+
+
 def test_attention_packed_qkv_strides():
     B, N, H, D = 2, 200, 4, 72
     qkv = torch.randn(B, N, 3, H, D, device=DEV).bfloat16()

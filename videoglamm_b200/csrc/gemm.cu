@@ -208,8 +208,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------ MMA issuer: the whole warp runs the loop converged and one elected lane issues
+      // (umma_bf16_elect). Under `if (lane == 0)` the compiler wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop, ~50 cycles of the
+      // single issuing thread each: more than the 32-64 cycles a BLOCK_N <= 128 MMA keeps the tensor pipe busy.
       constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BN);
       int stage = 0;
       uint32_t phase = 0;
@@ -229,15 +231,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_bf16_elect(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          umma_commit_elect(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == Cfg::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        umma_commit_elect(&tfull_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

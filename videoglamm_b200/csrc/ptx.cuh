@@ -86,6 +86,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same, executed by a CONVERGED warp: one elected lane issues. With warp-uniform operands the compiler keeps them in uniform registers and
+// emits a bare UTCHMMA; under `if (lane == 0)` it wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop (~50 cycles of a single thread each).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -170,6 +192,35 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// Two positive fp32 -> packed bf16x2 on the ALU pipe (round half up, then take the upper halves with one PRMT): F2FP shares the XU pipe with
+// MUFU.EX2, which is what bounds the attention softmax.
+__device__ __forceinline__ uint32_t pack_bf16_alu(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+// Packed fp32x2 arithmetic (sm_100): (d0, d1) = (a0, a1) * (b, b) + (c, c) and (d0, d1) = (a0, a1) + (b0, b1) in one instruction each.
+__device__ __forceinline__ void ffma2_bc(float& d0, float& d1, float a0, float a1, float b, float c) {
+  asm("{\n"
+      ".reg .b64 ra, rb, rc, rd;\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "mov.b64 rb, {%4, %4};\n"
+      "mov.b64 rc, {%5, %5};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1) {
+  asm("{\n"
+      ".reg .b64 ra, rd;\n"
+      "mov.b64 rd, {%0, %1};\n"
+      "mov.b64 ra, {%2, %3};\n"
+      "add.rn.f32x2 rd, rd, ra;\n"
+      "mov.b64 {%0, %1}, rd;\n"
+      "}\n"
+      : "+f"(d0), "+f"(d1)
+      : "f"(a0), "f"(a1));
 }
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
