@@ -220,6 +220,13 @@ def test_add_pool_upsample():
     assert rel(ops.pool2x2(q, 2, 8, 6, is_max=True), ref) < 1e-6
     ref = F.avg_pool2d(q.float().reshape(2, 8, 6, 16).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 16)
     assert rel(ops.pool2x2(q, 2, 8, 6, is_max=False, out_dtype=torch.float32), ref) < 1e-6
+    xf = torch.randn(3 * 6 * 10, 36, device=DEV)                          # fp32 -> fp32 (projector pooling): 4-channel vector path; 36 % 8 != 0
+    for is_max, fn in ((True, F.max_pool2d), (False, F.avg_pool2d)):
+        ref = fn(xf.reshape(3, 6, 10, 36).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 36)
+        assert rel(ops.pool2x2(xf, 3, 6, 10, is_max=is_max), ref) < 1e-6
+        xb = xf.bfloat16()                                                 # bf16, 36 channels: scalar path
+        refb = fn(xb.float().reshape(3, 6, 10, 36).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 36)
+        assert rel(ops.pool2x2(xb, 3, 6, 10, is_max=is_max), refb) < 4e-3
     lat, top = torch.randn(2 * 8 * 8, 32, device=DEV), torch.randn(2 * 4 * 4, 32, device=DEV)
     ref = lat.reshape(2, 8, 8, 32) + F.interpolate(top.reshape(2, 4, 4, 32).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
     assert rel(ops.upsample2x_add(lat, top, 2, 4, 4), ref.reshape(-1, 32)) < 1e-6

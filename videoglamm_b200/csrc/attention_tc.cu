@@ -61,8 +61,11 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + BM - 1) / BM;
-  const int split = blockIdx.x / q_tiles;
-  const int q0 = (blockIdx.x - split * q_tiles) * BM, h = blockIdx.y, b = blockIdx.z;
+  // causal: the query tiles with the most key tiles are issued first (blocks are scheduled in blockIdx order; with the light tiles first the
+  // heaviest blocks formed the tail: Phi-3 prefill 66 -> 53 us)
+  const int bx = p.causal ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  const int split = bx / q_tiles;
+  const int q0 = (bx - split * q_tiles) * BM, h = blockIdx.y, b = blockIdx.z;
   const int off = p.Nk - p.Nq;
   int k_begin = 0, k_end = p.Nk;
   if (p.causal) k_end = min(p.Nk, q0 + BM + off);

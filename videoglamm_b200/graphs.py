@@ -14,6 +14,7 @@ Cache policy (real eval sets vary in frame count, resolution, [SEG] count and pr
 from __future__ import annotations
 
 import collections
+import gc
 import os
 import threading
 
@@ -80,8 +81,17 @@ class GraphedStage:
                 self.pool = torch.cuda.graph_pool_handle()
             g = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
-            with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
-                out = fn(**static)
+            # A garbage collection inside the capture may destroy an unreachable CUDAGraph of an earlier engine (cudaGraphExecDestroy is not
+            # permitted while this thread captures and invalidates the capture): collect before, keep the collector off until the capture ends.
+            gc_on = gc.isenabled()
+            gc.collect()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, pool=self.pool, capture_error_mode="thread_local"):
+                    out = fn(**static)
+            finally:
+                if gc_on:
+                    gc.enable()
             for t, sv in zip(mutable_state, saved):
                 t.copy_(sv)
             ent = (g, static, out, ops.launch_count() - n0)
