@@ -61,11 +61,17 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = (p.Nq + BM - 1) / BM;
-  // causal: the query tiles with the most key tiles are issued first (blocks are scheduled in blockIdx order; with the light tiles first the
-  // heaviest blocks formed the tail: Phi-3 prefill 66 -> 53 us)
-  const int bx = p.causal ? static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x) : static_cast<int>(blockIdx.x);
+  // causal: the query tiles with the most key tiles of EVERY head are issued first (blocks are scheduled in blockIdx order; with the light
+  // tiles first the heaviest blocks formed the tail: Phi-3 prefill 66 -> 53 us)
+  int bx = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.causal) {   // 1-D launch: block i = (query tile, descending) x (head, batch)
+    const int hbn = p.H * p.B, xr = static_cast<int>(blockIdx.x) / hbn, r = static_cast<int>(blockIdx.x) - xr * hbn;
+    bx = q_tiles * p.nsplit - 1 - xr;
+    b = r / p.H;
+    h = r - b * p.H;
+  }
   const int split = bx / q_tiles;
-  const int q0 = (bx - split * q_tiles) * BM, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = (bx - split * q_tiles) * BM;
   const int off = p.Nk - p.Nq;
   int k_begin = 0, k_end = p.Nk;
   if (p.causal) k_end = min(p.Nk, q0 + BM + off);
@@ -365,8 +371,13 @@ flash_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_pairs = (p.Nq + 2 * BM - 1) / (2 * BM);
-  const int pair = q_pairs - 1 - static_cast<int>(blockIdx.x);   // heaviest (causal) pairs first
-  const int h = blockIdx.y, b = blockIdx.z;
+  int pair = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  if (p.causal) {   // 1-D launch: heaviest pairs of every (head, batch) first
+    const int hbn = p.H * p.B, xr = static_cast<int>(blockIdx.x) / hbn, r = static_cast<int>(blockIdx.x) - xr * hbn;
+    pair = q_pairs - 1 - xr;
+    b = r / p.H;
+    h = r - b * p.H;
+  }
   const int off = p.Nk - p.Nq;
   // key range of each tile of the pair, and the union the K/V ring walks
   int q0x[2], jb[2], je[2];
@@ -753,6 +764,7 @@ static int launch_tc(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
   }
   const int q_tiles = (a->Nq + 127) / 128;
   dim3 grid(q_tiles * p.nsplit, a->H, a->B);
+  if (p.causal) grid = dim3(q_tiles * p.nsplit * a->H * a->B, 1, 1);
   launch_k(flash_attn_tc_kernel<BN, MINB>, dim3(grid), dim3(256), smem, s, tq, tk, tv, p);
   count_launch();
   return check_launch("flash_attn_tc_kernel");
@@ -791,6 +803,7 @@ static int launch_tc2(const VgAttention* a, AttnTcParams& p, cudaStream_t s) {
   }
   const int q_pairs = (a->Nq + 255) / 256;
   dim3 grid(q_pairs, a->H, a->B);
+  if (p.causal) grid = dim3(q_pairs * a->H * a->B, 1, 1);
   launch_k(flash_attn_tc2_kernel<BN>, dim3(grid), dim3(384), smem, s, tq, tk, tv, p, kst);
   count_launch();
   return check_launch("flash_attn_tc2_kernel");
