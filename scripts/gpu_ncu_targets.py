@@ -12,6 +12,10 @@ is taken from this run). Order (= ncu launch ids):
  10 attn  Hiera stage-3 window 128 windows x 256 tokens x 8 heads x 72
  11 attn  Hiera stage-2 window 8192 windows x 16 tokens x 4 heads x 72 (window_attn_small_kernel)
  12 attn  Phi-3 decode         1 query x 1709 keys, 32 heads x 96
+ 13 gemv  batched decode gu    4 x 16384 x 3072     fused RMSNorm + SwiGLU (gemv_ring_mma_kernel)
+ 14 gemv  batched decode down  4 x 3072 x 8192      residual (gemv_ring_mma_kernel)
+ 15, 16   fused SAM2 mask decoder HW = 4096, B = 1 (split-bf16 tensor-core variant, then fp32-FMA variant)
+Run under `ncu -k regex:"gemm_tcgen05|gemv_|flash_attn|window_attn|attn_decode|mask_decoder"` so that only these launches are profiled.
 """
 import sys, torch
 sys.path.insert(0, ".")
@@ -63,4 +67,27 @@ q1 = torch.randn(1, 3 * D, device=dev).bfloat16()[:, :D].unflatten(1, (H, hd))[N
 ops.attention(q1, cache[:2048, D:2 * D].unflatten(1, (H, hd))[None], cache[:2048, 2 * D:].unflatten(1, (H, hd))[None], scale=hd ** -0.5, causal=True, window=2047,
               nk_dev=nk, decode_ws=ws)
 torch.cuda.synchronize()
-# the fused SAM2 mask decoder is captured separately: scripts/gpu_ncu_mask_decoder.py under `ncu -k regex:mask_decoder_kernel`
+def run_m(M, N, K, **kw):
+    a = torch.randn(M, K, device=dev).to(torch.float32 if kw.get("rms") else BF); w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    extra = {"a_rms_eps": 1e-5} if kw.get("rms") else {}
+    if kw.get("glu"): extra.update(glu=True, act="silu")
+    out = torch.randn(M, N // 2 if kw.get("glu") else N, device=dev).to(kw.get("od", BF))
+    if kw.get("resid"): extra["resid"] = out
+    ops.gemm(a, w, out=out, **extra)
+    torch.cuda.synchronize()
+run_m(4, 16384, 3072, glu=True, rms=True)
+run_m(4, 3072, 8192, resid=True, od=torch.float32)
+# the fused SAM2 mask decoder at full size (HW = 4096 -> 128 row blocks, B = 1 object, 9 tokens): tensor-core variant, then fp32-FMA variant
+from videoglamm_b200.config import Sam2Config
+from videoglamm_b200.sam2_engine import Sam2Engine
+from videoglamm_b200.statedict import random_state_dict, sam2_param_shapes
+cfg = Sam2Config()
+eng = Sam2Engine(random_state_dict(sam2_param_shapes(cfg), dev, seed=1), cfg, dev)
+HW = eng.HW
+pix = torch.randn(HW, 256, device=dev); s0 = torch.randn(16 * HW, 32, device=dev); s1 = torch.randn(4 * HW, 64, device=dev); sp = torch.randn(1, 3, 256, device=dev)
+torch.cuda.synchronize()
+eng.mask_decoder(pix, s0, s1, sp)
+torch.cuda.synchronize()
+eng.fused_exact = True
+eng.mask_decoder(pix, s0, s1, sp)
+torch.cuda.synchronize()
