@@ -16,8 +16,8 @@ from dataclasses import dataclass
 import torch
 
 from . import ops
-from .graphs import GraphedStage
 from .config import ClipConfig, Iv2Config, LmmConfig, PhiConfig
+from .graphs import GraphedStage, MAX_ENTRIES as _GRAPH_MAX
 
 BF, F32 = torch.bfloat16, torch.float32
 IMAGE_TOKEN_INDEX = -200
@@ -198,7 +198,8 @@ class LmmEngine:
             self.layers.append(dict(qkv=qkv, o=pk.lin(p + ".self_attn.o_proj"), gu=pk.mk(gu * n2[None], None), down=pk.lin(p + ".mlp.down_proj")))
         self.kv = None  # per-layer packed qkv cache [max_len, 3*hidden] bf16 (q rows are scratch)
         # graph-captured stages + the device-side decode state they read (token, position, key count, qkv scratch row)
-        self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill"), GraphedStage("decode")
+        # prefill graphs are keyed by (prompt length, KV-cache slot): a decode batch of 8 alone needs 8 live entries
+        self.g_vis, self.g_prefill, self.g_decode = GraphedStage("visual_tokens"), GraphedStage("prefill", max_entries=2 * _GRAPH_MAX + 8), GraphedStage("decode")
         self.g_decode_batch = GraphedStage("decode_batch")
         # batched decode: S <= 8 sequences stream the weights through the multi-row TMA-ring kernel (csrc/gemv_ring.cu: mma.sync on fp32 activations
         # split hi + lo, fused RMSNorm: the single-sequence step's arithmetic up to summation order). S >= batch_tc_min (none by default) goes through
