@@ -140,3 +140,29 @@ def test_batched_decode_equals_per_clip_generation():
         for t in seg_a:
             for o in seg_a[t]:
                 assert np.array_equal(seg_a[t][o], seg_b[t][o])
+
+
+def test_batched_towers_and_prefill_for_equally_shaped_clips():
+    """Equally shaped clips with equally long prompts: generate_batch runs ONE pass of the vision towers over all frames and ONE batched prefill into
+    cache slots 0..S-1 (`_prefill_last_multi`); tokens and [SEG] embeddings equal per-clip generation (eager first sight, capture, replay)."""
+    from oracle import lmm as M, weights as Wt
+    from videoglamm_b200.config import make_lmm_config
+    from videoglamm_b200.lmm_engine import LmmEngine
+    seg = 300
+    ocfg = M.make_cfg(**M.TINY_LMM, seg_token_idx=seg)
+    sd = Wt.make_lmm_state_dict(ocfg, seed=11)
+    eng = LmmEngine(sd, make_lmm_config(**M.TINY_LMM, seg_token_idx=seg))
+    reqs = []
+    for i in range(3):
+        g = torch.Generator().manual_seed(80 + i)
+        images, ctx = torch.randn(4, 3, 56, 56, generator=g), torch.randn(4, 3, 56, 56, generator=g)
+        ids = torch.cat([torch.randint(3, 290, (5,), generator=g), torch.full((4,), -200), torch.randint(3, 290, (9,), generator=g)])[None]
+        reqs.append((ids.cuda(), images.cuda(), ctx.cuda()))
+    forced = {2: seg, 6: seg}
+    single = [eng.generate(*r, 10, forced=forced) for r in reqs]
+    for rep in range(3):
+        batch = eng.generate_batch(reqs, 10, forced=forced)
+        for (ia, ea), (ib, eb) in zip(single, batch):
+            assert torch.equal(ia, ib)
+            assert ea.shape == eb.shape and ((ea - eb).norm() / ea.norm().clamp_min(1e-9)).item() < 1e-5
+    assert any(k[1] == "multi" for k in list(eng.g_prefill.entries) + list(eng.g_prefill.seen) if len(k) == 3)

@@ -228,9 +228,10 @@ class LmmEngine:
             h = ops.gemm(h, L.W(P), bias=L.b, act=None if last else "gelu", out_dtype=F32 if (last or P) else BF)
         return h
 
-    def visual_tokens(self, images: torch.Tensor, context_images: torch.Tensor) -> torch.Tensor:
+    def visual_tokens(self, images: torch.Tensor, context_images: torch.Tensor, clips: int = 1) -> torch.Tensor:
         """encode_videos model/videogpt_plus/model/arch.py:121-151 + project(input_type="video") :164-191:
-        -> fp32 [T*(gc/2)^2 + T*(gv/2)^2, hidden], context block first."""
+        -> fp32 [T*(gc/2)^2 + T*(gv/2)^2, hidden], context block first. clips > 1: the frames of that many equally shaped clips stacked along
+        dim 0 (one pass of the towers with 8x the rows fills the GEMM waves better: 11.4 -> 9.3 ms per clip at 8 clips) -> [clips, tokens, hidden]."""
         cfg = self.cfg
         T = images.shape[0]
         assert T % cfg.iv2.frames == 0, "encoder frames must be a multiple of CHUNK_SIZE=4 (arch.py:133)"
@@ -241,6 +242,8 @@ class LmmEngine:
         v = ops.pool2x2(v, T, gv, gv, is_max=False)
         c = self._project(ctx, self.ctx_proj)
         c = ops.pool2x2(c, T, gc, gc, is_max=False)
+        if clips > 1:                                               # frames of `clips` clips stacked: [clips, tokens per clip, hidden]
+            return torch.cat([c.view(clips, -1, c.shape[1]), v.view(clips, -1, v.shape[1])], 1)
         return torch.cat([c, v], 0)
 
     def image_tokens(self, image: torch.Tensor) -> torch.Tensor:
@@ -379,6 +382,33 @@ class LmmEngine:
             return x[-1:].contiguous()                      # un-normalised residual row: the consumers fuse the final norm
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
 
+    def _prefill_last_multi(self, x: torch.Tensor) -> torch.Tensor:
+        """Prefill of S equally long prompts at once into cache slots 0..S-1: x fp32 [S, n, hidden] -> the un-normalised last residual row of every
+        sequence [S, hidden]. Everything runs on the flattened [S*n, hidden] rows (the N = 3072 projections of ONE 1696-token prompt are 224
+        tiles = 1.5 waves of 148 SMs; eight prompts are 12 waves) except the qkv projection, a batched GEMM that writes the rows of every
+        sequence straight into its cache slot, RoPE (per slot) and attention (batch dimension = slot). Same arithmetic per element as `_llm`."""
+        ph = self.cfg.phi
+        S, n, _ = x.shape
+        H, hd, D = ph.heads, ph.head_dim, ph.hidden
+        pos = torch.arange(0, n, device=self.dev, dtype=torch.int32)
+        x = x.reshape(S * n, D)
+        for l, L in enumerate(self.layers):
+            cache = self.kv_slots[l]
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=BF)
+            rows = cache[:S, :n]                                                     # [S, n, 3*hidden], batch stride = one cache slot
+            ops.gemm(h.view(S, n, D), L["qkv"].w, out=rows)
+            for s in range(S):
+                ops.rope_neox_(rows[s], pos, 2 * H, hd, ph.rope_theta)
+            q = rows[:, :, :D].unflatten(2, (H, hd))
+            k = rows[:, :, D:2 * D].unflatten(2, (H, hd))
+            v = rows[:, :, 2 * D:].unflatten(2, (H, hd))
+            o = ops.attention(q, k, v, scale=hd ** -0.5, causal=True, window=ph.sliding_window or 0)
+            x = ops.gemm(o.view(S * n, D), L["o"].w, resid=x, out=x)
+            h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=BF)
+            h = ops.gemm(h, L["gu"].w, glu=True, act="silu", out_dtype=BF)
+            x = ops.gemm(h, L["down"].w, resid=x, out=x)
+        return x.view(S, n, D)[:, -1].contiguous()
+
     def _logits_argmax(self, x_last: torch.Tensor) -> torch.Tensor:
         """final RMSNorm (fused, weight folded into lm_head) -> lm_head -> argmax on one residual row [1, hidden] fp32."""
         if self.P:
@@ -413,15 +443,25 @@ class LmmEngine:
             return [self.generate(*requests[0], max_new_tokens, eos_ids=eos_ids, forced=forced)]
         ph = cfg.phi
         xs = []
-        for ids, images, ctx in requests:
-            if ctx is None:
-                vis = self.g_vis((tuple(images.shape), None), self.image_tokens, image=images)
-            else:
-                vis = self.g_vis((tuple(images.shape), tuple(ctx.shape)), self.visual_tokens, images=images, context_images=ctx)
-            xs.append(self.embed_prompt(ids, vis))
+        same_vis = all(r[2] is not None and r[1].shape == requests[0][1].shape and r[2].shape == requests[0][2].shape for r in requests)
+        if same_vis:                                            # equally shaped clips: ONE pass of the towers over all their frames
+            im_all, ctx_all = torch.cat([r[1] for r in requests], 0), torch.cat([r[2] for r in requests], 0)
+            vis_all = self.g_vis((tuple(im_all.shape), tuple(ctx_all.shape), S), lambda images, context_images: self.visual_tokens(images, context_images, clips=S),
+                                 images=im_all, context_images=ctx_all)
+            xs = [self.embed_prompt(ids, vis_all[s]) for s, (ids, _, _) in enumerate(requests)]
+        else:
+            for ids, images, ctx in requests:
+                if ctx is None:
+                    vis = self.g_vis((tuple(images.shape), None), self.image_tokens, image=images)
+                else:
+                    vis = self.g_vis((tuple(images.shape), tuple(ctx.shape)), self.visual_tokens, images=images, context_images=ctx)
+                xs.append(self.embed_prompt(ids, vis))
         L0 = [x.shape[0] for x in xs]
         self._alloc_cache(max(L0) + max_new_tokens + 1, slots=S)
-        x_last = torch.cat([self.g_prefill((x.shape[0], s), lambda x, s=s: self._prefill_last(x, slot=s), x=x).clone() for s, x in enumerate(xs)], 0)   # [S, hidden]
+        if len(set(L0)) == 1:                                   # equally long prompts: one batched prefill into slots 0..S-1
+            x_last = self.g_prefill((L0[0], "multi", S), self._prefill_last_multi, x=torch.stack(xs, 0)).clone()
+        else:
+            x_last = torch.cat([self.g_prefill((x.shape[0], s), lambda x, s=s: self._prefill_last(x, slot=s), x=x).clone() for s, x in enumerate(xs)], 0)   # [S, hidden]
         if S not in self._batch_state:
             self._batch_state[S] = dict(tok=torch.zeros(S, device=self.dev, dtype=torch.int64), pos=torch.zeros(S, device=self.dev, dtype=torch.int32),
                                         nk=torch.zeros(S, device=self.dev, dtype=torch.int32), qkv=torch.zeros((S, 3 * ph.hidden), device=self.dev, dtype=BF),
