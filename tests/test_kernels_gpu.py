@@ -272,6 +272,12 @@ def test_dwconv_conv3x3_bilinear():
     ref = F.conv2d(x, W, b, padding=3, groups=c).permute(0, 2, 3, 1).reshape(-1, c)
     y = ops.dwconv(x.permute(0, 2, 3, 1).reshape(-1, c).contiguous(), W.reshape(c, 7, 7).contiguous(), b, n, h, w, 7)
     assert rel(y, ref) < 1e-5
+    for hh, ww, cc, od in ((5, 12, 256, torch.bfloat16), (64, 64, 256, torch.float32), (7, 6, 8, torch.float32)):   # vector path (w % 4 == 0) / scalar fallback
+        xx = torch.randn(3, cc, hh, ww, device=DEV)
+        WW, bb = torch.randn(cc, 1, 7, 7, device=DEV), torch.randn(cc, device=DEV)
+        rr = F.conv2d(xx, WW, bb, padding=3, groups=cc).permute(0, 2, 3, 1).reshape(-1, cc)
+        yy = ops.dwconv(xx.permute(0, 2, 3, 1).reshape(-1, cc).contiguous(), WW.reshape(cc, 7, 7).contiguous(), bb, 3, hh, ww, 7, out_dtype=od)
+        assert yy.dtype == od and rel(yy, rr) < (4e-3 if od == torch.bfloat16 else 1e-5)
     for cin in (1, 4, 16, 64):
         cout = cin * 4
         x = torch.randn(n, cin, h, w, device=DEV)

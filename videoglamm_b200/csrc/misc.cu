@@ -373,6 +373,68 @@ __global__ void dwconv_kernel(const void* x, int xdt, const float* wt, const flo
   st(y, ydt, i, acc);
 }
 
+// fp32 channels-last depthwise KxK: a thread owns 4 channels x PX consecutive pixels of one row: per kernel row it loads the PX + K - 1 input
+// float4s once and slides the K taps over them in registers (the scalar kernel above: 49 dependent loads per output, 68 us for the 64x64x256
+// maps of the SAM2 memory fuser).
+template <int K, int PX>
+__global__ void dwconv_vec_kernel(const float* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias, void* y, int ydt, int n, int h, int w,
+                                  int c) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int R = K / 2;
+  const int cgs = c >> 2, xts = w / PX;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(n) * h * xts * cgs) return;
+  const int cg = static_cast<int>(idx % cgs);
+  long long t = idx / cgs;
+  const int xt = static_cast<int>(t % xts);
+  t /= xts;
+  const int py = static_cast<int>(t % h);
+  const int img = static_cast<int>(t / h);
+  const int ch = cg * 4, px0 = xt * PX;
+  float4 acc[PX];
+  const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < PX; ++p) acc[p] = b4;
+#pragma unroll 1
+  for (int ky = 0; ky < K; ++ky) {
+    const int iy = py + ky - R;
+    if (iy < 0 || iy >= h) continue;
+    const float* xr = x + (static_cast<long long>(img) * h + iy) * w * c + ch;
+    float4 row[PX + K - 1];
+#pragma unroll
+    for (int q = 0; q < PX + K - 1; ++q) {
+      const int ix = px0 + q - R;
+      row[q] = (ix >= 0 && ix < w) ? *reinterpret_cast<const float4*>(xr + static_cast<long long>(ix) * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float wk[4][K];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) wk[j][kx] = __ldg(wt + ((ch + j) * K + ky) * K + kx);
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+      for (int p = 0; p < PX; ++p) {
+        acc[p].x = fmaf(row[p + kx].x, wk[0][kx], acc[p].x);
+        acc[p].y = fmaf(row[p + kx].y, wk[1][kx], acc[p].y);
+        acc[p].z = fmaf(row[p + kx].z, wk[2][kx], acc[p].z);
+        acc[p].w = fmaf(row[p + kx].w, wk[3][kx], acc[p].w);
+      }
+  }
+  const long long o0 = ((static_cast<long long>(img) * h + py) * w + px0) * c + ch;
+#pragma unroll
+  for (int p = 0; p < PX; ++p) {
+    if (ydt == VG_F32) {
+      *reinterpret_cast<float4*>(static_cast<float*>(y) + o0 + static_cast<long long>(p) * c) = acc[p];
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(acc[p].x, acc[p].y), hi = __floats2bfloat162_rn(acc[p].z, acc[p].w);
+      *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + o0 + static_cast<long long>(p) * c) =
+          make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+    }
+  }
+}
+
 // one warp per output pixel; lanes stride over cout (<= 256 -> 8 per lane)
 __global__ void conv3x3s2_ln_gelu_kernel(const void* x, int xdt, const float* wt, const float* bias, const float* ln_w, const float* ln_b,
                                          float eps, void* y, int ydt, int n, int h, int w, int cin, int cout) {
@@ -942,6 +1004,12 @@ extern "C" int vg_im2col(const void* x, int x_dtype, void* out, int out_dtype, i
 extern "C" int vg_dwconv(const void* x, int x_dtype, const float* w, const float* bias, void* y, int y_dtype, int n, int h, int wd, int c, int k,
                          void* stream) {
   if (!x || !w || !y) return set_error(VG_EINVAL, "vg_dwconv: null");
+  if (k == 7 && x_dtype == VG_F32 && c % 4 == 0 && wd % 4 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15)) {
+    const long long threads = static_cast<long long>(n) * h * (wd / 4) * (c / 4);
+    launch_k(dwconv_vec_kernel<7, 4>, dim3(blocks_for(threads, 128)), dim3(128), 0, STREAM, static_cast<const float*>(x), w, bias, y, y_dtype, n, h, wd, c);
+    count_launch();
+    return check_launch("dwconv_vec_kernel");
+  }
   launch_k(dwconv_kernel, dim3(blocks_for(static_cast<long long>(n) * h * wd * c, 256)), dim3(256), 0, STREAM, x, x_dtype, w, bias, y, y_dtype, n, h, wd, c, k);
   count_launch();
   return check_launch("dwconv_kernel");
