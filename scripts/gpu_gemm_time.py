@@ -29,3 +29,8 @@ t(1696, 16384, 3072, glu=True, act="silu")
 t(2050, 1408, 6144, bias=True, resid=True, od=torch.float32)
 t(2050, 6144, 1408, bias=True, act="gelu")
 t(4096, 256, 256, bias=True)
+t(131072, 864, 288, bias=True)
+t(524288, 576, 144, bias=True, act="gelu")
+t(524288, 432, 144, bias=True)
+t(131072, 288, 1152, bias=True, resid=True, od=torch.float32)
+t(32768, 576, 576, bias=True, resid=True, od=torch.float32)
