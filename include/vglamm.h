@@ -170,6 +170,10 @@ int vg_bilinear(const float* x, void* y, int n, int ih, int iw, int oh, int ow, 
  * dim/2 features rotate with x, the rest with y, consecutive (even,odd) pairs are one complex number
  * (position_encoding.py:174-216). Rows [0, nrows). theta 10000. */
 int vg_rope2d(void* x, int x_dtype, long long ld, int nrows, int dim, int gw, int gh, void* stream);
+/* The same rotation from a table: vg_rope2d_table fills table[gw*gh][dim/2] = (cos, sin) pairs (fp32, 2 floats each) once; vg_rope2d_cached
+ * rotates `nblk` adjacent column blocks of width dim of every row (q and k of a packed qkv row in one launch), row r at table position r % period. */
+int vg_rope2d_table(float* table, int dim, int gw, int gh, void* stream);
+int vg_rope2d_cached(void* x, int x_dtype, long long ld, int nrows, int dim, int nblk, const float* table, int period, void* stream);
 /* Phi-3 / Llama rotate-half RoPE in place on q and k slices of a packed qkv tensor [rows][ld] (bf16 / fp32): for each head, pairs (i, i+hd/2).
  * pos[r] is the position of row r. */
 int vg_rope_neox(void* qkv, int x_dtype, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream);

@@ -421,6 +421,21 @@ def test_multi_row_ring_gemv_batched_decode_shapes(M):
     assert rel(buf[:, :N], F.gelu(xn @ w.float().T + bias)) < 4e-3 and float(buf[:, N:].abs().max()) == 0.0
 
 
+def test_rope2d_table_path_equals_direct_kernel():
+    """vg_rope2d_cached (table of (cos, sin) filled once, q and k column blocks in one launch, rows wrapping around the grid period) produces the
+    bits of vg_rope2d."""
+    gw = gh = 8
+    C = 64
+    table = ops.rope2d_table(C, gw, gh, DEV)
+    for dt in (torch.bfloat16, torch.float32):
+        x = torch.randn(3 * gw * gh + 5, 3 * C + 8, device=DEV).to(dt)
+        a, b = x.clone(), x.clone()
+        ops.rope2d_(a[:, :C], C, gw, gh)
+        ops.rope2d_(a[:, C:2 * C], C, gw, gh)
+        ops.rope2d_(b[:, :2 * C], C, gw, gh, table=table, nblk=2)
+        assert torch.equal(a, b) and not torch.equal(a[:, :2 * C], x[:, :2 * C]) and torch.equal(a[:, 2 * C:], x[:, 2 * C:])
+
+
 def test_rope_kv_append_and_fused_merge_decode_attention():
     H, hd, max_len = 8, 96, 2100
     D = H * hd

@@ -680,6 +680,40 @@ __global__ void rope2d_kernel(void* x, int xdt, long long ld, int nrows, int dim
   st(x, xdt, e + 1, a * sn + b * cs);
 }
 
+// The same rotation with the (cos, sin) of every (grid position, pair) read from a table filled once by rope2d_table_kernel (the same powf /
+// sincosf, so the bits are those of rope2d_kernel): the per-element transcendental functions made the 4096 x 256 calls of the SAM2 memory attention
+// ~10 us each, 112 per clip. `nblk` adjacent column blocks of width dim (q and k of a packed qkv row) share one launch.
+__global__ void rope2d_table_kernel(float2* table, int dim, int gw, int gh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2, quarter = dim / 4;
+  if (i >= gw * gh * half) return;
+  const int pr = i % half, r = i / half;
+  const int px = r % gw, py = (r / gw) % gh;
+  const int fi = pr < quarter ? pr : pr - quarter;
+  const float freq = 1.0f / powf(10000.0f, static_cast<float>(4 * fi) / dim);
+  const float ang = (pr < quarter ? px : py) * freq;
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  table[i] = make_float2(cs, sn);
+}
+
+__global__ void rope2d_cached_kernel(void* x, int xdt, long long ld, int nrows, int dim, int nblk, const float2* __restrict__ table, int period) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= static_cast<long long>(nrows) * half) return;
+  const int pr = static_cast<int>(i % half);
+  const long long r = i / half;
+  const float2 cssn = __ldg(table + (r % period) * half + pr);
+  for (int b = 0; b < nblk; ++b) {
+    const long long e = r * ld + static_cast<long long>(b) * dim + 2 * pr;
+    const float a0 = ld_(x, xdt, e), a1 = ld_(x, xdt, e + 1);
+    st(x, xdt, e, a0 * cssn.x - a1 * cssn.y);
+    st(x, xdt, e + 1, a0 * cssn.y + a1 * cssn.x);
+  }
+}
+
 __global__ void rope_neox_kernel(void* qkv, int xdt, long long ld, const int* pos, int rows, int nheads, int hd, float theta) {
   pdl_wait();  // programmatic dependent launch: inputs belong to the predecessor kernel
   pdl_launch_dependents();
@@ -1058,6 +1092,21 @@ extern "C" int vg_rope2d(void* x, int x_dtype, long long ld, int nrows, int dim,
   launch_k(rope2d_kernel, dim3(blocks_for(static_cast<long long>(nrows) * dim / 2, 256)), dim3(256), 0, STREAM, x, x_dtype, ld, nrows, dim, gw, gh);
   count_launch();
   return check_launch("rope2d_kernel");
+}
+
+extern "C" int vg_rope2d_table(float* table, int dim, int gw, int gh, void* stream) {
+  if (!table || dim % 4) return set_error(VG_EINVAL, "vg_rope2d_table: dim must be a multiple of 4");
+  launch_k(rope2d_table_kernel, dim3(blocks_for(static_cast<long long>(gw) * gh * dim / 2, 256)), dim3(256), 0, STREAM, reinterpret_cast<float2*>(table), dim, gw, gh);
+  count_launch();
+  return check_launch("rope2d_table_kernel");
+}
+
+extern "C" int vg_rope2d_cached(void* x, int x_dtype, long long ld, int nrows, int dim, int nblk, const float* table, int period, void* stream) {
+  if (!x || !table || dim % 4 || nblk < 1 || period < 1) return set_error(VG_EINVAL, "vg_rope2d_cached: bad argument");
+  launch_k(rope2d_cached_kernel, dim3(blocks_for(static_cast<long long>(nrows) * dim / 2, 256)), dim3(256), 0, STREAM, x, x_dtype, ld, nrows, dim, nblk,
+           reinterpret_cast<const float2*>(table), period);
+  count_launch();
+  return check_launch("rope2d_cached_kernel");
 }
 
 extern "C" int vg_rope_neox(void* qkv, int x_dtype, long long ld, const int* pos, int rows, int n_heads_total, int head_dim, float theta, void* stream) {

@@ -355,10 +355,23 @@ def bilinear(x: torch.Tensor, oh: int, ow: int, *, mode: int = 0, scale: float =
     return y
 
 
-def rope2d_(x: torch.Tensor, dim: int, gw: int, gh: int) -> torch.Tensor:
-    """in place on bf16 / fp32 [rows, >=dim] (row stride arbitrary)"""
-    _require_cuda(x)
+def rope2d_table(dim: int, gw: int, gh: int, device) -> torch.Tensor:
+    """(cos, sin) of every (grid position, rotation pair) for rope2d_(..., table=): fp32 [gw*gh, dim/2, 2]"""
+    t = torch.empty((gw * gh, dim // 2, 2), device=device, dtype=torch.float32)
+    L.check(L.lib().vg_rope2d_table(_ptr(t), dim, gw, gh, _stream()), "vg_rope2d_table")
+    return t
+
+
+def rope2d_(x: torch.Tensor, dim: int, gw: int, gh: int, table: torch.Tensor | None = None, nblk: int = 1) -> torch.Tensor:
+    """in place on bf16 / fp32 [rows, >=dim] (row stride arbitrary). With `table` (rope2d_table): table lookup instead of powf / sincosf per
+    element, and `nblk` adjacent column blocks of width dim rotated in one launch (q and k of packed qkv rows)."""
+    _require_cuda(x, table)
     assert x.dim() == 2 and x.stride(1) == 1
+    if table is not None:
+        assert x.shape[1] >= nblk * dim and tuple(table.shape) == (gw * gh, dim // 2, 2)
+        L.check(L.lib().vg_rope2d_cached(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), x.shape[0], dim, nblk, _ptr(table), gw * gh, _stream()), "vg_rope2d_cached")
+        return x
+    assert nblk == 1
     L.check(L.lib().vg_rope2d(_ptr(x), _dt(x.dtype), C.c_longlong(x.stride(0)), x.shape[0], dim, gw, gh, _stream()), "vg_rope2d")
     return x
 

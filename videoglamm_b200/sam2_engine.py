@@ -123,6 +123,7 @@ class Sam2Engine:
         fs = cfg.feat_size
         self.HW = fs * fs
         self.pos_top = self._sine_pos(fs, fs, C)              # [HW, C] vision_pos_enc of the top level
+        self.rope_table = ops.rope2d_table(C, fs, fs, self.dev)   # (cos, sin) of the memory attention's axial RoPE, filled once
         self.pos_mem = self._sine_pos(fs, fs, cfg.mem_dim)    # [HW, mem_dim] maskmem_pos_enc
         tpos = self._t("maskmem_tpos_enc").reshape(cfg.num_maskmem, cfg.mem_dim)
         self.mem_pos_slot = (self.pos_mem[None] + tpos[:, None]).contiguous()  # [7, HW, mem_dim] (sam2_base.py:577-581)
@@ -484,18 +485,17 @@ class Sam2Engine:
         for L in self.ma_layers:
             t = ops.norm(x, *L["n1"], eps=1e-5, out_dtype=adt)
             qkv = ops.gemm(t, L["qkv"].W(P), bias=L["qkv"].b, out_dtype=adt)                               # [B*HW, 3C]
-            ops.rope2d_(qkv[:, :C], C, fs, fs)
-            ops.rope2d_(qkv[:, C:2 * C], C, fs, fs)
+            ops.rope2d_(qkv[:, :2 * C], C, fs, fs, table=self.rope_table, nblk=2)                         # q and k in one launch
             q, k, v = (qkv[:, j * C:(j + 1) * C].view(B, HW, 1, C) for j in range(3))
             o = ops.attention(q, k, v, scale=C ** -0.5)
             x = ops.gemm(o.view(B * HW, C), L["sa_out"].W(P), bias=L["sa_out"].b, resid=x, out=x, out_dtype=F32)
             t = ops.norm(x, *L["n2"], eps=1e-5, out_dtype=adt)
             ca = L["ca"]
             q = ops.gemm(t, ca["q"].W(P), bias=ca["q"].b, out_dtype=adt)
-            ops.rope2d_(q, C, fs, fs)
+            ops.rope2d_(q, C, fs, fs, table=self.rope_table)
             kk = ops.gemm(k_in, ca["k"].W(P), bias=ca["k"].b, out_dtype=adt).view(B, Nk, C)
             for b in range(B):
-                ops.rope2d_(kk[b, :n_rope], C, fs, fs)                                                    # rope_k_repeat: position = row % HW
+                ops.rope2d_(kk[b, :n_rope], C, fs, fs, table=self.rope_table)                             # rope_k_repeat: position = row % HW
             vv = ops.gemm(mem2, ca["v"].W(P), bias=ca["v"].b, out_dtype=adt)
             o = ops.attention(q.view(B, HW, 1, C), kk.view(B, Nk, 1, C), vv.view(B, Nk, 1, C), scale=C ** -0.5)
             x = ops.gemm(o.view(B * HW, C), ca["out"].W(P), bias=ca["out"].b, resid=x, out=x, out_dtype=F32)
