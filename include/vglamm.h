@@ -52,6 +52,9 @@ void vg_launch_count_reset(void);
  * Requirements: lda, ldb multiples of 8; A, B 16-byte aligned; K >= 1 (K tail zero-filled by TMA).
  * batch > 1 with strideB == 0 shares one B (weights) across all batch entries.
  * With glu != 0 the N columns are interleaved [16 gate | 16 up] per 32 and the output has N/2 columns.
+ * M <= 8 (LLM decode, one row per decoding sequence) is HBM-bound weight streaming and leaves the tcgen05 path: M == 1 -> gemv_ring_kernel
+ * (cp.async.bulk rings, fp32 FMA), 2 <= M <= 8 -> gemv_ring_mma_kernel (the same rings feeding mma.sync, every weight row streamed once for all
+ * rows), shapes those decline (N_out < 1024, K not a multiple of 512) -> gemv_kernel; force_block_n != 0 keeps M <= 8 on the tcgen05 kernel.
  */
 typedef struct VgGemm {
   const void* A; long long lda; long long strideA; /* bf16 [batch][M][lda]   */
@@ -85,8 +88,9 @@ int vg_gemm_naive(const VgGemm* g, void* stream);
  * Replaces F.scaled_dot_product_attention at .../backbones/hieradet.py:72-76, .../sam/transformer.py:249-255,316-322,
  * InternVideo2 _naive_attn (internvideo2.py:190-209), HF CLIP / Phi-3 attention (called from clip_encoder.py:45-72, phi3.py:72-81).
  * Requirements: D % 8 == 0, D <= 256; q/k/v strides multiples of 8 elements, 16-byte aligned bases.
- * Kernels: dense problems with Nq, Nk >= 128 run on the tcgen05 kernel (attention_tc.cu: TMA -> smem -> tcgen05.mma, S and O in TMEM);
- * windowed / sliding-window / tiny problems use the mma.sync kernel; Nq == 1 uses the split-K decode kernel.
+ * Kernels: problems with Nq, Nk >= 128 (dense, causal, causal + sliding window, 16x16 Hiera windows) run on the tcgen05 kernels
+ * (attention_tc.cu: TMA -> smem -> tcgen05.mma, S and O in TMEM; two query tiles per block when D <= 128 and the problem is >= 1024 blocks deep);
+ * pooled-query windows and tiny problems use the mma.sync kernels; Nq == 1 uses the split-K decode kernel.
  */
 typedef struct VgAttention {
   const void *q, *k, *v; void* o;
