@@ -267,9 +267,21 @@ class LmmEngine:
             for g in (self.g_prefill, self.g_decode, self.g_decode_batch):
                 g.clear()
 
-    def _prefill_last(self, x: torch.Tensor, slot: int = 0) -> torch.Tensor:
-        """Prefill rows [0, n); returns the final-norm hidden state of the LAST row only ([1, hidden] fp32) — all that decoding needs."""
-        return self._llm(x, 0, last_only=True, slot=slot)
+    PREFILL_BUCKET = 64   # prompts are zero-padded to a multiple of this many rows: graph keys (and batched-prefill groups) per bucket, not per length
+
+    def _bucket(self, n: int) -> int:
+        return -(-n // self.PREFILL_BUCKET) * self.PREFILL_BUCKET
+
+    @staticmethod
+    def _pad_rows(x: torch.Tensor, n: int) -> torch.Tensor:
+        return x if x.shape[0] == n else torch.cat([x, x.new_zeros((n - x.shape[0], x.shape[1]))], 0)
+
+    def _prefill_last(self, x: torch.Tensor, slot: int = 0, last: torch.Tensor | None = None) -> torch.Tensor:
+        """Prefill rows [0, n); returns the un-normalised residual of the LAST real row only ([1, hidden] fp32) — all that decoding needs. `last`
+        (int64 [1], device): index of that row when x carries zero rows behind the prompt (bucketed length: under causal attention the pad rows
+        change nothing in front of them, and the decode steps overwrite their cache rows)."""
+        xr = self._llm(x, 0, raw=True, slot=slot)
+        return xr[-1:].contiguous() if last is None else xr.index_select(0, last)
 
     @staticmethod
     def _ksplit(K: int, want: int) -> int:
@@ -382,9 +394,9 @@ class LmmEngine:
             return x[-1:].contiguous()                      # un-normalised residual row: the consumers fuse the final norm
         return ops.norm(x, self.final_norm, eps=ph.eps, rms=True, out_dtype=F32)
 
-    def _prefill_last_multi(self, x: torch.Tensor) -> torch.Tensor:
-        """Prefill of S equally long prompts at once into cache slots 0..S-1: x fp32 [S, n, hidden] -> the un-normalised last residual row of every
-        sequence [S, hidden]. Everything runs on the flattened [S*n, hidden] rows (the N = 3072 projections of ONE 1696-token prompt are 224
+    def _prefill_last_multi(self, x: torch.Tensor, last: torch.Tensor) -> torch.Tensor:
+        """Prefill of S prompts of one length bucket at once into cache slots 0..S-1: x fp32 [S, n, hidden] (zero rows behind the shorter prompts),
+        last int64 [S] = index of the last real row of every sequence -> its un-normalised residual row [S, hidden]. Everything runs on the flattened [S*n, hidden] rows (the N = 3072 projections of ONE 1696-token prompt are 224
         tiles = 1.5 waves of 148 SMs; eight prompts are 12 waves) except the qkv projection, a batched GEMM that writes the rows of every
         sequence straight into its cache slot, RoPE (per slot) and attention (batch dimension = slot). Same arithmetic per element as `_llm`."""
         ph = self.cfg.phi
@@ -407,7 +419,7 @@ class LmmEngine:
             h = ops.norm(x, self.ones, eps=ph.eps, rms=True, out_dtype=BF)
             h = ops.gemm(h, L["gu"].w, glu=True, act="silu", out_dtype=BF)
             x = ops.gemm(h, L["down"].w, resid=x, out=x)
-        return x.view(S, n, D)[:, -1].contiguous()
+        return x.index_select(0, last + torch.arange(S, device=self.dev, dtype=torch.int64) * n)   # row last[s] of sequence s (pad rows follow it)
 
     def _logits_argmax(self, x_last: torch.Tensor) -> torch.Tensor:
         """final RMSNorm (fused, weight folded into lm_head) -> lm_head -> argmax on one residual row [1, hidden] fp32."""
@@ -457,11 +469,14 @@ class LmmEngine:
                     vis = self.g_vis((tuple(images.shape), tuple(ctx.shape)), self.visual_tokens, images=images, context_images=ctx)
                 xs.append(self.embed_prompt(ids, vis))
         L0 = [x.shape[0] for x in xs]
-        self._alloc_cache(max(L0) + max_new_tokens + 1, slots=S)
-        if len(set(L0)) == 1:                                   # equally long prompts: one batched prefill into slots 0..S-1
-            x_last = self.g_prefill((L0[0], "multi", S), self._prefill_last_multi, x=torch.stack(xs, 0)).clone()
+        Lb = [self._bucket(n) for n in L0]
+        self._alloc_cache(max(max(Lb), max(L0) + max_new_tokens + 1), slots=S)
+        last = torch.tensor([n - 1 for n in L0], device=self.dev, dtype=torch.int64)
+        if len(set(Lb)) == 1:                                   # prompts of one length bucket: one batched prefill into slots 0..S-1
+            x_last = self.g_prefill((Lb[0], "multi", S), self._prefill_last_multi, x=torch.stack([self._pad_rows(x, Lb[0]) for x in xs], 0), last=last).clone()
         else:
-            x_last = torch.cat([self.g_prefill((x.shape[0], s), lambda x, s=s: self._prefill_last(x, slot=s), x=x).clone() for s, x in enumerate(xs)], 0)   # [S, hidden]
+            x_last = torch.cat([self.g_prefill((Lb[s], s), lambda x, last, s=s: self._prefill_last(x, slot=s, last=last), x=self._pad_rows(x, Lb[s]),
+                                               last=last[s:s + 1]).clone() for s, x in enumerate(xs)], 0)   # [S, hidden]
         if S not in self._batch_state:
             self._batch_state[S] = dict(tok=torch.zeros(S, device=self.dev, dtype=torch.int64), pos=torch.zeros(S, device=self.dev, dtype=torch.int32),
                                         nk=torch.zeros(S, device=self.dev, dtype=torch.int32), qkv=torch.zeros((S, 3 * ph.hidden), device=self.dev, dtype=BF),
@@ -525,7 +540,10 @@ class LmmEngine:
         elif self.P:
             x_last = self._prefill_last(x)
         else:
-            x_last = self.g_prefill((L0,), self._prefill_last, x=x)
+            Lb = self._bucket(L0)
+            self._alloc_cache(max(Lb, L0 + max_new_tokens + 1))
+            x_last = self.g_prefill((Lb,), lambda x, last: self._prefill_last(x, last=last), x=self._pad_rows(x, Lb),
+                                    last=torch.tensor([L0 - 1], device=self.dev, dtype=torch.int64))
         new_ids, seg_hidden = [], []
         kv_bound = min(self.kv[0].shape[0], (L0 + max_new_tokens + 511) // 512 * 512)
         nxt_dev = self._logits_argmax(x_last)
