@@ -538,10 +538,14 @@ class Sam2Engine:
         per-frame [n_obj, H, W] tensors (views of graph-owned memory, valid until the next call with the same shapes)."""
         if collect is not None:
             return self._run_video(images, text_embeds, video_hw, binary, collect)
-        key = (tuple(images.shape), tuple(text_embeds.shape), tuple(video_hw), binary, images.dtype)
-        out = self.g_video(key, lambda images, text_embeds: torch.stack(self._run_video(images, text_embeds, video_hw, binary, None)),
+        # the graph ends at the low-res mask logits [T, n_obj, 4fs, 4fs]; the upsampling to the video's own resolution (one launch for all planes)
+        # stays outside, so that neither the resolution nor the output format is part of the key: eval sets change resolution per video
+        key = (tuple(images.shape), tuple(text_embeds.shape), images.dtype)
+        low = self.g_video(key, lambda images, text_embeds: torch.stack(self._run_video(images, text_embeds, None, False, None)),
                            images=images, text_embeds=text_embeds.to(F32))
-        return list(out.unbind(0))
+        T, B, side = low.shape[0], low.shape[1], low.shape[-1]
+        out = ops.bilinear(low.view(T * B, side, side), int(video_hw[0]), int(video_hw[1]), mode=_OUT_MODE[binary])
+        return list(out.view(T, B, *out.shape[1:]).unbind(0))
 
     def _run_video(self, images: torch.Tensor, text_embeds: torch.Tensor, video_hw: tuple, binary: bool | str = False, collect: dict | None = None):
         """The VideoGLaMM video-branch session (VideoGLaMM.py:846-875 -> sam2_video_predictor.py init_state_from_tensor :109-180,
@@ -551,7 +555,7 @@ class Sam2Engine:
         cfg = self.cfg
         T, B = images.shape[0], text_embeds.shape[0]
         HW, C = self.HW, cfg.d_model
-        Hv, Wv = video_hw
+        # video_hw None: return the low-res logits [n_obj, 4fs, 4fs] per frame (run_video upsamples all planes at once outside the graph)
         # no temporal dependence in the image encoder: encode all frames up front, `frames_per_encode` at a time (fills GEMM waves)
         feats = []
         for t0 in range(0, T, self.frames_per_encode):
@@ -583,7 +587,7 @@ class Sam2Engine:
                     non_cond[old].maskmem = None                                   # ring buffer: nothing older is ever read again
             if collect is not None:
                 collect.setdefault("low_res", {})[t] = pred
-            outs.append(ops.bilinear(pred, Hv, Wv, mode=_OUT_MODE[binary]))
+            outs.append(pred if video_hw is None else ops.bilinear(pred, int(video_hw[0]), int(video_hw[1]), mode=_OUT_MODE[binary]))
         return outs
 
     # ------------------------------------------------------------------------------------------------ framewise branch
