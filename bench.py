@@ -160,7 +160,13 @@ def run_engine(args):
     n_obj, CPS = len(forced), CFG["clips"]
     host_clips = [synth_inputs(rank * CPS + j, pinned=True) for j in range(CPS)]       # CPS different clips per GPU and step
     res_clips = [[t.to(dev) for t in h] for h in host_clips]
-    raw_clips = [[h[0], h[1], synth_raw_frames(rank * CPS + j), h[3]] for j, h in enumerate(host_clips)]   # e2e arm: raw uint8 SAM2 frames
+    # e2e arm: ONLY the raw uint8 frames (+ prompt ids) cross PCIe: the SAM2 frames and the T_ENC encoder frames sampled from them; the IV2 / CLIP /
+    # SAM2 pre-processing runs on the GPU (preprocess.EncPreprocessGPU, SAM_v2_PreprocessGPU: the reference's cv2 / PIL / HF arithmetic)
+    raw_clips = []
+    for j, h in enumerate(host_clips):
+        raw_sam = synth_raw_frames(rank * CPS + j)
+        raw_enc = raw_sam[:: max(T_SAM // T_ENC, 1)][:T_ENC].contiguous().pin_memory()
+        raw_clips.append([raw_enc, raw_enc, raw_sam, h[3]])
     host, resident = host_clips[0], res_clips[0]
     L = host[3].shape[1] - T_ENC + 208 * T_ENC
 
@@ -292,7 +298,7 @@ def run_engine(args):
         tp, tall = prof["tensor_big"], prof["tensor"]
         ach = tp["flops"] / (tp["ms"] * 1e-3) / 1e12 if tp["ms"] > 0 else 0.0
         ach_all = tall["flops"] / (tall["ms"] * 1e-3) / 1e12 if tall["ms"] > 0 else 0.0
-        h2d = CPS * sum(t.numel() * t.element_size() for t in raw_clips[0])
+        h2d = CPS * sum(t.numel() * t.element_size() for t in raw_clips[0][1:])   # encoder frames (uploaded once for both towers) + SAM2 frames + ids
         h2d_fp32 = CPS * sum(t.numel() * t.element_size() for t in host)
         d2h = CPS * (T_SAM * n_obj * ((VIDEO_HW[0] * VIDEO_HW[1] + 7) // 8) + 8)     # bit-packed masks + the per-token id reads of the decode loop
         ms_clip = ms / (args.steps * CPS)
@@ -311,10 +317,11 @@ def run_engine(args):
                        **({"value_decode_batch_1": n_clips / (ms_db1 * 1e-3)} if ms_db1 else {}),
                        "latency_ms_single_clip": latency_ms},
             "e2e": {"value": n_clips / (ms_e2e * 1e-3), "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "passes_ms": ms_e2e_passes,
-                    "inputs": "pinned host tensors: IV2 / CLIP frames fp32 (CPU-preprocessed as the reference does), SAM2 frames RAW uint8 [T,H,W,3] pre-processed on "
-                              "the GPU (vg_resize_u8_pil + vg_sam_normalize_squash), prompt ids; outputs: bit-packed masks expanded to bool arrays on the host",
+                    "inputs": "pinned host tensors: the RAW uint8 video frames [T,H,W,3] (SAM2 frames + the encoder frames sampled from them) and the prompt ids; IV2 "
+                              "(cv2-bilinear 224 px), CLIP (PIL-bicubic + centre crop 336 px) and SAM2 (PIL-bilinear + squash 1024 px) pre-processing on the GPU, "
+                              "bit-exact resampling; outputs: bit-packed masks expanded to bool arrays on the host",
                     "with_fp32_sam_inputs": {"value": n_clips / (ms_e2e_fp32 * 1e-3), "h2d_bytes_per_step": h2d_fp32,
-                                             "note": "the reference's input format: SAM2 frames pre-processed on the CPU, uploaded as fp32 [T,3,1024,1024]"}},
+                                             "note": "the reference's input format: all three inputs pre-processed on the CPU, uploaded as fp32 (SAM2 [T,3,1024,1024])"}},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (every tensor-core GEMM launch of one clip with >= 1 GFLOP: "
                          f"{tp['n']} launches carrying {tp['flops'] / max(tall['flops'], 1):.1%} of the GEMM FLOPs)", "achieved": ach, "peak": tf_peak,

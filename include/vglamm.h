@@ -288,6 +288,18 @@ void vg_mask_decoder_set_timeline(void* dev_buf);
 int vg_resize_u8_pil(const unsigned char* src, unsigned char* tmp, unsigned char* dst, int n, int h, int w, int c, int oh, int ow, const int* kh, const int* bh,
                      int ksize_h, const int* kv, const int* bv, int ksize_v, void* stream);
 int vg_sam_normalize_squash(const unsigned char* src, float* dst, int n, int h, int w, int S, const float* mean3, const float* std3, void* stream);
+/* GPU pre-processing of the encoder inputs (EncPreprocessor_VideoGPTPlus.preprocess, VideoGLaMM/utils/enc_preprocessors.py:108-166):
+ * vg_resize_u8_cv: cv2.resize(x, (ow, oh)) = INTER_LINEAR on uint8 HWC frames, BIT-EXACT (VideoTrainProcessor.frames2tensor,
+ * model/videogpt_plus/model/internvideo/utils.py:120-131). xi / yi: int32 [ow] / [oh] left / upper source index, xc / yc: int32 [ow][2] / [oh][2]
+ * 11-bit coefficients (videoglamm_b200/preprocess.py:cv_linear_tables). The PIL BICUBIC resize of the CLIP branch is vg_resize_u8_pil with
+ * bicubic coefficient tables (preprocess.py:pil_coeffs).
+ * vg_u8_normalize_chw: src uint8 [n][h][w][3], crop [top, top+oh) x [left, left+ow) -> dst fp32 [n][3][oh][ow]. mode 0: float32(x * (1/255)), then
+ * (v - mean) / std in float32 (HF CLIPImageProcessor rescale + normalize); mode 1: (x / 255 - mean) / std in float64, rounded once
+ * (VideoTrainProcessor.normalize). mean3 / std3 are HOST pointers to 3 doubles. */
+int vg_resize_u8_cv(const unsigned char* src, unsigned char* dst, int n, int h, int w, int c, int oh, int ow, const int* xi, const int* xc, const int* yi,
+                    const int* yc, void* stream);
+int vg_u8_normalize_chw(const unsigned char* src, float* dst, int n, int h, int w, int oh, int ow, int top, int left, int mode, const double* mean3,
+                        const double* std3, void* stream);
 /* argmax over each row of a [rows][cols] fp32/bf16 matrix -> int64 index (first maximal index, like torch.argmax) */
 int vg_argmax(const void* x, int x_dtype, long long ldx, long long* out, int rows, int cols, void* stream);
 

@@ -80,3 +80,28 @@ def test_pil_bilinear_restatement_is_bit_exact(H_, W_, oh, ow):
     ref = np.array(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
     assert np.array_equal(P.pil_bilinear_resize_numpy(img, oh, ow), ref)
     assert (oh, ow) == P.get_preprocess_shape(H_, W_, 1024) or (H_, W_) == (1500, 1100)
+
+
+@pytest.mark.parametrize("H_,W_", [(336, 336), (480, 854), (720, 1280), (100, 60), (448, 448), (37, 53), (1080, 1920)])
+def test_encoder_preprocessing_restatements_are_bit_exact(H_, W_):
+    """What EncPreprocessGPU executes, restated in numpy and pinned against the libraries the reference calls (utils/enc_preprocessors.py:108-166):
+    cv2.resize INTER_LINEAR (IV2 frames, internvideo/utils.py:120-131) and PIL BICUBIC shortest-edge resize (HF CLIPImageProcessor), bit for bit,
+    down- and up-scaling incl. the exact 2x case."""
+    import cv2
+    from PIL import Image
+    img = np.random.default_rng(H_ * 3 + W_).integers(0, 256, (H_, W_, 3), dtype=np.uint8)
+    assert np.array_equal(P.cv_resize_linear_numpy(img, 224, 224), cv2.resize(img, (224, 224)))
+    ch, cw = P.clip_resize_shape(H_, W_, 336)
+    assert min(ch, cw) == 336
+    ref = np.array(Image.fromarray(img).resize((cw, ch), Image.BICUBIC))
+    assert np.array_equal(P.pil_resize_numpy(img, ch, cw, "bicubic"), ref)
+    # the whole CLIP branch against the HF processor (resize -> centre crop -> rescale -> normalize)
+    want = P.clip_image_processor().preprocess(Image.fromarray(img), return_tensors="pt")["pixel_values"][0].numpy()
+    r = P.pil_resize_numpy(img, ch, cw, "bicubic") if (ch, cw) != (H_, W_) else img
+    top, left = (ch - 336) // 2, (cw - 336) // 2
+    v = (r[top:top + 336, left:left + 336].astype(np.float64) * (1 / 255)).astype(np.float32)
+    got = ((v - np.array(P.CLIP_MEAN, np.float32)) / np.array(P.CLIP_STD, np.float32)).transpose(2, 0, 1)
+    # transformers 4.41 (pinned by the reference) resizes through PIL — the arithmetic restated above; the installed 5.x processor resizes through
+    # torchvision and lands one (two when up-scaling) 8-bit levels away on a few percent of the pixels at most: everything else agrees to float32 rounding
+    d = np.abs(want - got)
+    assert want.shape == got.shape == (3, 336, 336) and d.max() < 2.02 / 255 / min(P.CLIP_STD) and (d > 2e-6).mean() < 0.05

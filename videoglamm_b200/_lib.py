@@ -75,7 +75,7 @@ SYMBOLS = [
     "vg_rope2d", "vg_rope2d_table", "vg_rope2d_cached", "vg_rope_neox", "vg_embedding", "vg_argmax", "vg_row_scatter", "vg_launch_count_add", "vg_rope_kv_append", "vg_multimask_select",
     "vg_connected_components", "vg_im2col3x3s2_cl", "vg_layernorm_gelu", "vg_split3", "vg_attention_f32",
     "vg_mask_decoder", "vg_mask_decoder_workspace_bytes", "vg_mask_decoder_set_timeline",
-    "vg_resize_u8_pil", "vg_sam_normalize_squash", "vg_sum_parts",
+    "vg_resize_u8_pil", "vg_sam_normalize_squash", "vg_resize_u8_cv", "vg_u8_normalize_chw", "vg_sum_parts",
 ]
 
 

@@ -299,8 +299,8 @@ class VideoGLaMMForCausalLM:
                 sam_in = sam_in.to(dev, non_blocking=True)
                 copy_done = torch.cuda.Event()
                 copy_done.record(self._copy_stream)
-        out_ids, emb = self.lmm.generate(input_ids.to(dev), images[0].to(dev, torch.float32), None if ctx is None else ctx.to(dev, torch.float32),
-                                         max_new_tokens, eos_ids=self._eos_ids(), forced=forced_tokens)
+        enc_images, enc_ctx = self.encoder_inputs(images[0], ctx)
+        out_ids, emb = self.lmm.generate(input_ids.to(dev), enc_images, enc_ctx, max_new_tokens, eos_ids=self._eos_ids(), forced=forced_tokens)
         if emb.shape[0] == 0:
             return (out_ids, [{}], None) if return_logits else (out_ids, [{}])       # VideoGLaMM.py:840-842
         H, W = original_size_list[0]
@@ -318,6 +318,19 @@ class VideoGLaMMForCausalLM:
         frames = run(sam_in.to(dev), emb[:, None, :], (int(H), int(W)), binary="packed")
         segs, self.last_packed = self.masks_to_host(frames, int(H), int(W))
         return out_ids, [segs]
+
+    def encoder_inputs(self, images: torch.Tensor, ctx: torch.Tensor | None):
+        """(IV2 frames, CLIP context images) on the device as fp32. `images` may be the RAW uint8 frames [T,H,W,3] (with `ctx` the same tensor or None):
+        they are then pre-processed on the GPU (preprocess.EncPreprocessGPU: cv2-bilinear 224 px + PIL-bicubic / centre-crop 336 px, the
+        reference's EncPreprocessor_VideoGPTPlus arithmetic) — H*W*3 bytes per frame over PCIe instead of 1.9 MB of fp32."""
+        dev = self.device
+        if images.dtype == torch.uint8:
+            assert images.dim() == 4 and images.shape[3] == 3 and (ctx is None or ctx.dtype == torch.uint8), "uint8 images must be raw frames [T,H,W,3]"
+            if not hasattr(self, "_enc_pre_gpu"):
+                from ..preprocess import EncPreprocessGPU
+                self._enc_pre_gpu = EncPreprocessGPU(dev, self.lmm.cfg.iv2.image_size, self.lmm.cfg.clip.image_size)
+            return self._enc_pre_gpu.preprocess_video(images)
+        return images.to(dev, torch.float32, non_blocking=True), None if ctx is None else ctx.to(dev, torch.float32, non_blocking=True)
 
     def sam_preprocessor_gpu(self):
         if not hasattr(self, "_sam_pre_gpu"):

@@ -523,6 +523,29 @@ def sam_normalize_squash(frames: torch.Tensor, S: int, mean: tuple, std: tuple) 
     return out
 
 
+def resize_u8_cv(frames: torch.Tensor, oh: int, ow: int, tables: tuple) -> torch.Tensor:
+    """cv2.resize(x, (ow, oh)) (INTER_LINEAR, bit-exact) on uint8 [n,h,w,c] cuda frames; tables = (xi, xc, yi, yc) from preprocess.cv_linear_tables."""
+    _require_cuda(frames, *tables)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4
+    xi, xc, yi, yc = tables
+    assert all(t.dtype == torch.int32 and t.is_contiguous() for t in tables) and xi.numel() == ow and yi.numel() == oh
+    n, h, w, c = frames.shape
+    out = torch.empty((n, oh, ow, c), device=frames.device, dtype=torch.uint8)
+    L.check(L.lib().vg_resize_u8_cv(_ptr(frames), _ptr(out), n, h, w, c, oh, ow, _ptr(xi), _ptr(xc), _ptr(yi), _ptr(yc), _stream()), "vg_resize_u8_cv")
+    return out
+
+
+def u8_normalize_chw(frames: torch.Tensor, oh: int, ow: int, top: int, left: int, mean: tuple, std: tuple, mode: int) -> torch.Tensor:
+    """uint8 [n,h,w,3] cuda, crop [top, top+oh) x [left, left+ow) -> fp32 [n,3,oh,ow]; mode 0: HF rescale + normalize (float32), mode 1: (x/255 - mean)/std in float64."""
+    _require_cuda(frames)
+    assert frames.dtype == torch.uint8 and frames.is_contiguous() and frames.dim() == 4 and frames.shape[3] == 3
+    n, h, w, _ = frames.shape
+    out = torch.empty((n, 3, oh, ow), device=frames.device, dtype=torch.float32)
+    m3, s3 = (C.c_double * 3)(*mean), (C.c_double * 3)(*std)
+    L.check(L.lib().vg_u8_normalize_chw(_ptr(frames), _ptr(out), n, h, w, oh, ow, top, left, mode, m3, s3, _stream()), "vg_u8_normalize_chw")
+    return out
+
+
 def gemm_ksplit(a: torch.Tensor, w: torch.Tensor, nparts: int, *, resid: torch.Tensor | None = None, out: torch.Tensor | None = None,
                 block_n: int = 64) -> torch.Tensor:
     """Skinny projection out = a @ w^T (+ resid) with FEW output columns (a bf16 [M <= 8, K], w bf16 [N, K]) as `nparts` batched tensor-core GEMMs over

@@ -58,9 +58,8 @@ class ClipPipeline:
                                     ev_copy = torch.cuda.Event()
                                     ev_copy.record(self.s_copy)
                             sams.append((sam_dev, ev_copy))
-                            ctx = c.get("context_images")
-                            reqs.append((c["input_ids"].to(dev, non_blocking=True), c["images"].to(dev, torch.float32, non_blocking=True),
-                                         None if ctx is None else ctx.to(dev, torch.float32, non_blocking=True)))
+                            enc_images, enc_ctx = m.encoder_inputs(c["images"], c.get("context_images"))   # fp32 tensors, or raw uint8 frames -> GPU pre-processing
+                            reqs.append((c["input_ids"].to(dev, non_blocking=True), enc_images, enc_ctx))
                         self._mark("lmm0", i0, self.s_lmm)
                         outs = m.lmm.generate_batch(reqs, max_new_tokens, eos_ids=m._eos_ids(), forced=forced_tokens)
                         self._mark("lmm1", i0, self.s_lmm)

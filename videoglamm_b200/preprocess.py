@@ -76,14 +76,26 @@ class SAM_v2_Preprocess:
         return sam_preprocess(x)
 
 
-def pil_bilinear_coeffs(in_size: int, out_size: int) -> tuple[np.ndarray, np.ndarray]:
-    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c) for the BILINEAR filter (support 1, scaled by the
-    down-sampling factor): int32 coefficients [out, ksize] with 22 fractional bits and bounds [out, 2] = (first input index, tap count).
-    Evaluated in float64 exactly as Pillow does, so vg_resize_u8_pil reproduces Image.resize bit for bit (tests/test_preprocess_cpu.py)."""
+def _pil_filter(name: str):
+    """Pillow's resampling kernels (src/libImaging/Resample.c): (function on |x| arrays, support)."""
+    if name == "bilinear":
+        return (lambda a: np.where(a < 1.0, 1.0 - a, 0.0)), 1.0
+    if name == "bicubic":                                        # a = -0.5
+        def f(a, A=-0.5):
+            return np.where(a < 1.0, ((A + 2.0) * a - (A + 3.0)) * a * a + 1.0, np.where(a < 2.0, (((a - 5.0) * a + 8.0) * a - 4.0) * A, 0.0))
+        return f, 2.0
+    raise ValueError(name)
+
+
+def pil_coeffs(in_size: int, out_size: int, filt: str = "bilinear") -> tuple[np.ndarray, np.ndarray]:
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c) for the BILINEAR (support 1) or BICUBIC (support 2, a = -0.5)
+    filter, support scaled by the down-sampling factor: int32 coefficients [out, ksize] with 22 fractional bits and bounds [out, 2] = (first input
+    index, tap count). Evaluated in float64 exactly as Pillow does, so vg_resize_u8_pil reproduces Image.resize bit for bit (tests/test_preprocess_cpu.py)."""
     import math
+    fn, sup = _pil_filter(filt)
     scale = in_size / out_size
     fs = max(scale, 1.0)
-    support = 1.0 * fs
+    support = sup * fs
     ksize = int(math.ceil(support)) * 2 + 1
     kk = np.zeros((out_size, ksize), dtype=np.float64)
     bounds = np.zeros((out_size, 2), dtype=np.int32)
@@ -92,8 +104,7 @@ def pil_bilinear_coeffs(in_size: int, out_size: int) -> tuple[np.ndarray, np.nda
         center = (xx + 0.5) * scale
         xmin = max(int(center - support + 0.5), 0)
         xmax = min(int(center + support + 0.5), in_size) - xmin
-        a = np.abs((np.arange(xmax) + xmin - center + 0.5) * inv)
-        w = np.where(a < 1.0, 1.0 - a, 0.0)
+        w = fn(np.abs((np.arange(xmax) + xmin - center + 0.5) * inv))
         ww = w.sum()
         kk[xx, :xmax] = w / ww if ww != 0 else w
         bounds[xx] = (xmin, xmax)
@@ -101,22 +112,113 @@ def pil_bilinear_coeffs(in_size: int, out_size: int) -> tuple[np.ndarray, np.nda
     return ki, bounds
 
 
-def pil_bilinear_resize_numpy(img: np.ndarray, oh: int, ow: int) -> np.ndarray:
-    """Host restatement of Pillow's 8-bit two-pass bilinear resampling (the arithmetic vg_resize_u8_pil executes); used by the CPU tests."""
+def pil_bilinear_coeffs(in_size: int, out_size: int) -> tuple[np.ndarray, np.ndarray]:
+    return pil_coeffs(in_size, out_size, "bilinear")
+
+
+def pil_resize_numpy(img: np.ndarray, oh: int, ow: int, filt: str = "bilinear") -> np.ndarray:
+    """Host restatement of Pillow's 8-bit two-pass resampling (the arithmetic vg_resize_u8_pil executes); used by the CPU tests."""
     H, W, C = img.shape
-    kh, bh = pil_bilinear_coeffs(W, ow)
+    kh, bh = pil_coeffs(W, ow, filt)
     tmp = np.zeros((H, ow, C), np.uint8)
     for x in range(ow):
         lo, n = bh[x]
         acc = (1 << 21) + (img[:, lo:lo + n, :].astype(np.int64) * kh[x, :n][None, :, None]).sum(1)
         tmp[:, x] = np.clip(acc >> 22, 0, 255)
-    kv, bv = pil_bilinear_coeffs(H, oh)
+    kv, bv = pil_coeffs(H, oh, filt)
     out = np.zeros((oh, ow, C), np.uint8)
     for y in range(oh):
         lo, n = bv[y]
         acc = (1 << 21) + (tmp[lo:lo + n].astype(np.int64) * kv[y, :n][:, None, None]).sum(0)
         out[y] = np.clip(acc >> 22, 0, 255)
     return out
+
+
+def pil_bilinear_resize_numpy(img: np.ndarray, oh: int, ow: int) -> np.ndarray:
+    return pil_resize_numpy(img, oh, ow, "bilinear")
+
+
+def cv_linear_tables(in_size: int, out_size: int, vertical: bool) -> tuple[np.ndarray, np.ndarray]:
+    """OpenCV `cv::resize(..., INTER_LINEAR)` on 8-bit images (modules/imgproc/src/resize.cpp): per output index the left source index and the two
+    11-bit fixed-point coefficients (INTER_RESIZE_COEF_BITS). Horizontally the index is clamped and the fraction reset at both borders;
+    vertically the fraction is kept and the two ROW indices are clipped instead (so a border row is a two-term sum of the same row)."""
+    scale = in_size / out_size
+    idx, coef = np.zeros(out_size, np.int32), np.zeros((out_size, 2), np.int32)
+    for d in range(out_size):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - s)
+        if not vertical:
+            if s < 0:
+                s, f = 0, np.float32(0)
+            if s >= in_size - 1:
+                s, f = in_size - 1, np.float32(0)
+        idx[d] = s
+        coef[d] = (int(np.rint(np.float32((np.float32(1.0) - f) * 2048))), int(np.rint(np.float32(f * 2048))))
+    return idx, coef
+
+
+def cv_resize_linear_numpy(img: np.ndarray, oh: int, ow: int) -> np.ndarray:
+    """Host restatement of cv2.resize(img, (ow, oh)) for uint8 HWC images, bit for bit (tests/test_preprocess_cpu.py): the arithmetic of vg_resize_u8_cv."""
+    H, W, _ = img.shape
+    xi, xc = cv_linear_tables(W, ow, False)
+    yi, yc = cv_linear_tables(H, oh, True)
+    x1 = np.minimum(xi + 1, W - 1)
+    rows = img[:, xi, :].astype(np.int64) * xc[:, 0][None, :, None] + img[:, x1, :].astype(np.int64) * xc[:, 1][None, :, None]
+    y0, y1 = np.clip(yi, 0, H - 1), np.clip(yi + 1, 0, H - 1)
+    b0, b1 = yc[:, 0][:, None, None], yc[:, 1][:, None, None]
+    out = (((b0 * (rows[y0] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def clip_resize_shape(h: int, w: int, size: int = 336) -> tuple[int, int]:
+    """HF get_resize_output_image_size for {"shortest_edge": size}: the short side becomes `size`, the long side int(size * long / short)."""
+    short, long = (h, w) if h <= w else (w, h)
+    new_short, new_long = size, int(size * long / short)
+    return (new_short, new_long) if h <= w else (new_long, new_short)
+
+
+class EncPreprocessGPU:
+    """EncPreprocessor_VideoGPTPlus.preprocess (utils/enc_preprocessors.py:108-166) for a whole clip ON THE GPU from the raw
+    uint8 frames [T,H,W,3]:
+      IV2 frames    cv2.resize(x, (224, 224)) (INTER_LINEAR, 11-bit fixed point, bit-exact) -> (x / 255 - mean) / std in float64 -> fp32 [T,3,224,224]
+      CLIP context  PIL BICUBIC resize of the short side to 336 (Pillow's two-pass fixed-point resampling, bit-exact) -> centre crop 336x336 ->
+                    float32(x * (1/255)) -> (v - mean) / std in float32 (HF CLIPImageProcessor's arithmetic) -> fp32 [T,3,336,336]
+    Frame trimming / padding to NUM_FRAMES stays with the caller (it is list bookkeeping)."""
+
+    def __init__(self, device="cuda", iv2_size: int = 224, clip_size: int = 336):
+        self.device, self.iv2_size, self.clip_size, self._tables = torch.device(device), iv2_size, clip_size, {}
+
+    def tables(self, h: int, w: int):
+        key = (h, w)
+        if key not in self._tables:
+            if len(self._tables) > 32:
+                self._tables.clear()
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            xi, xc = cv_linear_tables(w, self.iv2_size, False)
+            yi, yc = cv_linear_tables(h, self.iv2_size, True)
+            ch, cw = clip_resize_shape(h, w, self.clip_size)
+            pil = None
+            if (ch, cw) != (h, w):                      # PIL returns a copy when the size does not change
+                kh, bh = pil_coeffs(w, cw, "bicubic")
+                kv, bv = pil_coeffs(h, ch, "bicubic")
+                pil = tuple(dev(a) for a in (kh, bh, kv, bv))
+            self._tables[key] = (tuple(dev(a) for a in (xi, xc, yi, yc)), (ch, cw), pil)
+        return self._tables[key]
+
+    def preprocess_video(self, frames) -> tuple[torch.Tensor, torch.Tensor]:
+        """frames: uint8 [T,H,W,3] (numpy, or a torch tensor on the host / device) -> (images fp32 [T,3,224,224], context_images fp32 [T,3,336,336])."""
+        from . import ops
+        t = torch.from_numpy(np.ascontiguousarray(frames)) if isinstance(frames, np.ndarray) else frames
+        assert t.dtype == torch.uint8 and t.dim() == 4 and t.shape[3] == 3
+        t = t.to(self.device, non_blocking=True).contiguous()
+        cv_tabs, (ch, cw), pil = self.tables(t.shape[1], t.shape[2])
+        small = ops.resize_u8_cv(t, self.iv2_size, self.iv2_size, cv_tabs)
+        images = ops.u8_normalize_chw(small, self.iv2_size, self.iv2_size, 0, 0, tuple(IMAGENET_MEAN.flatten().tolist()), tuple(IMAGENET_STD.flatten().tolist()), mode=1)
+        r = t if pil is None else ops.resize_u8_pil(t, ch, cw, pil)
+        S = self.clip_size
+        context = ops.u8_normalize_chw(r, S, S, (ch - S) // 2, (cw - S) // 2, tuple(CLIP_MEAN), tuple(CLIP_STD), mode=0)
+        return images, context
 
 
 class SAM_v2_PreprocessGPU:
