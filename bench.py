@@ -185,7 +185,8 @@ def run_engine(args):
     # the HBM-bound decode loops of up to DB = 8 queued clips run as ONE batched loop (one weight pass per token for all of them): two C3 steps of 4
     # clips; for the 1-clip-per-step configs, DB consecutive clips of the stream (throughput serving; --decode-batch 1 turns it off). Measured
     # DB = 4 -> 8: C2 13.0 -> 13.1, C3 6.2 -> 7.2, C5 2.61 -> 2.66 clips/s
-    DB = max(CPS, min(int(args.decode_batch), 8))
+    db_req = int(args.decode_batch) if args.decode_batch else (args.steps * CPS + 1) // 2     # auto: at least two groups, so that LMM and SAM2 stages overlap
+    DB = max(CPS, min(db_req, 8))
     pipe = ClipPipeline(model, decode_batch=DB)
     pipe1 = ClipPipeline(model, decode_batch=CPS) if DB != CPS else None
 
@@ -576,7 +577,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--decode-batch", type=int, default=8, help="decode loops of this many queued clips run as one batched loop (>= clips per step)")
+    ap.add_argument("--decode-batch", type=int, default=0,
+                    help="decode loops of this many queued clips run as one batched loop (>= clips per step, <= 8); 0 = auto: min(8, half the clips of the run)")
     ap.add_argument("--sequential", action="store_true", help="one clip at a time (latency mode); default overlaps consecutive clips")
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json configs[N-1]: 2 (headline, default), 3, 4, 5")
     a = ap.parse_args()
