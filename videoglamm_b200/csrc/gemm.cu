@@ -884,13 +884,18 @@ extern "C" int vg_gemm(const VgGemm* g, void* stream) {
   if (bn == 256 && g->force_block_n == 0) {
     // N not a multiple of 256 (Hiera widths are multiples of 144): 192- or 96-column tiles waste fewer MMA columns. Cost model: waves x
     // (tile columns + a fixed per-tile overhead of ~32 columns); ties keep the wider tile (fewer A re-reads from shared memory).
+    // Measured exceptions (profiles/r02_gemm_bn_sweep.md): in the epilogue-bound small-K regime a 256-wide tile beats 192 whenever it wastes
+    // <= 12 % of its columns and the problem is several waves deep (131072x1152x288 GELU: 165 vs 183 us; 32768x1728x576: 61 vs 66 us).
     const long long tm = (g->M + BLOCK_M - 1) / BLOCK_M;
+    const long long n256 = (g->N + 255) / 256;
+    const bool keep256 = g->K <= 576 && n256 * 256 * 100 <= static_cast<long long>(g->N) * 112 && tm * n256 * g->batch >= 4LL * num_sms();
     double best = 1e30;
     for (int cand : {256, 192, 96}) {
+      if (keep256 && cand != 256) continue;
       if (cand == 96 && (g->N % 96 != 0 || g->N % 128 == 0)) continue;
       const long long tiles = tm * ((g->N + cand - 1) / cand) * g->batch;
       const double cost = static_cast<double>((tiles + num_sms() - 1) / num_sms()) * (cand + 32);
-      if (cost < best * 0.97) {
+      if (cost < best) {   // strictly cheaper (131072x864x288: 192 at 7840 vs 256 at 8064 measures 101 vs 109 us)
         best = cost;
         bn = cand;
       }
