@@ -214,6 +214,9 @@ def test_add_pool_upsample():
     b = torch.randn(3, 40, device=DEV).bfloat16()
     assert rel(ops.add(a, b, alpha=0.1), a + 0.1 * b.float().repeat(4, 1)) < 1e-6
     assert ops.cast(a, torch.bfloat16).dtype == torch.bfloat16
+    a4, p4 = torch.randn(6 * 50, 144, device=DEV), torch.randn(50, 144, device=DEV)       # fp32 + row-broadcast fp32: 16-byte vector path
+    assert torch.equal(ops.add(a4, p4), (a4.view(6, 50, 144) + p4).view(-1, 144))
+    assert rel(ops.add(p4, a4[:50], alpha=0.1, rows=150), (p4 + 0.1 * a4[:50]).repeat(3, 1)) < 1e-7
     x = torch.randn(2 * 8 * 6, 3 * 16, device=DEV).bfloat16()
     q = x[:, :16]
     ref = F.max_pool2d(q.float().reshape(2, 8, 6, 16).permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).reshape(-1, 16)
